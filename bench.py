@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 Fractional-ICP hot path (BASELINE.json metric: hypothesis-iterations/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+Workload (config 3 of BASELINE.json, "synthetic stand"): 500 trees vs 1e6 CHM points, 4096 start-pose
+hypotheses (128 rotations x 2 flips x 4x4 translations at 2.5 m), XYZ matching; `--plots-per-gpu` such
+plots per GPU (weak scaling: the hypotheses of every plot are dealt round-robin to the ranks, so each
+GPU always runs plots_per_gpu * 4096 ICPs; the exchange step is the NCCL all-reduce(MIN) of the packed
+best keys).  A "step" = every one of those ICPs run to convergence (two stages) against the resident
+target grid + the best-of-hypotheses reduction.  One unit = one hypothesis-iteration = one NN pass of
+one hypothesis (`find_correspondences` call in the reference, ficp.py:123,137).
+
+value   device-timed (CUDA events on the launching stream), inputs resident in HBM.
+e2e     the same metric through the public host-array API (`register_batch[_distributed]`): target +
+        plots + hypotheses copied from pinned host memory, grid build, kernel, results read back, all
+        inside the timed region (wall clock around synchronised calls).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_QUERY = 312.0      # 18 candidate records x 16 B + 3 row-range lookups x 8 B
+GRID_BYTES_PER_POINT = 48.0      # grid build traffic per target point
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--trees", type=int, default=500)
+    ap.add_argument("--dims", type=int, default=3, choices=[2, 3])
+    ap.add_argument("--plots-per-gpu", type=int, default=8)
+    ap.add_argument("--rotations", type=int, default=128)
+    ap.add_argument("--tside", type=int, default=4, help="translation lattice side (tside^2 translations)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the CPU baseline sample (0 = one per core, <= 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload(args, n_plots):
+    from oracle import ficp_oracle as orc      # scene generator only (synthetic data), not the timed path
+    tgt, plots, _ = orc.synthetic_scene(args.points, args.trees, seed=3, dims=args.dims, n_plots=n_plots,
+                                        hidden_pose=True)
+    hyp = orc.hypothesis_table(args.rotations, flips=(0, 1), translations=orc.translation_lattice(args.tside, 2.5))
+    name = (f"C3 synthetic stand: {args.trees} trees vs {args.points} CHM points, {hyp.shape[0]} hypotheses "
+            f"({args.rotations} rot x 2 flips x {args.tside}x{args.tside} translations), {'XYZ' if args.dims == 3 else 'XY'} matching")
+    return tgt, plots, hyp, name
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def _cpu_one(job):
+    """One hypothesis through the reference algorithm as shipped: kd-tree rebuilt on every pass, O(N^2)
+    FRMSD loop (oracle port of ficp.py:122-154)."""
+    from oracle import ficp_oracle as orc
+    src, tgt, row, centre, hoist = job
+    tr = orc.RunTrace()
+    s0 = orc.pre_transform(src, row, centre)
+    if hoist:
+        orc.ficp_run(s0, tgt, nn="tree", hoist_tree=True, trace=tr, closed_form=True)
+    else:
+        orc.ficp_run(s0, tgt, nn="reference", hoist_tree=False, trace=tr, pairwise=True)
+    return tr.passes
+
+
+_POOL = None
+
+
+def cpu_step(src, tgt, hyp, n_sample, procs, hoist=False):
+    """Runs `n_sample` strided hypotheses of one plot on `procs` processes; returns (passes, seconds)."""
+    global _POOL
+    import multiprocessing as mp
+    if _POOL is None or _POOL[1] != procs:
+        if _POOL is not None:
+            _POOL[0].terminate()
+        _POOL = (mp.get_context("fork").Pool(procs), procs)
+    centre = src[:, :2].mean(axis=0)
+    ids = np.linspace(0, hyp.shape[0] - 1, n_sample).astype(int)
+    jobs = [(src, tgt, hyp[h], centre, hoist) for h in ids]
+    t0 = time.perf_counter()
+    passes = _POOL[0].map(_cpu_one, jobs, chunksize=1)
+    return int(sum(passes)), time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tgt, plots, hyp, name = workload(args, 1)
+    procs = max(1, min(host_threads(), 32))
+    n_sample = args.cpu_sample or procs
+    for _ in range(args.warmup):
+        cpu_step(plots[0], tgt, hyp, min(n_sample, procs), procs)
+    tot_p, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        p, t = cpu_step(plots[0], tgt, hyp, n_sample, procs)
+        tot_p += p
+        tot_t += t
+    val = tot_p / tot_t
+    sample = f"{n_sample} strided hypotheses of one plot per step on {procs} processes (kd-tree rebuilt every pass, as shipped)"
+    line = {"impl": "reference", "metric": "FICP hypothesis-iterations/sec", "value": val, "unit": "hyp-iter/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "sample": sample},
+            "nn_queries_per_s": val * args.trees,
+            "cpu_baseline": {"value": val, "unit": "hyp-iter/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "hyp-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, n): n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+                 for n in dir(nv) if n.startswith("nvmlClocksThrottleReason") or n.startswith("nvmlClocksEventReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and bin(bit).count("1") == 1:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        keep = [r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting")]
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(keep),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from coregistrationgame_b200 import IcpBatch, TargetIndex, _lib, register_batch
+    from coregistrationgame_b200.dist import reduce_best, register_batch_distributed, shard_of
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.require_device()
+    _lib.check(_lib.load().ficp_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n_plots = args.plots_per_gpu * world
+    tgt, plots, hyp, name = workload(args, n_plots)
+    props = _lib.device_props()
+
+    # ---- resident inputs
+    index = TargetIndex(tgt)
+    tinfo = index.info()
+    batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), warps_per_cta=args.warps,
+                     ctas_per_sm=args.ctas_per_sm)
+    keys = torch.empty(n_plots, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step(evk=None):
+        batch.run(stream)
+        if evk is not None:
+            evk.record(stream)
+        batch.copy_best_keys_to(keys.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    passes_per_step = batch.results(stream, per_hypothesis=False)["stats"]["passes"]
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                           # evict L2 between timed iterations
+        e0, ek, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        step(ek)
+        e1.record(stream)
+        evs.append((e0, ek, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    step_ms = sum(a.elapsed_time(c) for a, _, c in evs)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
+    stats = batch.results(stream, per_hypothesis=False)["stats"]
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    units = torch.tensor([float(stats["passes"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    passes_all = float(units.item())             # all ranks, one step
+    value = passes_all * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API, host (pinned) buffers in, results out
+    def pinned(a):
+        tbuf = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        tbuf.numpy()[...] = a
+        return tbuf.numpy()
+    h_tgt, h_plots, h_hyp = pinned(tgt), [pinned(p) for p in plots], pinned(hyp)
+    e2e_steps = args.e2e_steps or args.steps
+
+    def e2e_step():
+        if world > 1:
+            return register_batch_distributed(h_plots, h_tgt, h_hyp, warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm)
+        r = register_batch(h_plots, h_tgt, h_hyp, warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm)
+        r["passes_global"] = r["stats"]["passes"]
+        return r
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_passes = 0
+    for _ in range(e2e_steps):
+        r = e2e_step()
+        e2e_passes += r["passes_global"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_passes / float(e2e_s.item())
+    h2d, d2h = r["h2d_bytes"], r["d2h_bytes"]
+
+    # ---- standalone kernels (reported, not the headline): bulk NN query and grid build
+    extra = {}
+    if rank == 0:
+        nq = 1 << 22
+        rng = np.random.default_rng(1)
+        bb = tinfo["bbox"]
+        q = np.empty((nq, args.dims))
+        q[:, 0] = rng.uniform(bb[0], bb[1], nq)
+        q[:, 1] = rng.uniform(bb[2], bb[3], nq)
+        if args.dims == 3:
+            q[:, 2] = rng.uniform(5, 35, nq)
+        dq = torch.from_numpy(q).to(dev)
+        didx = torch.empty(nq, dtype=torch.int32, device=dev)
+        ddist = torch.empty(nq, dtype=torch.float64, device=dev)
+        lib = _lib.load()
+        import ctypes as C
+        sp = C.c_void_p(stream.cuda_stream)
+        for _ in range(2):
+            _lib.check(lib.ficp_nn_query_device(index.handle, C.c_void_p(dq.data_ptr()), nq, args.dims, int(args.dims == 3),
+                                                C.c_void_p(didx.data_ptr()), C.c_void_p(ddist.data_ptr()), sp))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1)
+        a.record(stream)
+        _lib.check(lib.ficp_nn_query_device(index.handle, C.c_void_p(dq.data_ptr()), nq, args.dims, int(args.dims == 3),
+                                            C.c_void_p(didx.data_ptr()), C.c_void_p(ddist.data_ptr()), sp))
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        extra["nn_query_kernel"] = {"queries": nq, "ms": ms, "queries_per_s": nq / (ms * 1e-3),
+                                    "alg_GBps_L2_level": nq * ALG_BYTES_PER_QUERY / (ms * 1e-3) / 1e9}
+        extra["grid_build"] = {"points": int(tinfo["m"]), "ms": tinfo["build_ms"],
+                               "alg_GBps": tinfo["m"] * GRID_BYTES_PER_POINT / (tinfo["build_ms"] * 1e-3) / 1e9,
+                               "grid": [tinfo["grid_w"], tinfo["grid_h"]], "cell_m": tinfo["cell"]}
+
+    # ---- roofline of the dominant kernel (the persistent ICP kernel)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = passes_per_step * args.trees * ALG_BYTES_PER_QUERY          # this rank, one launch
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("icp_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "icp_kernel (persistent two-stage FICP)", "kernel_ms": kern_ms,
+                "peak_source": peak_src,
+                "note": ("algorithmic bytes = hypothesis-iterations x trees x 312 B (SURVEY 8d, as if every candidate "
+                         "record came from memory); the kernel serves them from a shared-memory window / L1 / L2, so "
+                         "frac is NOT an HBM utilisation and can exceed 1 - see DESIGN.md for the on-chip bound")}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = max(1, min(host_threads(), 32))
+        n_sample = args.cpu_sample or procs
+        p_asis, t_asis = cpu_step(plots[0], tgt, hyp, n_sample, procs, hoist=False)
+        p_h, t_h = cpu_step(plots[0], tgt, hyp, n_sample, procs, hoist=True)
+        sample = f"{n_sample} strided hypotheses of plot 0 on {procs} processes"
+        cpu_baseline = {"value": p_asis / t_asis, "unit": "hyp-iter/s", "cores": procs, "kind": "port",
+                        "sample": sample + " (reference algorithm as shipped: kd-tree rebuilt every pass, O(N^2) FRMSD loop)",
+                        "seconds": t_asis,
+                        "index_hoisted": {"value": p_h / t_h, "unit": "hyp-iter/s", "seconds": t_h,
+                                          "sample": sample + " (kd-tree built once, cumsum FRMSD)"}}
+
+    if rank == 0:
+        line = {"metric": "FICP hypothesis-iterations/sec", "value": value, "unit": "hyp-iter/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "plots_per_gpu": args.plots_per_gpu, "plots": n_plots,
+                           "icps_per_gpu_per_step": args.plots_per_gpu * hyp.shape[0],
+                           "hyp_iterations_per_step": passes_all, "parallelism": f"hypotheses round-robin over {world} GPU(s)",
+                           "l2": "flushed between timed steps (256 MB write)", "launch": batch.info,
+                           "device": props},
+                "nn_queries_per_s": value * args.trees,
+                "e2e": {"value": e2e_val, "unit": "hyp-iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "api": "register_batch_distributed" if world > 1 else "register_batch"},
+                "gpu_launches": args.steps,
+                "roofline": roofline, "clocks": sampler.summary(),
+                "path_stats": stats}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        line.update(extra)
+        print(json.dumps(line))
+    batch.close()
+    index.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,278 @@
+"""Host side of the batched Fractional-ICP search (extension over the reference API).
+
+The reference runs one plot from one start pose per call (``app.py:630-661``).  This module
+batches ``FractionalICP(pre_transform(src, h), tgt).run()`` over many plots and many start-pose
+hypotheses ``h`` (rotation grid x flip x coarse translation, with the semantics of
+``trees.py:165-222``) and picks the best registration per plot.  All arithmetic happens in the
+CUDA kernels behind ``libficp_b200.so``; this file only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+
+STAGE2_LAMBDA = {2: 1.3, 3: 0.95}  # ficp.py:152
+
+
+# --------------------------------------------------------------------------- hypothesis tables
+def hypothesis_matrix(theta_deg, flip):
+    """2x2 linear part of a start pose: y-flip (optional) then CCW rotation, both about the plot
+    centre - ``Plot.coordinate_flip`` / ``Plot.rotate_plot`` (trees.py:165-222)."""
+    th = np.radians(theta_deg)
+    c, s = np.cos(th), np.sin(th)
+    if flip:
+        return np.array([[c, s], [s, -c]])
+    return np.array([[c, -s], [s, c]])
+
+
+def hypothesis_table(n_rot, flips=(0, 1), translations=((0.0, 0.0),)):
+    """(H, 6) float64 rows ``[m00 m01 m10 m11 dx dy]``; translation-major, then flip, then rotation."""
+    rows = []
+    for (dx, dy) in translations:
+        for f in flips:
+            for r in range(n_rot):
+                m = hypothesis_matrix(360.0 * r / n_rot, f)
+                rows.append([m[0, 0], m[0, 1], m[1, 0], m[1, 1], dx, dy])
+    return np.array(rows, dtype=np.float64).reshape(-1, 6)
+
+
+def translation_lattice(n_side, pitch):
+    off = (np.arange(n_side) - (n_side - 1) / 2.0) * pitch
+    return [(float(dx), float(dy)) for dy in off for dx in off]
+
+
+IDENTITY_HYPOTHESIS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
+
+
+def frmsd_weights(n, lam):
+    """w[k-1] = 1/((k/n)**lam) with Python-float semantics - the very expression of ficp.py:60,81,
+    so the table is bit-identical to what the reference multiplies with."""
+    return np.array([1.0 / ((k / n) ** lam) for k in range(1, n + 1)], dtype=np.float64)
+
+
+def fixed_fraction_k(n, frac):
+    return max(1, min(n, int(math.floor(frac * n + 1e-9))))
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):   # torch.cuda.Stream
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+# --------------------------------------------------------------------------- target index
+class TargetIndex:
+    """Device-resident uniform-grid index over the Layer-2 (CHM) points; built once, reused by
+    every pass of every hypothesis (the reference rebuilds its kd-tree on every pass, ficp.py:69)."""
+
+    def __init__(self, target, use_z=None, pts_per_cell=2.0, stream=None):
+        lib = _lib.load()
+        arr = np.ascontiguousarray(np.asarray(target, dtype=np.float64))
+        if arr.ndim != 2 or arr.shape[1] < 2:
+            raise ValueError("source and target must be 2D arrays (N, D).")
+        self.m, self.ld = int(arr.shape[0]), int(arr.shape[1])
+        self.has_z = bool(arr.shape[1] >= 3) if use_z is None else bool(use_z)
+        self._h = C.c_void_p()
+        _lib.require_device()
+        _lib.check(lib.ficp_target_create(_lib.ptr(arr), self.m, self.ld, int(self.has_z), float(pts_per_cell),
+                                          _stream_ptr(stream), C.byref(self._h)), "ficp_target_create")
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise _lib.FicpError("TargetIndex already closed")
+        return self._h
+
+    def info(self):
+        ti = _lib.TargetInfo()
+        _lib.check(_lib.load().ficp_target_get_info(self.handle, C.byref(ti)))
+        return {"m": ti.m, "has_z": bool(ti.has_z), "grid_w": ti.grid_w, "grid_h": ti.grid_h, "cell": ti.cell,
+                "x0": ti.x0, "y0": ti.y0, "bbox": tuple(ti.bbox), "build_ms": ti.build_ms}
+
+    def query(self, points, use_z=None, stream=None):
+        """Exact NN of every row: (original target index int64, Euclidean distance float64)."""
+        q = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+        if q.ndim != 2 or q.shape[1] < 2:
+            raise ValueError("query points must be a 2D array (N, D>=2)")
+        z = self.has_z and q.shape[1] >= 3 if use_z is None else bool(use_z)
+        md = 3 if z else 2
+        if not np.isfinite(q[:, :md]).all():
+            raise ValueError("'x' must be finite, check for nan or inf values")
+        n = q.shape[0]
+        idx = np.empty(n, dtype=np.int64)
+        dist = np.empty(n, dtype=np.float64)
+        if n and self.m:
+            _lib.check(_lib.load().ficp_nn_query(self.handle, _lib.ptr(q), n, q.shape[1], int(z), _lib.ptr(idx),
+                                                 _lib.ptr(dist), _stream_ptr(stream)), "ficp_nn_query")
+        return idx, dist
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().ficp_target_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- batch
+class IcpBatch:
+    """Plots x hypotheses uploaded once; ``run()`` launches the persistent kernel, ``results()`` reads back."""
+
+    def __init__(self, index, sources, hyp_table=None, centres=None, lambda_val=3.0, stage2_lambda=None, n_stages=2,
+                 threshold=1e-6, max_iterations=1000, allow_reflection=False, min_k=3, fixed_frac=None,
+                 hyp_shard=(0, 1), want_final_xy=False, window_margin=-1.0, warps_per_cta=0, ctas_per_sm=0,
+                 disable_window=False, stream=None):
+        lib = _lib.load()
+        if isinstance(sources, np.ndarray) and sources.ndim == 2:
+            sources = [sources]
+        srcs = [np.ascontiguousarray(np.asarray(s, dtype=np.float64)) for s in sources]
+        if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
+            raise ValueError("every plot must be a non-empty 2D array (N, D)")
+        ld = srcs[0].shape[1]
+        if any(s.shape[1] != ld for s in srcs):
+            raise ValueError("all plots must have the same number of columns")
+        self.index = index
+        self.match_dims = 3 if (ld >= 3 and index.has_z) else 2
+        self.n_plots = len(srcs)
+        self.sizes = np.array([s.shape[0] for s in srcs], dtype=np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        self.src = np.ascontiguousarray(np.vstack(srcs))
+        self.hyp = np.ascontiguousarray(IDENTITY_HYPOTHESIS if hyp_table is None else
+                                        np.asarray(hyp_table, dtype=np.float64).reshape(-1, 6))
+        if centres is None:
+            centres = np.array([s[:, :2].mean(axis=0) for s in srcs])
+        self.centres = np.ascontiguousarray(np.asarray(centres, dtype=np.float64).reshape(self.n_plots, 2))
+        self.n_stages = int(n_stages)
+        lam2 = STAGE2_LAMBDA[self.match_dims] if stage2_lambda is None else stage2_lambda
+        self.lambdas = [lambda_val, lam2][: self.n_stages]
+        # FRMSD weight tables, one per distinct plot size
+        uniq = sorted(set(int(n) for n in self.sizes))
+        tab_of = {n: i for i, n in enumerate(uniq)}
+        tabs, offs = [], [0]
+        for n in uniq:
+            for lam in self.lambdas:
+                tabs.append(frmsd_weights(n, lam))
+            offs.append(offs[-1] + self.n_stages * n)
+        self.weights = np.ascontiguousarray(np.concatenate(tabs))
+        self.weight_offsets = np.array(offs, dtype=np.int64)
+        self.plot_tab = np.array([tab_of[int(n)] for n in self.sizes], dtype=np.int32)
+        self.fixed_k = None
+        if fixed_frac is not None:
+            self.fixed_k = np.array([fixed_fraction_k(int(n), fixed_frac) for n in self.sizes], dtype=np.int32)
+        self.hyp_begin, self.hyp_stride = int(hyp_shard[0]), int(hyp_shard[1])
+        prm = _lib.BatchParams(self.n_stages, int(max_iterations), int(bool(allow_reflection)), int(min_k),
+                               float(threshold), float(window_margin), int(warps_per_cta), int(ctas_per_sm),
+                               int(bool(disable_window)), 0)
+        self._h = C.c_void_p()
+        _lib.check(lib.ficp_batch_create(index.handle, _lib.ptr(self.src), ld, int(self.match_dims == 3),
+                                         _lib.ptr(self.offsets), self.n_plots, _lib.ptr(self.centres),
+                                         _lib.ptr(self.hyp), self.hyp.shape[0], self.hyp_begin, self.hyp_stride,
+                                         _lib.ptr(self.weights), _lib.ptr(self.weight_offsets),
+                                         _lib.ptr(self.plot_tab), len(uniq), _lib.ptr(self.fixed_k), C.byref(prm),
+                                         int(bool(want_final_xy)), _stream_ptr(stream), C.byref(self._h)),
+                   "ficp_batch_create")
+        bi = _lib.BatchInfo()
+        _lib.check(lib.ficp_batch_get_info(self._h, C.byref(bi)))
+        self.info = {f: getattr(bi, f) for f, _ in bi._fields_}
+        self.n_hyp = self.hyp.shape[0]
+        self.n_hyp_local = bi.n_hyp_local
+        self.want_final_xy = bool(want_final_xy) and self.n_hyp_local == 1
+        self.h2d_bytes = int(self.src.nbytes + self.hyp.nbytes + self.centres.nbytes + self.weights.nbytes)
+
+    def run(self, stream=None):
+        _lib.check(_lib.load().ficp_batch_run(self._h, _stream_ptr(stream)), "ficp_batch_run")
+        return self
+
+    def copy_best_keys_to(self, device_ptr, stream=None):
+        _lib.check(_lib.load().ficp_batch_copy_best_keys_device(self._h, C.c_void_p(int(device_ptr)),
+                                                                _stream_ptr(stream)))
+
+    def results(self, stream=None, per_hypothesis=True):
+        """Synchronise and read back.  Returns a dict:
+        ``hyp`` structured array (n_plots, n_hyp_local) of per-hypothesis outcomes (see HYP_RESULT_DTYPE),
+        ``hyp_ids`` global hypothesis id of each local column, ``best_key`` uint64 per plot, ``best_hyp``,
+        ``best_score``, ``stats`` and (optionally) ``final_xy``."""
+        lib = _lib.load()
+        res = np.empty((self.n_plots, self.n_hyp_local), dtype=_lib.HYP_RESULT_DTYPE) if per_hypothesis else None
+        keys = np.empty(self.n_plots, dtype=np.uint64)
+        stats = np.zeros(8, dtype=np.uint64)
+        final = np.empty((int(self.offsets[-1]), 2), dtype=np.float64) if self.want_final_xy else None
+        _lib.check(lib.ficp_batch_results(self._h, _lib.ptr(res), _lib.ptr(keys), _lib.ptr(final), _lib.ptr(stats),
+                                          _stream_ptr(stream)), "ficp_batch_results")
+        out = {"hyp": res, "best_key": keys, "final_xy": final,
+               "hyp_ids": self.hyp_begin + self.hyp_stride * np.arange(self.n_hyp_local),
+               "stats": {"passes": int(stats[0]), "global_path_queries": int(stats[1]),
+                         "windows_disabled": int(stats[2]), "fixup_rounds": int(stats[3]), "queries": int(stats[4])}}
+        out.update(decode_best_keys(keys))
+        self.d2h_bytes = int(keys.nbytes + stats.nbytes + (res.nbytes if res is not None else 0)
+                             + (final.nbytes if final is not None else 0))
+        return out
+
+    def transform_of(self, plot, hyp_row):
+        """2x3 world-coordinate transform [A | b] of one result row: final = A p + b."""
+        return compose_world_transform(hyp_row, self.centres[plot])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().ficp_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_best_keys(keys):
+    keys = np.asarray(keys, dtype=np.uint64)
+    score = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
+    return {"best_hyp": (keys & np.uint64(0xFFFFFFFF)).astype(np.int64), "best_score": score}
+
+
+def compose_world_transform(row, centre):
+    """final = M (p - centre) + c  ->  [M | c - M centre]."""
+    m = np.array([[row["m00"], row["m01"]], [row["m10"], row["m11"]]], dtype=np.float64)
+    b = np.array([row["cx"], row["cy"]]) - m @ np.asarray(centre, dtype=np.float64)
+    return np.hstack([m, b[:, None]])
+
+
+def register_batch(sources, target, hyp_table=None, index=None, **kw):
+    """One-call batched registration from HOST arrays (the end-to-end path bench.py times as ``e2e``):
+    build the target index (unless one is passed), upload plots + hypotheses, run, read back.
+
+    Returns per plot: best hypothesis id, its score (final FRMSD, fp32-rounded), its 2x3 transform,
+    trimmed size ``k``, RMSE and the number of passes, plus the per-hypothesis table."""
+    own = index is None
+    if own:
+        index = TargetIndex(target)
+    try:
+        batch = IcpBatch(index, sources, hyp_table, **kw)
+        try:
+            out = batch.run().results()
+            best_rows = []
+            for p in range(batch.n_plots):
+                j = (int(out["best_hyp"][p]) - batch.hyp_begin) // batch.hyp_stride
+                best_rows.append(out["hyp"][p, j])
+            out["best_row"] = np.array(best_rows, dtype=_lib.HYP_RESULT_DTYPE)
+            out["best_transform"] = np.stack([compose_world_transform(best_rows[p], batch.centres[p])
+                                              for p in range(batch.n_plots)])
+            out["h2d_bytes"] = batch.h2d_bytes + (int(np.asarray(target).nbytes) if own else 0)
+            out["d2h_bytes"] = batch.d2h_bytes
+            out["launch"] = dict(batch.info)
+            return out
+        finally:
+            batch.close()
+    finally:
+        if own:
+            index.close()

@@ -1,0 +1,524 @@
+// extern "C" entry points of libficp_b200.so (declared in include/ficp_b200.h).
+// Host-side orchestration only: argument checks, device buffers, launch configuration.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/ficp_b200.h"
+#include "ficp_internal.h"
+
+namespace ficp {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return kErrNoDevice;
+    return kErrCuda;
+}
+
+static_assert(sizeof(ficp_hyp_result) == sizeof(HypResult), "ABI struct mismatch");
+
+// RAII device buffer for the host-buffer convenience calls
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t n) {
+        FICP_CUDA(cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)));
+        return kOk;
+    }
+};
+
+struct Batch {
+    const Target* tgt = nullptr;
+    int n_plots = 0, n_hyp = 0, n_hyp_local = 0;
+    long long rows = 0;
+    bool z3 = false;
+    bool want_final = false;
+    IcpParams params{};
+    IcpLaunch launch{};
+    int ctas_per_sm = 0;
+    double2* d_src_u = nullptr;
+    double* d_src_z = nullptr;
+    PlotMeta* d_plots = nullptr;
+    double* d_hyp = nullptr;
+    double* d_tabs = nullptr;
+    HypResult* d_results = nullptr;
+    unsigned long long* d_best = nullptr;
+    double* d_final = nullptr;
+    int* d_counters = nullptr;  // [0] slice counter, [1..n_plots] hypothesis counters
+    unsigned long long* d_stats = nullptr;
+    ~Batch() {
+        cudaFree(d_src_u); cudaFree(d_src_z); cudaFree(d_plots); cudaFree(d_hyp); cudaFree(d_tabs);
+        cudaFree(d_results); cudaFree(d_best); cudaFree(d_final); cudaFree(d_counters); cudaFree(d_stats);
+    }
+};
+
+static int pick_e(int max_n) {
+    int e = 1;
+    while (32 * e < max_n) e <<= 1;
+    return e;
+}
+
+}  // namespace ficp
+
+using namespace ficp;
+
+extern "C" {
+
+const char* ficp_last_error(void) { return g_last_error.c_str(); }
+
+int ficp_device_count(int32_t* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    *n = c;
+    return kOk;
+}
+
+int ficp_set_device(int32_t device) {
+    FICP_CUDA(cudaSetDevice(device));
+    return kOk;
+}
+
+int ficp_device_props(int32_t* sms, int64_t* l2_bytes, int64_t* smem_optin, int32_t* clock_khz) {
+    int dev = 0, v = 0;
+    FICP_CUDA(cudaGetDevice(&dev));
+    FICP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (sms) *sms = v;
+    FICP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev));
+    if (l2_bytes) *l2_bytes = v;
+    FICP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem_optin) *smem_optin = v;
+    FICP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev));
+    if (clock_khz) *clock_khz = v;
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------ target
+int ficp_target_create(const double* pts_host, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
+                       void* stream, ficp_target** out) {
+    if (!out || (m > 0 && !pts_host)) { set_error("ficp_target_create: null pointer"); return kErrInvalid; }
+    Target* t = nullptr;
+    const int rc = target_build(pts_host, 0, m, ld, use_z, pts_per_cell, (cudaStream_t)stream, &t);
+    *out = reinterpret_cast<ficp_target*>(t);
+    return rc;
+}
+
+int ficp_target_create_device(const double* pts_dev, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
+                              void* stream, ficp_target** out) {
+    if (!out || (m > 0 && !pts_dev)) { set_error("ficp_target_create_device: null pointer"); return kErrInvalid; }
+    Target* t = nullptr;
+    const int rc = target_build(pts_dev, 1, m, ld, use_z, pts_per_cell, (cudaStream_t)stream, &t);
+    *out = reinterpret_cast<ficp_target*>(t);
+    return rc;
+}
+
+int ficp_target_get_info(const ficp_target* th, ficp_target_info* info) {
+    if (!th || !info) { set_error("ficp_target_get_info: null pointer"); return kErrInvalid; }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    info->m = t->m;
+    info->has_z = t->has_z;
+    info->grid_w = t->view.g.gw;
+    info->grid_h = t->view.g.gh;
+    info->cell = t->view.g.h;
+    info->x0 = t->view.g.x0;
+    info->y0 = t->view.g.y0;
+    for (int i = 0; i < 4; ++i) info->bbox[i] = t->bbox[i];
+    info->build_ms = t->build_ms;
+    return kOk;
+}
+
+void ficp_target_destroy(ficp_target* t) { target_free(reinterpret_cast<Target*>(t)); }
+
+// ------------------------------------------------------------------------------------------ NN query
+int ficp_nn_query_device(const ficp_target* th, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
+                         int32_t* idx_dev, double* dist_dev, void* stream) {
+    if (!th) { set_error("ficp_nn_query: null target"); return kErrInvalid; }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    if (ld < 2 || (use_z && ld < 3)) { set_error("ficp_nn_query: not enough columns"); return kErrInvalid; }
+    if (use_z && !t->has_z) { set_error("ficp_nn_query: target was built without Z"); return kErrInvalid; }
+    return launch_nn_query(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, (cudaStream_t)stream);
+}
+
+int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
+                  int64_t* idx_out, double* dist_out, void* stream) {
+    if (n <= 0) return kOk;
+    if (!th || !q_host || !idx_out) { set_error("ficp_nn_query: null pointer"); return kErrInvalid; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<double> dq, dd;
+    DevBuf<int> di;
+    int rc;
+    if ((rc = dq.alloc((size_t)n * ld)) || (rc = dd.alloc(n)) || (rc = di.alloc(n))) return rc;
+    FICP_CUDA(cudaMemcpyAsync(dq.p, q_host, sizeof(double) * (size_t)n * ld, cudaMemcpyHostToDevice, s));
+    if ((rc = ficp_nn_query_device(th, dq.p, n, ld, use_z, di.p, dd.p, stream))) return rc;
+    std::vector<int> hi((size_t)n);
+    FICP_CUDA(cudaMemcpyAsync(hi.data(), di.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (dist_out) FICP_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; ++i) idx_out[i] = hi[(size_t)i];
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------ trimming
+int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* corr_host, int32_t ld_c,
+                         const double* dist_host, int64_t n, int32_t md, const double* weights_host, int64_t fixed_k,
+                         int64_t* k_out, double* frmsd_out, int64_t* order_out) {
+    if (k_out) *k_out = 0;
+    if (frmsd_out) *frmsd_out = HUGE_VAL;
+    if (n <= 0) return kOk;
+    if (!dist_host) { set_error("ficp_select_fraction: null distances"); return kErrInvalid; }
+    if (n > kSelectMaxN) { set_error("ficp_select_fraction: more than 8192 points per plot are not supported"); return kErrTooLarge; }
+    const bool want_k = (src_host != nullptr);
+    if (want_k && (!corr_host || !weights_host || ld_s < md || ld_c < md || (md != 2 && md != 3))) {
+        set_error("ficp_select_fraction: bad source/correspondence arguments");
+        return kErrInvalid;
+    }
+    if (fixed_k < 0 || fixed_k > n) { set_error("ficp_select_fraction: fixed_k out of range"); return kErrInvalid; }
+    DevBuf<double> ds, dc, dd, dw, df;
+    DevBuf<long long> dk;
+    DevBuf<int> dord;
+    int rc;
+    if ((rc = dd.alloc(n)) || (rc = dk.alloc(1)) || (rc = df.alloc(1)) || (rc = dord.alloc(n))) return rc;
+    FICP_CUDA(cudaMemcpy(dd.p, dist_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (want_k) {
+        if ((rc = ds.alloc((size_t)n * ld_s)) || (rc = dc.alloc((size_t)n * ld_c)) || (rc = dw.alloc(n))) return rc;
+        FICP_CUDA(cudaMemcpy(ds.p, src_host, sizeof(double) * n * ld_s, cudaMemcpyHostToDevice));
+        FICP_CUDA(cudaMemcpy(dc.p, corr_host, sizeof(double) * n * ld_c, cudaMemcpyHostToDevice));
+        FICP_CUDA(cudaMemcpy(dw.p, weights_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    rc = launch_select_fraction(want_k ? ds.p : nullptr, ld_s, dc.p, ld_c, dd.p, (int)n, md, dw.p, (int)fixed_k, dk.p,
+                                df.p, order_out ? dord.p : nullptr, 0);
+    if (rc) return rc;
+    FICP_CUDA(cudaDeviceSynchronize());
+    if (want_k) {
+        long long k = 0;
+        FICP_CUDA(cudaMemcpy(&k, dk.p, sizeof k, cudaMemcpyDeviceToHost));
+        if (k_out) *k_out = k;
+        if (frmsd_out) FICP_CUDA(cudaMemcpy(frmsd_out, df.p, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (order_out) {
+        std::vector<int> ho((size_t)n);
+        FICP_CUDA(cudaMemcpy(ho.data(), dord.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i) order_out[i] = ho[(size_t)i];
+    }
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------ fit / apply
+int ficp_fit_rigid2d(const double* src_host, int32_t ld_s, const double* tgt_host, int32_t ld_t, int64_t k,
+                     int32_t allow_reflection, double* T9) {
+    if (!src_host || !tgt_host || !T9 || k <= 0 || ld_s < 2 || ld_t < 2 || k > 100000000LL) {
+        set_error("ficp_fit_rigid2d: bad arguments (need k >= 1 rows with >= 2 columns)");
+        return kErrInvalid;
+    }
+    DevBuf<double> ds, dt, dT;
+    int rc;
+    if ((rc = ds.alloc((size_t)k * ld_s)) || (rc = dt.alloc((size_t)k * ld_t)) || (rc = dT.alloc(9))) return rc;
+    FICP_CUDA(cudaMemcpy(ds.p, src_host, sizeof(double) * k * ld_s, cudaMemcpyHostToDevice));
+    FICP_CUDA(cudaMemcpy(dt.p, tgt_host, sizeof(double) * k * ld_t, cudaMemcpyHostToDevice));
+    if ((rc = launch_fit_rigid2d(ds.p, ld_s, dt.p, ld_t, nullptr, (int)k, allow_reflection, dT.p, 0))) return rc;
+    FICP_CUDA(cudaMemcpy(T9, dT.p, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+int ficp_apply_xy(const double* in_host, double* out_host, int64_t n, int32_t ld, const double* T9) {
+    if (n <= 0) return kOk;
+    if (!in_host || !out_host || !T9 || ld < 2) { set_error("ficp_apply_xy: bad arguments"); return kErrInvalid; }
+    DevBuf<double> di, dout, dT;
+    int rc;
+    if ((rc = di.alloc((size_t)n * ld)) || (rc = dout.alloc((size_t)n * ld)) || (rc = dT.alloc(9))) return rc;
+    FICP_CUDA(cudaMemcpy(di.p, in_host, sizeof(double) * n * ld, cudaMemcpyHostToDevice));
+    FICP_CUDA(cudaMemcpy(dT.p, T9, sizeof(double) * 9, cudaMemcpyHostToDevice));
+    if ((rc = launch_apply_xy(di.p, dout.p, n, ld, dT.p, 0))) return rc;
+    FICP_CUDA(cudaMemcpy(out_host, dout.p, sizeof(double) * n * ld, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+int ficp_sumsq(const double* a_host, int32_t ld_a, const double* b_host, int32_t ld_b, int64_t k, int32_t md,
+               double* out) {
+    if (!out) { set_error("ficp_sumsq: null output"); return kErrInvalid; }
+    *out = 0.0;
+    if (k <= 0) return kOk;
+    if (!a_host || !b_host || ld_a < md || ld_b < md || (md != 2 && md != 3)) { set_error("ficp_sumsq: bad arguments"); return kErrInvalid; }
+    DevBuf<double> da, db, dout;
+    int rc;
+    if ((rc = da.alloc((size_t)k * ld_a)) || (rc = db.alloc((size_t)k * ld_b)) || (rc = dout.alloc(1))) return rc;
+    FICP_CUDA(cudaMemcpy(da.p, a_host, sizeof(double) * k * ld_a, cudaMemcpyHostToDevice));
+    FICP_CUDA(cudaMemcpy(db.p, b_host, sizeof(double) * k * ld_b, cudaMemcpyHostToDevice));
+    if ((rc = launch_sumsq(da.p, ld_a, db.p, ld_b, nullptr, (int)k, md, dout.p, 0))) return rc;
+    FICP_CUDA(cudaMemcpy(out, dout.p, sizeof(double), cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------ batch
+int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld, int32_t use_z,
+                      const int64_t* plot_offsets, int64_t n_plots, const double* centres, const double* hyp,
+                      int64_t n_hyp, int32_t hyp_begin, int32_t hyp_stride, const double* weights,
+                      const int64_t* weight_offsets, const int32_t* plot_tab, int32_t n_tabs, const int32_t* fixed_k,
+                      const ficp_batch_params* prm, int32_t want_final_xy, void* stream, ficp_batch** out) {
+    if (out) *out = nullptr;
+    if (!th || !src_host || !plot_offsets || !centres || !hyp || !weights || !weight_offsets || !plot_tab || !prm || !out) {
+        set_error("ficp_batch_create: null pointer");
+        return kErrInvalid;
+    }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    if (t->m <= 0) { set_error("ficp_batch_create: empty target (callers return the source unchanged, ficp.py:66-68)"); return kErrInvalid; }
+    if (n_plots <= 0 || n_hyp <= 0 || hyp_stride <= 0 || hyp_begin < 0 || hyp_begin >= hyp_stride + n_hyp) {
+        set_error("ficp_batch_create: need n_plots >= 1, n_hyp >= 1, hyp_stride >= 1");
+        return kErrInvalid;
+    }
+    if (ld < 2 || (use_z && (ld < 3 || !t->has_z))) { set_error("ficp_batch_create: Z requested but not available on both sides"); return kErrInvalid; }
+    if (prm->n_stages < 1 || prm->n_stages > kMaxStages) { set_error("ficp_batch_create: n_stages must be 1 or 2"); return kErrInvalid; }
+    if (n_plots > 50000000 || n_hyp > 100000000) { set_error("ficp_batch_create: batch too large"); return kErrTooLarge; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const GridGeom& g = t->view.g;
+
+    const long long rows = plot_offsets[n_plots];
+    int max_n = 0;
+    for (int64_t p = 0; p < n_plots; ++p) {
+        const long long n = plot_offsets[p + 1] - plot_offsets[p];
+        if (n <= 0) { set_error("ficp_batch_create: empty plot (callers return an empty plot unchanged)"); return kErrInvalid; }
+        if (n > 1024) { set_error("ficp_batch_create: more than 1024 trees per plot are not supported by the persistent kernel"); return kErrTooLarge; }
+        if (plot_tab[p] < 0 || plot_tab[p] >= n_tabs) { set_error("ficp_batch_create: plot_tab out of range"); return kErrInvalid; }
+        if (weight_offsets[plot_tab[p] + 1] - weight_offsets[plot_tab[p]] != (long long)prm->n_stages * n) {
+            set_error("ficp_batch_create: weight table length does not match n_stages * plot size");
+            return kErrInvalid;
+        }
+        if (fixed_k && (fixed_k[p] < 0 || fixed_k[p] > n)) { set_error("ficp_batch_create: fixed_k out of range"); return kErrInvalid; }
+        max_n = std::max<int>(max_n, (int)n);
+    }
+    const int e = pick_e(max_n);
+    const int npad = 32 * e;
+    const bool z3 = use_z != 0;
+    const int n_hyp_local = (hyp_begin < n_hyp) ? (int)((n_hyp - hyp_begin + hyp_stride - 1) / hyp_stride) : 0;
+    if (n_hyp_local <= 0) { set_error("ficp_batch_create: this shard owns no hypothesis"); return kErrInvalid; }
+
+    Batch* b = new Batch();
+    struct Guard { Batch* b; bool armed = true; ~Guard() { if (armed) delete b; } } guard{b};
+    b->tgt = t; b->n_plots = (int)n_plots; b->n_hyp = (int)n_hyp; b->n_hyp_local = n_hyp_local;
+    b->rows = rows; b->z3 = z3; b->want_final = (want_final_xy != 0) && n_hyp_local == 1;
+
+    // ---- hypothesis translation range (for the window footprint)
+    double dxmin = HUGE_VAL, dxmax = -HUGE_VAL, dymin = HUGE_VAL, dymax = -HUGE_VAL;
+    for (int64_t h = 0; h < n_hyp; ++h) {
+        for (int c = 0; c < 6; ++c)
+            if (!std::isfinite(hyp[h * 6 + c])) { set_error("hypothesis table contains non-finite values"); return kErrNonFinite; }
+        dxmin = std::min(dxmin, hyp[h * 6 + 4]); dxmax = std::max(dxmax, hyp[h * 6 + 4]);
+        dymin = std::min(dymin, hyp[h * 6 + 5]); dymax = std::max(dymax, hyp[h * 6 + 5]);
+    }
+
+    // ---- launch shape: warps per CTA, shared-memory budget, window capacity
+    int dev = 0, sms = 0, smem_optin = 0;
+    FICP_CUDA(cudaGetDevice(&dev));
+    FICP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FICP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int warps = prm->warps_per_cta > 0 ? prm->warps_per_cta : std::min(icp_max_warps(e), 16);
+    warps = std::max(1, std::min(warps, std::min(icp_max_warps(e), n_hyp_local)));
+    int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));
+    const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
+    size_t budget = std::min<size_t>((size_t)smem_optin, sm_total / want_ctas_per_sm - 1024);
+    const int wcap_rows = 256;
+    const size_t fixed_bytes = icp_smem_bytes(e, z3, warps, 0, 0, wcap_rows);
+    const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
+    int wcap_pts = 0;
+    if (!prm->disable_window && budget > fixed_bytes + 4096) wcap_pts = (int)std::min<size_t>(65535, (budget - fixed_bytes - 256) / per_pt);
+
+    // ---- per-plot metadata: local coordinates u = p - centre, shift point, window rectangle
+    std::vector<PlotMeta> plots((size_t)n_plots);
+    std::vector<double2> h_u((size_t)rows);
+    std::vector<double> h_z(z3 ? (size_t)rows : 0);
+    const double mean_cell_pts = (double)t->m / ((double)g.gw * g.gh);
+    double margin0 = prm->window_margin >= 0.0 ? prm->window_margin : (3.0 * g.h + 5.0);
+    int need_pts = 0;
+    for (int64_t p = 0; p < n_plots; ++p) {
+        PlotMeta& pm = plots[(size_t)p];
+        pm.off = plot_offsets[p];
+        pm.n = (int)(plot_offsets[p + 1] - plot_offsets[p]);
+        pm.tab = plot_tab[p];
+        pm.cinx = centres[2 * p]; pm.ciny = centres[2 * p + 1];
+        pm.fixed_k = fixed_k ? fixed_k[p] : 0;
+        pm.pad = 0;
+        double sx = 0, sy = 0;
+        for (int i = 0; i < pm.n; ++i) {
+            const double* r = src_host + (size_t)(pm.off + i) * ld;
+            if (!std::isfinite(r[0]) || !std::isfinite(r[1]) || (z3 && !std::isfinite(r[2]))) {
+                set_error("source contains non-finite coordinates ('x' must be finite)");
+                return kErrNonFinite;
+            }
+            const double ux = r[0] - pm.cinx, uy = r[1] - pm.ciny;  // same single subtraction as the oracle
+            h_u[(size_t)(pm.off + i)] = make_double2(ux, uy);
+            if (z3) h_z[(size_t)(pm.off + i)] = r[2];
+            sx += ux; sy += uy;
+        }
+        pm.ubx = sx / pm.n; pm.uby = sy / pm.n;
+        double rho = 0;
+        for (int i = 0; i < pm.n; ++i) {
+            const double2 u = h_u[(size_t)(pm.off + i)];
+            rho = std::max(rho, std::hypot(u.x - pm.ubx, u.y - pm.uby));
+        }
+        // footprint of the plot centroid over all start poses: centre_h = M_h ubar + cin + d_h
+        double fx0, fx1, fy0, fy1;
+        if (std::hypot(pm.ubx, pm.uby) <= 1e-9 * (rho + 1.0)) {
+            fx0 = pm.cinx + dxmin; fx1 = pm.cinx + dxmax; fy0 = pm.ciny + dymin; fy1 = pm.ciny + dymax;
+        } else {
+            fx0 = fy0 = HUGE_VAL; fx1 = fy1 = -HUGE_VAL;
+            for (int64_t h = 0; h < n_hyp; ++h) {
+                const double* hr = hyp + h * 6;
+                const double cx = hr[0] * pm.ubx + hr[1] * pm.uby + pm.cinx + hr[4];
+                const double cy = hr[2] * pm.ubx + hr[3] * pm.uby + pm.ciny + hr[5];
+                fx0 = std::min(fx0, cx); fx1 = std::max(fx1, cx); fy0 = std::min(fy0, cy); fy1 = std::max(fy1, cy);
+            }
+        }
+        pm.wx0 = pm.wy0 = pm.wx1 = pm.wy1 = 0;
+        if (wcap_pts > 0) {
+            double margin = margin0;
+            for (int attempt = 0; attempt < 12; ++attempt, margin *= 0.7) {
+                const double r = rho + margin;
+                const double bx0 = fx0 - r, bx1 = fx1 + r;
+                const double by0 = fy0 - r, by1 = fy1 + r;
+                if (bx1 < g.x0 || by1 < g.y0 || bx0 > g.x0 + g.gw * g.h || by0 > g.y0 + g.gh * g.h) break;  // off the map
+                const int x0 = clamp_cell((bx0 - g.x0) * g.inv_h, g.gw), x1 = clamp_cell((bx1 - g.x0) * g.inv_h, g.gw) + 1;
+                const int y0 = clamp_cell((by0 - g.y0) * g.inv_h, g.gh), y1 = clamp_cell((by1 - g.y0) * g.inv_h, g.gh) + 1;
+                const long long cells = (long long)(x1 - x0) * (y1 - y0);
+                const double est = cells * mean_cell_pts * 1.25 + 64;
+                if (cells <= wcap_pts && (y1 - y0) <= wcap_rows && est <= wcap_pts) {
+                    pm.wx0 = x0; pm.wx1 = x1; pm.wy0 = y0; pm.wy1 = y1;
+                    need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est * 1.2 + 256));
+                    need_pts = std::max<long long>(need_pts, cells);
+                    break;
+                }
+            }
+        }
+    }
+    // do not reserve more on-chip window than any plot can use
+    wcap_pts = std::min(wcap_pts, need_pts);
+    const int wcap_cells = wcap_pts;
+    const size_t smem = icp_smem_bytes(e, z3, warps, wcap_pts, wcap_cells, wcap_rows);
+    if (smem > (size_t)smem_optin) { set_error("ficp_batch_create: shared-memory plan exceeds the device limit"); return kErrTooLarge; }
+    int occ = 0;
+    int rc = icp_max_ctas_per_sm(e, z3, warps, smem, &occ);
+    if (rc) return rc;
+    if (occ < 1) { set_error("ficp_batch_create: kernel does not fit on an SM with this configuration"); return kErrTooLarge; }
+    const int ctas_per_sm = prm->ctas_per_sm > 0 ? std::min(occ, prm->ctas_per_sm) : occ;
+    const long long resident = (long long)sms * ctas_per_sm;
+    const int max_slices_per_plot = (n_hyp_local + warps - 1) / warps;
+    int slices_per_plot = (int)std::min<long long>(max_slices_per_plot, std::max<long long>(1, (resident + n_plots - 1) / n_plots));
+    const long long n_slices = (long long)n_plots * slices_per_plot;
+    if (n_slices > 2000000000LL) { set_error("ficp_batch_create: too many work slices"); return kErrTooLarge; }
+
+    // ---- FRMSD weight tables: [table][stage][g | c][NPAD], lane-permuted (k-1 = lane*E + r  ->  r*32 + lane)
+    std::vector<double> h_tabs((size_t)n_tabs * prm->n_stages * 2 * npad, HUGE_VAL);
+    for (int tb = 0; tb < n_tabs; ++tb) {
+        const long long len = weight_offsets[tb + 1] - weight_offsets[tb];
+        if (len % prm->n_stages) { set_error("ficp_batch_create: malformed weight table"); return kErrInvalid; }
+        const int nt = (int)(len / prm->n_stages);
+        if (nt > npad) { set_error("ficp_batch_create: weight table larger than the plot size class"); return kErrInvalid; }
+        for (int st = 0; st < prm->n_stages; ++st) {
+            double* gdst = h_tabs.data() + ((size_t)(tb * prm->n_stages + st) * 2) * npad;
+            double* cdst = gdst + npad;
+            for (int k = 1; k <= nt; ++k) {
+                const double c = weights[weight_offsets[tb] + (long long)st * nt + (k - 1)];
+                const int lane = (k - 1) / e, r = (k - 1) % e;
+                cdst[r * 32 + lane] = c;
+                gdst[r * 32 + lane] = c * c / (double)k;
+            }
+        }
+    }
+
+    // ---- device buffers
+    FICP_CUDA(cudaMalloc(&b->d_src_u, sizeof(double2) * (size_t)rows));
+    if (z3) FICP_CUDA(cudaMalloc(&b->d_src_z, sizeof(double) * (size_t)rows));
+    FICP_CUDA(cudaMalloc(&b->d_plots, sizeof(PlotMeta) * (size_t)n_plots));
+    FICP_CUDA(cudaMalloc(&b->d_hyp, sizeof(double) * 6 * (size_t)n_hyp));
+    FICP_CUDA(cudaMalloc(&b->d_tabs, sizeof(double) * h_tabs.size()));
+    FICP_CUDA(cudaMalloc(&b->d_results, sizeof(HypResult) * (size_t)n_plots * n_hyp_local));
+    FICP_CUDA(cudaMalloc(&b->d_best, sizeof(unsigned long long) * (size_t)n_plots));
+    if (b->want_final) FICP_CUDA(cudaMalloc(&b->d_final, sizeof(double) * 2 * (size_t)rows));
+    FICP_CUDA(cudaMalloc(&b->d_counters, sizeof(int) * (size_t)(n_plots + 1)));
+    FICP_CUDA(cudaMalloc(&b->d_stats, sizeof(unsigned long long) * 8));
+    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.data(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.data(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * 6 * (size_t)n_hyp, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(b->d_tabs, h_tabs.data(), sizeof(double) * h_tabs.size(), cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaStreamSynchronize(s));  // the staging vectors go out of scope below
+
+    IcpParams& P = b->params;
+    P.grid = t->view;
+    P.src_u = b->d_src_u; P.src_z = b->d_src_z; P.plots = b->d_plots; P.n_plots = (int)n_plots;
+    P.hyp = b->d_hyp; P.n_hyp = (int)n_hyp; P.hyp_begin = hyp_begin; P.hyp_stride = hyp_stride; P.n_hyp_local = n_hyp_local;
+    P.tabs = b->d_tabs; P.n_stages = prm->n_stages; P.threshold = prm->threshold;
+    P.max_iter = prm->max_iterations; P.allow_reflection = prm->allow_reflection; P.min_k = prm->min_k;
+    P.results = b->d_results; P.best_key = b->d_best; P.final_xy = b->d_final;
+    P.slice_counter = b->d_counters; P.hyp_counter = b->d_counters + 1;
+    P.slices_per_plot = slices_per_plot; P.n_slices = (int)n_slices;
+    P.wcap_pts = wcap_pts; P.wcap_cells = wcap_cells; P.wcap_rows = wcap_rows;
+    P.stats = b->d_stats;
+    b->launch.e = e; b->launch.z3 = z3; b->launch.warps = warps; b->launch.smem = smem;
+    b->launch.ctas = (int)std::min<long long>(n_slices, resident);
+    b->ctas_per_sm = ctas_per_sm;
+    guard.armed = false;
+    *out = reinterpret_cast<ficp_batch*>(b);
+    return kOk;
+}
+
+int ficp_batch_get_info(const ficp_batch* bh, ficp_batch_info* info) {
+    if (!bh || !info) { set_error("ficp_batch_get_info: null pointer"); return kErrInvalid; }
+    const Batch* b = reinterpret_cast<const Batch*>(bh);
+    info->n_plots = b->n_plots; info->n_hyp = b->n_hyp; info->n_hyp_local = b->n_hyp_local;
+    info->elems_per_lane = b->launch.e; info->match_z = b->z3 ? 1 : 0; info->warps_per_cta = b->launch.warps;
+    info->ctas = b->launch.ctas; info->ctas_per_sm = b->ctas_per_sm; info->slices_per_plot = b->params.slices_per_plot;
+    info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells;
+    info->smem_bytes = (int64_t)b->launch.smem; info->rows = b->rows;
+    return kOk;
+}
+
+int ficp_batch_run(ficp_batch* bh, void* stream) {
+    if (!bh) { set_error("ficp_batch_run: null batch"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    cudaStream_t s = (cudaStream_t)stream;
+    FICP_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * (size_t)(b->n_plots + 1), s));
+    FICP_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(unsigned long long) * 8, s));
+    FICP_CUDA(cudaMemsetAsync(b->d_best, 0xFF, sizeof(unsigned long long) * (size_t)b->n_plots, s));
+    return launch_icp(b->params, b->launch, s);
+}
+
+int ficp_batch_results(ficp_batch* bh, ficp_hyp_result* results, uint64_t* best_keys, double* final_xy, uint64_t* stats,
+                       void* stream) {
+    if (!bh) { set_error("ficp_batch_results: null batch"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (results)
+        FICP_CUDA(cudaMemcpyAsync(results, b->d_results, sizeof(HypResult) * (size_t)b->n_plots * b->n_hyp_local,
+                                  cudaMemcpyDeviceToHost, s));
+    if (best_keys)
+        FICP_CUDA(cudaMemcpyAsync(best_keys, b->d_best, sizeof(uint64_t) * (size_t)b->n_plots, cudaMemcpyDeviceToHost, s));
+    if (final_xy) {
+        if (!b->want_final) { set_error("ficp_batch_results: batch was not created with want_final_xy (or owns > 1 hypothesis per plot)"); return kErrInvalid; }
+        FICP_CUDA(cudaMemcpyAsync(final_xy, b->d_final, sizeof(double) * 2 * (size_t)b->rows, cudaMemcpyDeviceToHost, s));
+    }
+    if (stats) FICP_CUDA(cudaMemcpyAsync(stats, b->d_stats, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
+    return kOk;
+}
+
+int ficp_batch_copy_best_keys_device(ficp_batch* bh, void* dst_dev, void* stream) {
+    if (!bh || !dst_dev) { set_error("ficp_batch_copy_best_keys_device: null pointer"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    FICP_CUDA(cudaMemcpyAsync(dst_dev, b->d_best, sizeof(uint64_t) * (size_t)b->n_plots, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+    return kOk;
+}
+
+void ficp_batch_destroy(ficp_batch* b) { delete reinterpret_cast<Batch*>(b); }
+
+}  // extern "C"

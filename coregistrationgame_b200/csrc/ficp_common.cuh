@@ -1,0 +1,58 @@
+// Shared definitions for the B200 Fractional-ICP kernels.
+//
+// Numerics contract (DESIGN.md "Numerics"): every quantity the reference computes in IEEE
+// float64 (ficp.py:34-35) is float64 here as well - B200's FP64 pipe runs at half the FP32
+// rate, so the hot path keeps bit-level parity of the NN indices with the reference instead of
+// approximating in fp32.  Squared distances are evaluated WITHOUT fused multiply-add in the
+// order ((dx*dx)+(dy*dy))+(dz*dz), which is bit-identical to scipy's cKDTree (ficp.py:69-70).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#if defined(__CUDACC__)
+#define FICP_HD __host__ __device__ __forceinline__
+#else
+#define FICP_HD inline
+#endif
+
+namespace ficp {
+
+#if defined(__CUDA_ARCH__)
+FICP_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+FICP_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+FICP_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+// host build (tests/hostcheck): compiled with -ffp-contract=off
+FICP_HD double dmul(double a, double b) { return a * b; }
+FICP_HD double dadd(double a, double b) { return a + b; }
+FICP_HD double dsub(double a, double b) { return a - b; }
+#endif
+
+constexpr double kInf = __builtin_huge_val();  // +inf (nvcc and gcc both accept the builtin in constant expressions)
+
+// Geometry of the uniform grid over the Layer-2 (CHM) points.
+struct GridGeom {
+    double x0, y0;     // lower-left corner (min x, min y of the target)
+    double h, inv_h;   // cell edge and its reciprocal
+    double eps;        // conservative slack for cell-box bounds (covers binning round-off)
+    int gw, gh;        // cells per row / number of rows
+};
+
+// Device view of a built target index (cell-sorted copy of the target + CSR cell table).
+struct GridView {
+    GridGeom g;
+    const double2* xy;          // [M] cell-sorted XY
+    const double* z;            // [M] cell-sorted Z (nullptr when the target has no 3rd column)
+    const int* orig;            // [M] original row index of each sorted point
+    const unsigned* cell_start; // [gw*gh + 1] exclusive prefix of per-cell counts
+    long long m;
+};
+
+FICP_HD int clamp_cell(double f, int n) {
+    // f = (coord - origin) * inv_h ; robust to huge magnitudes (clamped before conversion)
+    if (!(f > 0.0)) return 0;
+    if (f >= (double)(n - 1)) return n - 1;
+    return (int)f;
+}
+
+}  // namespace ficp

@@ -1,0 +1,122 @@
+// Internal (non-ABI) declarations shared by the translation units of libficp_b200.so.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <cuda_runtime.h>
+#include "ficp_common.cuh"
+
+namespace ficp {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+enum Status : int {
+    kOk = 0,
+    kErrInvalid = -1,    // bad argument (maps to ValueError in the Python shim)
+    kErrNonFinite = -2,  // NaN/Inf coordinate (the reference raises ValueError via scipy)
+    kErrCuda = -3,       // CUDA runtime failure
+    kErrTooLarge = -4,   // size outside what the kernels support
+    kErrNoDevice = -5,
+};
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define FICP_CUDA(call)                                                          \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess) return ::ficp::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- target index -----------------------------------------------------------------------------
+struct Target {
+    int device = 0;
+    long long m = 0;
+    int has_z = 0;
+    GridView view{};
+    double bbox[4] = {0, 0, 0, 0};  // xmin xmax ymin ymax
+    double pts_per_cell = 2.0;
+    // owned device buffers
+    double2* d_xy = nullptr;
+    double* d_z = nullptr;
+    int* d_orig = nullptr;
+    unsigned* d_cell_start = nullptr;
+    float build_ms = 0.f;  // device time of the build kernels (CUDA events)
+};
+
+// Builds the grid from row-major points (ld doubles per row; columns 0,1[,2]).  `pts` is a host
+// pointer unless on_device != 0.
+int target_build(const double* pts, int on_device, long long m, int ld, int use_z, double pts_per_cell,
+                 cudaStream_t stream, Target** out);
+void target_free(Target* t);
+
+// ---- standalone stage kernels (host launchers; all pointers are DEVICE pointers) ----------------
+int launch_nn_query(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
+                    double* d_d2, cudaStream_t stream);
+// Sort by (dist, index) + FRMSD prefix scan + first-minimum k (auto) or fixed k.  n <= kSelectMaxN.
+constexpr int kSelectMaxN = 8192;
+int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, int ld_c, const double* d_dist,
+                           int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,
+                           double* d_frmsd_out, int* d_order_out, cudaStream_t stream);
+int launch_fit_rigid2d(const double* d_src, int ld_s, const double* d_tgt, int ld_t, const int* d_sel, int k,
+                       int allow_reflection, double* d_T9, cudaStream_t stream);
+int launch_apply_xy(const double* d_in, double* d_out, long long n, int ld, const double* d_T9, cudaStream_t stream);
+int launch_sumsq(const double* d_a, int ld_a, const double* d_b, int ld_b, const int* d_sel, int k, int md,
+                 double* d_out, cudaStream_t stream);
+
+// ---- persistent batched ICP ---------------------------------------------------------------------
+constexpr int kMaxStages = 2;
+
+struct PlotMeta {
+    long long off;       // first row of this plot in the concatenated source arrays
+    int n;               // trees in the plot
+    int tab;             // index of its FRMSD weight table
+    double cinx, ciny;   // centre the hypotheses rotate about (source rows are stored as u = p - cin)
+    double ubx, uby;     // mean of u (shift point for the cross-covariance sums)
+    int wx0, wy0, wx1, wy1;  // window of grid cells staged in shared memory ([x0,x1) x [y0,y1))
+    int fixed_k;         // 0 = FRMSD-optimal subset size (reference behaviour); >0 = fixed trim size
+    int pad;
+};
+
+struct HypResult {
+    double m00, m01, m10, m11;  // linear part:  final = M (p - cin) + c
+    double cx, cy;              // c
+    double frmsd, rmse;         // FRMSD and trimmed RMSE of the final pass
+    int k;                      // trimmed subset size of the final pass
+    int passes;                 // NN passes executed (= hypothesis-iterations)
+    int flags;
+    int pad;
+};
+
+struct IcpParams {
+    GridView grid;
+    const double2* src_u;
+    const double* src_z;
+    const PlotMeta* plots;
+    int n_plots;
+    const double* hyp;  // [n_hyp][6] m00 m01 m10 m11 dx dy
+    int n_hyp, hyp_begin, hyp_stride, n_hyp_local;
+    const double* tabs;       // per table: [stage][2][NPAD] (g = c*c/k, then c), lane-permuted
+    int n_stages;
+    double threshold;
+    int max_iter, allow_reflection, min_k;
+    HypResult* results;             // [n_plots][n_hyp_local]
+    unsigned long long* best_key;   // [n_plots]
+    double* final_xy;               // optional [rows][2], only when n_hyp_local == 1
+    int* slice_counter;
+    int* hyp_counter;               // [n_plots]
+    int slices_per_plot, n_slices;
+    int wcap_pts, wcap_cells, wcap_rows;
+    unsigned long long* stats;      // [0] passes [1] queries resolved on the global path [2] window disabled
+                                    // [3] trim-order fix-up rounds [4] queries
+};
+
+struct IcpLaunch {
+    int e;            // elements per lane (NPAD = 32*e)
+    bool z3;
+    int warps;        // warps per CTA
+    int ctas;         // grid size
+    size_t smem;      // dynamic shared memory per CTA
+};
+int icp_max_warps(int e);
+size_t icp_smem_bytes(int e, bool z3, int warps, int wcap_pts, int wcap_cells, int wcap_rows);
+int icp_max_ctas_per_sm(int e, bool z3, int warps, size_t smem, int* out);
+int launch_icp(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream);
+
+}  // namespace ficp

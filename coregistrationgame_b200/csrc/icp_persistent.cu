@@ -1,0 +1,597 @@
+// Kernel 4: the whole two-stage Fractional ICP loop on-device, batched over plots x start-pose
+// hypotheses.  Fuses kernels 1b/2/3 (NN query, FRMSD trimming, closed-form rigid fit):
+//
+//   run()/_iterate()             /root/reference/ficp.py:122-154   -> icp_run_hypothesis
+//   find_correspondences          ficp.py:65-71                     -> nn phase of icp_pass
+//   find_optimal_fraction, frmsd  ficp.py:54-60,73-86               -> trim phase of icp_pass
+//   get_n_first_elements          ficp.py:62-63                     -> (d2, index) threshold of the k-th element
+//   compute_optimal_transform_2d  ficp.py:89-110                    -> icp_fit (no SVD: normalised (H00+H11, H01-H10))
+//   apply_transform_2d_xy_only    ficp.py:112-119                   -> composed into (M, c); Z never touched
+//
+// Mapping (DESIGN.md "persistent kernel"):
+//   * one WARP owns one (plot, hypothesis) ICP from start to convergence - no block barrier inside
+//     the loop, so the 5..70-pass spread between hypotheses costs nothing;
+//   * each lane owns E source points (N <= 32*E); the trim order is a register-resident bitonic
+//     sort of packed 32-bit keys (quantised d2 | point index) followed by an exact fix-up on the
+//     fp64 (d2, index) keys, a warp prefix scan of d2 and an arg-min of FRMSD(k);
+//   * a CTA is bound to one plot at a time: the plot's source points, its FRMSD weight tables and
+//     the WINDOW of grid cells its hypotheses can reach are staged in shared memory once and
+//     shared by all warps; a query whose search leaves the window falls back to the global grid
+//     (same exact search), so results never depend on the window;
+//   * CTAs pull (plot, slice) work from a global counter and warps pull hypotheses of the plot
+//     from a per-plot counter (dynamic load balance across the whole GPU).
+#include <algorithm>
+#include <climits>
+#include "ficp_internal.h"
+#include "nn_search.cuh"
+
+namespace ficp {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+template <int E>
+struct LaneCfg {
+    static constexpr int kNPad = 32 * E;
+    static constexpr int kIdxBits = (E == 1) ? 5 : (E == 2) ? 6 : (E == 4) ? 7 : (E == 8) ? 8 : (E == 16) ? 9 : 10;
+    static constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
+};
+
+// ---- shared-memory carve-up (host and device use the same function) -------------------------------
+struct SmemLayout {
+    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, w_cell, rowoff, rowdelta, rowg, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, int wcap_pts, int wcap_cells,
+                                                  int wcap_rows) {
+    SmemLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+    L.s_u = take((size_t)npad * 16);
+    L.w_xy = take((size_t)wcap_pts * 16);
+    L.s_z = take(z3 ? (size_t)npad * 8 : 0);
+    L.w_z = take(z3 ? (size_t)wcap_pts * 8 : 0);
+    L.s_g = take((size_t)kMaxStages * npad * 8);
+    L.sd2 = take((size_t)warps * npad * 8);
+    L.snn = take((size_t)warps * npad * 4);
+    L.w_cell = take((size_t)wcap_cells * 4);
+    L.rowoff = take((size_t)(wcap_rows + 1) * 4);
+    L.rowdelta = take((size_t)wcap_rows * 4);
+    L.rowg = take((size_t)wcap_rows * 4);
+    L.total = o;
+    return L;
+}
+
+// ---- register-resident bitonic sort of 32*E keys across one warp -----------------------------------
+// Logical position p = lane*E + r.  Steps with stride < E are compare-exchanges between registers
+// of one lane; larger strides exchange with lane ^ (stride/E) through shuffles.  Validated against
+// a numpy emulation of the same loops.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned (&key)[E], int lane) {
+    constexpr int N = 32 * E;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                const int lj = j / E;
+                const bool up = (lane & lj) != 0;
+                const bool desc = (k < N) && (((lane * E) & k) != 0);
+                const bool takemin = (up == desc);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned o = __shfl_xor_sync(kFull, key[r], lj);
+                    key[r] = takemin ? min(key[r], o) : max(key[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int l = r ^ j;
+                    if (l > r) {
+                        bool desc;
+                        if (k < E) desc = (r & k) != 0;
+                        else if (k < N) desc = ((lane * E) & k) != 0;
+                        else desc = false;
+                        const unsigned a = key[r], b = key[l];
+                        const unsigned mn = min(a, b), mx = max(a, b);
+                        key[r] = desc ? mx : mn;
+                        key[l] = desc ? mn : mx;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool key_greater(double da, unsigned ka, double db, unsigned kb) {
+    return (da > db) || (da == db && ka > kb);
+}
+
+struct Pose {  // q = M u + c ; warp-uniform
+    double m00, m01, m10, m11, cx, cy;
+};
+
+struct PassOut {
+    int k;          // trimmed subset size (0: none, like ficp.py:125)
+    double f;       // FRMSD at k
+    double rmse;    // sqrt(S_k / k)
+    double thr;     // d2 of the k-th point in trim order
+    int thr_idx;    // its source index (ties in d2 are ordered by index)
+};
+
+struct PlotCtx {
+    const double2* s_u;
+    const double* s_z;
+    int n;
+    int fixed_k;
+    double ubx, uby;
+};
+
+__device__ __forceinline__ void pose_apply(const Pose& P, const double2 u, double& qx, double& qy) {
+    // same expression, same order, no FMA, as oracle.pre_transform
+    qx = dadd(dadd(dmul(P.m00, u.x), dmul(P.m01, u.y)), P.cx);
+    qy = dadd(dadd(dmul(P.m10, u.x), dmul(P.m11, u.y)), P.cy);
+}
+
+// One NN pass + trimming for the warp's hypothesis.
+template <int E, bool Z3>
+__device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
+                                            const Pose& P, const double* __restrict__ s_g,
+                                            const double* __restrict__ g_c, double* __restrict__ sd2,
+                                            int* __restrict__ snn, int lane, unsigned& n_global, unsigned& n_fix) {
+    using C = LaneCfg<E>;
+    const int n = pc.n;
+    const GlobalAcc ga{G.xy, G.z, G.orig, G.cell_start, G.g.gw};
+
+    // ---- nearest neighbours (one query per lane per round) ----
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        double best = kInf;
+        int code = -1;
+        if (i < n) {
+            double qx, qy;
+            pose_apply(P, pc.s_u[i], qx, qy);
+            const double qz = Z3 ? pc.s_z[i] : 0.0;
+            int pos = -1;
+            bool ok = false;
+            if (win_ok) ok = nn_search<Z3>(W, G.g, qx, qy, qz, best, pos);
+            if (ok) {
+                code = pos;
+            } else {
+                nn_search<Z3>(ga, G.g, qx, qy, qz, best, pos);
+                code = (int)((unsigned)pos | 0x80000000u);
+                ++n_global;
+            }
+        }
+        sd2[i] = best;
+        snn[i] = code;
+    }
+    __syncwarp();
+
+    // ---- trim order: packed keys (monotone 32-IDXBITS-bit code of d2 | index), warp bitonic sort ----
+    unsigned key[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        const unsigned fb = __float_as_uint(__double2float_rd(sd2[i]));
+        key[e] = (i < n) ? (((fb >> (C::kIdxBits - 1)) << C::kIdxBits) | (unsigned)i) : 0xFFFFFFFFu;
+    }
+    warp_bitonic_sort<E>(key, lane);
+    double dd[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) dd[r] = sd2[key[r] & C::kIdxMask];
+
+    // ---- exact fix-up: points whose quantised codes collide are re-ordered by the true (d2, index) ----
+    for (;;) {
+        bool sw = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+#pragma unroll
+            for (int r = par; r + 1 < E; r += 2) {
+                if (key_greater(dd[r], key[r], dd[r + 1], key[r + 1])) {
+                    const double td = dd[r]; dd[r] = dd[r + 1]; dd[r + 1] = td;
+                    const unsigned tk = key[r]; key[r] = key[r + 1]; key[r + 1] = tk;
+                    sw = true;
+                }
+            }
+        }
+        if (E >= 2) {
+            // boundary pair: my last element vs the next lane's first
+            const double nd = __shfl_down_sync(kFull, dd[0], 1);
+            const unsigned nk = __shfl_down_sync(kFull, key[0], 1);
+            const double pd = __shfl_up_sync(kFull, dd[E - 1], 1);
+            const unsigned pk = __shfl_up_sync(kFull, key[E - 1], 1);
+            const bool hi = (lane < 31) && key_greater(dd[E - 1], key[E - 1], nd, nk);
+            const bool lo = (lane > 0) && key_greater(pd, pk, dd[0], key[0]);
+            if (hi) { dd[E - 1] = nd; key[E - 1] = nk; sw = true; }
+            if (lo) { dd[0] = pd; key[0] = pk; sw = true; }
+        } else {
+            // one element per lane: odd-even transposition across lanes
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const bool left = ((lane & 1) == par);  // left member of the pair (lane, lane + 1)
+                const int partner = left ? lane + 1 : lane - 1;
+                const bool valid = (partner >= 0) && (partner < 32);
+                const double od = __shfl_sync(kFull, dd[0], partner & 31);
+                const unsigned ok2 = __shfl_sync(kFull, key[0], partner & 31);
+                if (valid) {
+                    const bool doswap = left ? key_greater(dd[0], key[0], od, ok2) : key_greater(od, ok2, dd[0], key[0]);
+                    if (doswap) { dd[0] = od; key[0] = ok2; sw = true; }
+                }
+            }
+        }
+        if (!__any_sync(kFull, sw)) break;
+        ++n_fix;
+    }
+
+    // ---- inclusive prefix sums S_k of d2 in trim order ----
+    double s[E];
+    double run = 0.0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) { run += dd[r]; s[r] = run; }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    double excl = __shfl_up_sync(kFull, inc, 1);
+    if (lane == 0) excl = 0.0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) s[r] = excl + s[r];
+
+    // ---- subset size ----
+    PassOut out;
+    int kstar;
+    double fstar = kInf, rstar = 0.0;
+    if (pc.fixed_k > 0) {
+        kstar = pc.fixed_k;
+    } else {
+        // filter with G(k) = S_k * (c_k^2 / k) ~ FRMSD(k)^2 (one multiply per k) ...
+        double gbest = kInf;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const int p = lane * E + r;
+            if (p < n) gbest = fmin(gbest, s[r] * s_g[r * 32 + lane]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gbest = fmin(gbest, __shfl_xor_sync(kFull, gbest, o));
+        // ... then evaluate the reference's exact expression c_k * sqrt(S_k / k) only for the k whose G is
+        // within rounding distance of the minimum; first strict minimum wins (ficp.py:84)
+        const double gthr = gbest * (1.0 + 1e-12);
+        int kb = INT_MAX;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const int p = lane * E + r;
+            if (p < n && s[r] * s_g[r * 32 + lane] <= gthr) {
+                const int k = p + 1;
+                const double rm = sqrt(s[r] / (double)k);
+                const double f = __ldg(g_c + r * 32 + lane) * rm;
+                if (f < fstar) { fstar = f; kb = k; rstar = rm; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double of = __shfl_xor_sync(kFull, fstar, o);
+            const int ok = __shfl_xor_sync(kFull, kb, o);
+            const double orr = __shfl_xor_sync(kFull, rstar, o);
+            if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
+        }
+        kstar = (kb == INT_MAX) ? 0 : kb;
+    }
+    out.k = kstar;
+    if (kstar == 0) {
+        out.f = kInf; out.rmse = 0.0; out.thr = -1.0; out.thr_idx = -1;
+        return out;
+    }
+    // the k-th element in trim order defines the inlier set {(d2, i) <= (thr, thr_idx)}
+    const int pstar = kstar - 1, lstar = pstar / E, rsel = pstar % E;
+    double tsel = dd[0], ssel = s[0];
+    unsigned ksel = key[0];
+#pragma unroll
+    for (int r = 1; r < E; ++r)
+        if (r == rsel) { tsel = dd[r]; ksel = key[r]; ssel = s[r]; }
+    out.thr = __shfl_sync(kFull, tsel, lstar);
+    out.thr_idx = (int)(__shfl_sync(kFull, ksel, lstar) & C::kIdxMask);
+    if (pc.fixed_k > 0) {
+        const double sk = __shfl_sync(kFull, ssel, lstar);
+        rstar = sqrt(sk / (double)kstar);
+        fstar = __ldg(g_c + rsel * 32 + lstar) * rstar;
+    }
+    out.f = fstar;
+    out.rmse = rstar;
+    return out;
+}
+
+// Closed-form rigid fit on the trimmed subset and composition into the pose.
+template <int E, bool Z3>
+__device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, const PlotCtx& pc, Pose& P,
+                                        const PassOut& po, const double* __restrict__ sd2,
+                                        const int* __restrict__ snn, int lane, int allow_reflection) {
+    const int n = pc.n;
+    // shift point: the plot centroid under the current pose (keeps the running sums well conditioned)
+    const double ax = P.m00 * pc.ubx + P.m01 * pc.uby + P.cx;
+    const double ay = P.m10 * pc.ubx + P.m11 * pc.uby + P.cy;
+    double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+#pragma unroll 2
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        if (i < n) {
+            const double d2 = sd2[i];
+            if (d2 < po.thr || (d2 == po.thr && i <= po.thr_idx)) {
+                double qx, qy;
+                pose_apply(P, pc.s_u[i], qx, qy);
+                const int code = snn[i];
+                const double2 t = (code < 0) ? __ldg(G.xy + (code & 0x7FFFFFFF)) : W.xy[code];
+                const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
+                su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
+                h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        su0 += __shfl_xor_sync(kFull, su0, o); su1 += __shfl_xor_sync(kFull, su1, o);
+        sv0 += __shfl_xor_sync(kFull, sv0, o); sv1 += __shfl_xor_sync(kFull, sv1, o);
+        h00 += __shfl_xor_sync(kFull, h00, o); h01 += __shfl_xor_sync(kFull, h01, o);
+        h10 += __shfl_xor_sync(kFull, h10, o); h11 += __shfl_xor_sync(kFull, h11, o);
+    }
+    const double inv_k = 1.0 / (double)po.k;
+    const double mu0 = su0 * inv_k, mu1 = su1 * inv_k, mv0 = sv0 * inv_k, mv1 = sv1 * inv_k;
+    // centred cross-covariance H = sum (u - mu)(v - mv)^T, from the shifted sums.  When the exact H is zero
+    // (k == 1, or all inlier trees coincide - the reference's centred sums are then exactly 0 and its SVD
+    // returns R = I) the subtraction below leaves only rounding noise: detect that and use H = 0.
+    const double hscale = fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) +
+                          (fabs(su0) + fabs(su1)) * (fabs(mv0) + fabs(mv1));
+    h00 -= su0 * mv0; h01 -= su0 * mv1; h10 -= su1 * mv0; h11 -= su1 * mv1;
+    if (fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) <= 1e-12 * hscale) h00 = h01 = h10 = h11 = 0.0;
+    double r00, r01, r10, r11;
+    // reflection only when det(H) is negative beyond rounding noise (det == 0: SVD's choice is arbitrary)
+    if (allow_reflection && (h00 * h11 - h01 * h10) < -1e-14 * (fabs(h00 * h11) + fabs(h01 * h10))) {
+        const double a = h00 - h11, b = h01 + h10, nrm = sqrt(a * a + b * b);
+        const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
+        r00 = c; r01 = s; r10 = s; r11 = -c;
+    } else {
+        const double a = h00 + h11, b = h01 - h10, nrm = sqrt(a * a + b * b);
+        const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
+        r00 = c; r01 = -s; r10 = s; r11 = c;
+    }
+    // q' = R (q - a - mu) + a + mv   with q = M u + c   ->   M' = R M ;  c' = R (c - a - mu) + a + mv
+    const double ex = P.cx - ax - mu0, ey = P.cy - ay - mu1;
+    Pose Q;
+    Q.m00 = r00 * P.m00 + r01 * P.m10; Q.m01 = r00 * P.m01 + r01 * P.m11;
+    Q.m10 = r10 * P.m00 + r11 * P.m10; Q.m11 = r10 * P.m01 + r11 * P.m11;
+    Q.cx = (r00 * ex + r01 * ey) + (ax + mv0);
+    Q.cy = (r10 * ex + r11 * ey) + (ay + mv1);
+    P = Q;
+}
+
+template <int E, bool Z3, int NT>
+__global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
+    using C = LaneCfg<E>;
+    constexpr int NPAD = C::kNPad;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const SmemLayout L = smem_layout(NPAD, Z3, nwarps, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    double2* s_u = reinterpret_cast<double2*>(smem + L.s_u);
+    double2* w_xy = reinterpret_cast<double2*>(smem + L.w_xy);
+    double* s_z = reinterpret_cast<double*>(smem + L.s_z);
+    double* w_z = reinterpret_cast<double*>(smem + L.w_z);
+    double* s_g = reinterpret_cast<double*>(smem + L.s_g);
+    double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)warp * NPAD;
+    int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)warp * NPAD;
+    unsigned* w_cell = reinterpret_cast<unsigned*>(smem + L.w_cell);
+    int* rowoff = reinterpret_cast<int*>(smem + L.rowoff);
+    int* rowdelta = reinterpret_cast<int*>(smem + L.rowdelta);
+    int* rowg = reinterpret_cast<int*>(smem + L.rowg);
+    __shared__ int sh_slice;
+    __shared__ int sh_win_ok;
+
+    const GridView& G = P.grid;
+    int staged_plot = -1;
+    unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0;
+
+    for (;;) {
+        __syncthreads();  // everyone is done with the previous slice (and with sh_slice)
+        if (threadIdx.x == 0) sh_slice = atomicAdd(P.slice_counter, 1);
+        __syncthreads();
+        const int slice = sh_slice;
+        if (slice >= P.n_slices) break;
+        const int plot = slice / P.slices_per_plot;
+        const PlotMeta pm = P.plots[plot];
+
+        if (plot != staged_plot) {
+            // ---- stage the plot: source rows, weight tables, window of grid cells ----
+            for (int i = threadIdx.x; i < NPAD; i += blockDim.x) {
+                s_u[i] = (i < pm.n) ? P.src_u[pm.off + i] : make_double2(0.0, 0.0);
+                if (Z3) s_z[i] = (i < pm.n) ? P.src_z[pm.off + i] : 0.0;
+            }
+            const double* tab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NPAD;
+            for (int i = threadIdx.x; i < P.n_stages * NPAD; i += blockDim.x)
+                s_g[i] = tab[(size_t)(i / NPAD) * 2 * NPAD + (i % NPAD)];
+            const int ww = pm.wx1 - pm.wx0, wh = pm.wy1 - pm.wy0;
+            bool ok = (ww > 0 && wh > 0 && (long long)ww * wh <= P.wcap_cells && wh <= P.wcap_rows && G.m > 0);
+            if (ok) {
+                for (int r = threadIdx.x; r < wh; r += blockDim.x) {
+                    const size_t rowbase = (size_t)(pm.wy0 + r) * G.g.gw;
+                    const unsigned gs = G.cell_start[rowbase + pm.wx0], ge = G.cell_start[rowbase + pm.wx1];
+                    rowg[r] = (int)gs;
+                    rowdelta[r] = (int)(ge - gs);  // temporarily: the row's point count
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (ok) {
+                    int o = 0;
+                    for (int r = 0; r < wh; ++r) {
+                        const int cnt = rowdelta[r];
+                        rowoff[r] = o;
+                        rowdelta[r] = rowg[r] - o;
+                        o += cnt;
+                    }
+                    rowoff[wh] = o;
+                    if (o > P.wcap_pts || o > 65535) ok = false;
+                }
+                sh_win_ok = ok ? 1 : 0;
+                if (!ok) atomicAdd(P.stats + 2, 1ull);
+            }
+            __syncthreads();
+            ok = (sh_win_ok != 0);
+            if (ok) {
+                for (int c = threadIdx.x; c < ww * wh; c += blockDim.x) {
+                    const int r = c / ww, col = c - r * ww;
+                    const size_t g = (size_t)(pm.wy0 + r) * G.g.gw + pm.wx0 + col;
+                    const unsigned a = G.cell_start[g], b = G.cell_start[g + 1];
+                    w_cell[c] = (unsigned)(rowoff[r] + (int)(a - (unsigned)rowg[r])) | ((b - a) << 16);
+                }
+                for (int r = warp; r < wh; r += nwarps) {
+                    const int cnt = rowoff[r + 1] - rowoff[r], gs = rowg[r], lo = rowoff[r];
+                    for (int j = lane; j < cnt; j += 32) {
+                        w_xy[lo + j] = G.xy[gs + j];
+                        if (Z3) w_z[lo + j] = G.z[gs + j];
+                    }
+                }
+            }
+            staged_plot = plot;
+            __syncthreads();
+        }
+        const bool win_ok = (sh_win_ok != 0);
+        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G.orig,
+                          pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0};
+        const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
+        const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NPAD;  // [stage][0]=g [stage][1]=c
+
+        // ---- warps pull hypotheses of this plot until none are left ----
+        for (;;) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(P.hyp_counter + plot, 1);
+            j = __shfl_sync(kFull, j, 0);
+            if (j >= P.n_hyp_local) break;
+            const int h = P.hyp_begin + j * P.hyp_stride;
+            const double* hr = P.hyp + (size_t)h * 6;
+            Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
+            unsigned n_global = 0, n_fix = 0;
+            int passes = 0;
+            PassOut po{0, kInf, 0.0, -1.0, -1};
+            for (int st = 0; st < P.n_stages; ++st) {
+                const double* sg = s_g + (size_t)st * NPAD;
+                const double* gc = g_ctab + ((size_t)st * 2 + 1) * NPAD;
+                // ficp.py:122-147 with ONE call site for the pass:
+                //   pass; [first: k==0 -> stage ends | else: converged -> stage ends]; it == max -> ends; fit; repeat
+                double cur = 0.0;
+                int it = 0;
+                bool first = true;
+                for (;;) {
+                    po = icp_pass<E, Z3>(G, W, win_ok, pc, pose, sg, gc, sd2, snn, lane, n_global, n_fix);
+                    ++passes;
+                    if (first) {
+                        if (po.k == 0) break;  // ficp.py:125-126
+                        cur = po.f;
+                        first = false;
+                    } else {
+                        if (cur - po.f <= P.threshold) break;  // also stops on a regression, keeping the pose (ficp.py:142)
+                        cur = po.f;
+                        ++it;
+                    }
+                    if (it >= P.max_iter) break;
+                    icp_fit<E, Z3>(G, W, pc, pose, po, sd2, snn, lane, P.allow_reflection);
+                    __syncwarp();
+                }
+                __syncwarp();
+            }
+            // ---- results ----
+            n_global = __reduce_add_sync(kFull, n_global);  // counted per lane
+            const size_t ridx = (size_t)plot * P.n_hyp_local + j;
+            if (lane == 0) {
+                HypResult r;
+                r.m00 = pose.m00; r.m01 = pose.m01; r.m10 = pose.m10; r.m11 = pose.m11;
+                r.cx = pose.cx; r.cy = pose.cy;
+                r.frmsd = po.f; r.rmse = po.rmse; r.k = po.k; r.passes = passes;
+                r.flags = (n_global ? 1 : 0) | (win_ok ? 0 : 2);
+                r.pad = 0;
+                P.results[ridx] = r;
+                const float score = (po.k >= P.min_k && po.k > 0) ? (float)po.f : __int_as_float(0x7F800000);
+                const unsigned long long bk = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)h;
+                atomicMin(P.best_key + plot, bk);
+            }
+            if (P.final_xy && P.n_hyp_local == 1) {
+                for (int i = lane; i < pm.n; i += 32) {
+                    double qx, qy;
+                    pose_apply(pose, s_u[i], qx, qy);
+                    P.final_xy[(pm.off + i) * 2] = qx;
+                    P.final_xy[(pm.off + i) * 2 + 1] = qy;
+                }
+            }
+            acc_passes += passes; acc_global += n_global; acc_fix += n_fix;
+            acc_queries += (unsigned long long)passes * pm.n;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && acc_passes) {
+        atomicAdd(P.stats + 0, acc_passes);
+        atomicAdd(P.stats + 1, acc_global);
+        atomicAdd(P.stats + 3, acc_fix);
+        atomicAdd(P.stats + 4, acc_queries);
+    }
+}
+
+template <int E, bool Z3>
+struct KernelFor {
+    // threads per CTA the kernel is compiled for (register budget = 64K / NT)
+    static constexpr int kNT = (E >= 32) ? 384 : (E >= 16) ? 512 : 512;
+};
+
+template <int E, bool Z3>
+int launch_one(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream) {
+    constexpr int NT = KernelFor<E, Z3>::kNT;
+    if (l.warps * 32 > NT) {
+        set_error("launch_icp: too many warps per CTA for this instantiation");
+        return kErrInvalid;
+    }
+    auto kern = icp_kernel<E, Z3, NT>;
+    FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
+    kern<<<l.ctas, l.warps * 32, l.smem, stream>>>(p);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+template <int E, bool Z3>
+int occupancy_one(int warps, size_t smem, int* out) {
+    constexpr int NT = KernelFor<E, Z3>::kNT;
+    auto kern = icp_kernel<E, Z3, NT>;
+    FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, warps * 32, smem));
+    return kOk;
+}
+
+}  // namespace
+
+size_t icp_smem_bytes(int e, bool z3, int warps, int wcap_pts, int wcap_cells, int wcap_rows) {
+    return smem_layout(32 * e, z3, warps, wcap_pts, wcap_cells, wcap_rows).total;
+}
+
+int icp_max_warps(int e) { return (e >= 32) ? 12 : 16; }  // = KernelFor<E>::kNT / 32
+
+#define FICP_DISPATCH(FN, ...)                                                                    \
+    switch (e) {                                                                                  \
+        case 1: return z3 ? FN<1, true>(__VA_ARGS__) : FN<1, false>(__VA_ARGS__);                 \
+        case 2: return z3 ? FN<2, true>(__VA_ARGS__) : FN<2, false>(__VA_ARGS__);                 \
+        case 4: return z3 ? FN<4, true>(__VA_ARGS__) : FN<4, false>(__VA_ARGS__);                 \
+        case 8: return z3 ? FN<8, true>(__VA_ARGS__) : FN<8, false>(__VA_ARGS__);                 \
+        case 16: return z3 ? FN<16, true>(__VA_ARGS__) : FN<16, false>(__VA_ARGS__);              \
+        case 32: return z3 ? FN<32, true>(__VA_ARGS__) : FN<32, false>(__VA_ARGS__);              \
+        default: set_error("launch_icp: unsupported elements-per-lane"); return kErrInvalid;      \
+    }
+
+int icp_max_ctas_per_sm(int e, bool z3, int warps, size_t smem, int* out) {
+    FICP_DISPATCH(occupancy_one, warps, smem, out)
+}
+
+int launch_icp(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream) {
+    const int e = l.e;
+    const bool z3 = l.z3;
+    FICP_DISPATCH(launch_one, p, l, stream)
+}
+
+}  // namespace ficp

@@ -1,0 +1,53 @@
+// Kernel 1b (standalone form): bulk nearest-neighbour query against a built target index.
+//
+// Replaces `tree.query(self._xyz_or_xy(source), k=1)` + `target[idx]` of
+// /root/reference/ficp.py:70-71 for callers that use FractionalICP.find_correspondences directly.
+// One thread per query over the global (L2-resident) grid; the persistent ICP kernel uses the same
+// search routine through a shared-memory window instead (icp_persistent.cu).
+//
+// Outputs per query: original target index (lowest index among exact ties), Euclidean distance
+// sqrt(d2) (IEEE, identical bits to scipy) and optionally d2 itself.
+#include "ficp_internal.h"
+#include "nn_search.cuh"
+
+namespace ficp {
+
+namespace {
+
+template <bool Z3>
+__global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double* __restrict__ q, long long n, int ld,
+                                                       int* __restrict__ idx, double* __restrict__ dist,
+                                                       double* __restrict__ d2out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qx = q[i * ld], qy = q[i * ld + 1];
+    const double qz = Z3 ? q[i * ld + 2] : 0.0;
+    const GlobalAcc acc{v.xy, v.z, v.orig, v.cell_start, v.g.gw};
+    double best;
+    int pos;
+    nn_search<Z3>(acc, v.g, qx, qy, qz, best, pos);
+    idx[i] = __ldg(v.orig + pos);
+    if (dist) dist[i] = sqrt(best);
+    if (d2out) d2out[i] = best;
+}
+
+}  // namespace
+
+int launch_nn_query(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
+                    double* d_d2, cudaStream_t stream) {
+    if (n <= 0) return kOk;
+    if (v.m <= 0) {
+        set_error("nn_query: empty target");
+        return kErrInvalid;
+    }
+    const int t = 128;
+    const unsigned nb = (unsigned)((n + t - 1) / t);
+    if (z3)
+        nn_query_kernel<true><<<nb, t, 0, stream>>>(v, d_q, n, ld, d_idx, d_dist, d_d2);
+    else
+        nn_query_kernel<false><<<nb, t, 0, stream>>>(v, d_q, n, ld, d_idx, d_dist, d_d2);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+}  // namespace ficp

@@ -1,0 +1,165 @@
+// Exact nearest-neighbour search over the uniform grid (replaces scipy.spatial.cKDTree build +
+// query(k=1) at /root/reference/ficp.py:69-70).
+//
+// One thread resolves one query.  The search visits the query's own cell, then rings of cells of
+// growing Chebyshev radius, and stops as soon as the best distance found is strictly smaller than
+// the distance from the query to the border of the block of cells already visited - so the result
+// is the exact NN over ALL target points, not an approximate one.  Cell segments whose box is
+// farther than the current best are skipped.  Exact distance ties resolve to the LOWEST ORIGINAL
+// INDEX (stricter than the reference, whose tie choice depends on kd-tree traversal order).
+//
+// The code is accessor-generic: `GlobalAcc` reads the cell-sorted target from global memory
+// (L2-resident), `WindowAcc` reads a per-plot window of cells staged in shared memory.  It is also
+// host-compilable (tests/hostcheck) so the ring / termination logic is unit-tested on the CPU.
+#pragma once
+#include "ficp_common.cuh"
+
+namespace ficp {
+
+#if defined(__CUDA_ARCH__)
+#define FICP_LDG(p) __ldg(p)
+#else
+#define FICP_LDG(p) (*(p))
+#endif
+
+struct GlobalAcc {
+    const double2* xy;
+    const double* z;
+    const int* org;
+    const unsigned* cell_start;
+    int gw;
+
+    FICP_HD bool covers(int, int, int, int) const { return true; }
+    FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
+        const unsigned* row = cell_start + (size_t)y * gw;
+        s = (int)FICP_LDG(row + xa);
+        e = (int)FICP_LDG(row + xb + 1);
+    }
+    template <bool Z3>
+    FICP_HD void load(int j, double& x, double& y, double& zz) const {
+        const double2 p = FICP_LDG(xy + j);
+        x = p.x;
+        y = p.y;
+        if (Z3) zz = FICP_LDG(z + j);
+    }
+    FICP_HD int orig(int j) const { return FICP_LDG(org + j); }
+};
+
+// Window of cells [wx0,wx1) x [wy0,wy1) copied to shared memory.  cell[] packs
+// (first local position | count << 16) per window cell; rows are stored back to back, so a run of
+// cells within one row is one contiguous range of points.
+struct WindowAcc {
+    const double2* xy;     // shared
+    const double* z;       // shared
+    const unsigned* cell;  // shared
+    const int* rowoff;     // shared: first local position of each window row (+ total at [wh])
+    const int* rowdelta;   // shared: global sorted position = local position + rowdelta[row]
+    const int* gorg;       // global: original indices of the sorted target
+    int wx0, wy0, wx1, wy1, ww, wh;
+
+    FICP_HD bool covers(int xl, int xh, int yl, int yh) const {
+        return xl >= wx0 && xh < wx1 && yl >= wy0 && yh < wy1;
+    }
+    FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
+        const unsigned* row = cell + (y - wy0) * ww - wx0;
+        const unsigned c0 = row[xa];
+        s = (int)(c0 & 0xFFFFu);
+        const unsigned c1 = (xb == xa) ? c0 : row[xb];
+        e = (int)(c1 & 0xFFFFu) + (int)(c1 >> 16);
+    }
+    template <bool Z3>
+    FICP_HD void load(int j, double& x, double& y, double& zz) const {
+        const double2 p = xy[j];
+        x = p.x;
+        y = p.y;
+        if (Z3) zz = z[j];
+    }
+    FICP_HD int global_pos(int j) const {  // rare path (exact ties, final index lookup)
+        int lo = 0, hi = wh - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rowoff[mid] <= j) lo = mid; else hi = mid - 1;
+        }
+        return j + rowdelta[lo];
+    }
+    FICP_HD int orig(int j) const { return FICP_LDG(gorg + global_pos(j)); }
+};
+
+template <bool Z3, class Acc>
+FICP_HD void nn_scan_segment(const Acc& acc, int y, int xa, int xb, double qx, double qy, double qz,
+                             double& best, int& bestpos) {
+    int s, e;
+    acc.seg(y, xa, xb, s, e);
+    for (int j = s; j < e; ++j) {
+        double tx, ty, tz = 0.0;
+        acc.template load<Z3>(j, tx, ty, tz);
+        const double dx = dsub(qx, tx);
+        const double dy = dsub(qy, ty);
+        double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+        if (Z3) {
+            const double dz = dsub(qz, tz);
+            d2 = dadd(d2, dmul(dz, dz));
+        }
+        if (d2 <= best) {
+            if (d2 < best || bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) {
+                best = d2;
+                bestpos = j;
+            }
+        }
+    }
+}
+
+template <bool Z3, class Acc>
+FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, int xb, double qx, double qy,
+                            double qz, double& best, int& bestpos) {
+    // distance from the query to the (slightly inflated) box of the segment; skip when it cannot
+    // hold a point at distance <= best (ties must still be seen for the lowest-index rule)
+    const double bx0 = g.x0 + xa * g.h - g.eps, bx1 = g.x0 + (xb + 1) * g.h + g.eps;
+    const double by0 = g.y0 + y * g.h - g.eps, by1 = g.y0 + (y + 1) * g.h + g.eps;
+    const double dx = fmax(fmax(bx0 - qx, qx - bx1), 0.0);
+    const double dy = fmax(fmax(by0 - qy, qy - by1), 0.0);
+    if (dx * dx + dy * dy > best) return;
+    nn_scan_segment<Z3>(acc, y, xa, xb, qx, qy, qz, best, bestpos);
+}
+
+// Returns false when the search needs cells the accessor does not cover (window miss): the
+// caller then repeats the query with GlobalAcc.  On success best = squared distance (canonical
+// arithmetic) and bestpos = accessor-local position of the winner.
+template <bool Z3, class Acc>
+FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, double& best,
+                       int& bestpos) {
+    const int cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+    const int cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+    best = kInf;
+    bestpos = -1;
+    if (!acc.covers(cx, cx, cy, cy)) return false;
+    nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
+    for (int r = 1;; ++r) {
+        // every unvisited point lies outside the block of radius r-1: lower-bound its distance
+        const int xl = cx - (r - 1), xh = cx + (r - 1), yl = cy - (r - 1), yh = cy + (r - 1);
+        double b = kInf;
+        if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
+        if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
+        if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
+        if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
+        if (b == kInf) break;  // the block already spans the whole grid
+        b -= g.eps;
+        if (b > 0.0 && best < b * b) break;
+        const int nxl = (cx - r > 0) ? cx - r : 0;
+        const int nxh = (cx + r < g.gw - 1) ? cx + r : g.gw - 1;
+        const int nyl = (cy - r > 0) ? cy - r : 0;
+        const int nyh = (cy + r < g.gh - 1) ? cy + r : g.gh - 1;
+        if (!acc.covers(nxl, nxh, nyl, nyh)) return false;
+        for (int y = nyl; y <= nyh; ++y) {
+            if (y == cy - r || y == cy + r) {
+                nn_try_segment<Z3>(acc, g, y, nxl, nxh, qx, qy, qz, best, bestpos);
+            } else {
+                if (cx - r >= 0) nn_try_segment<Z3>(acc, g, y, cx - r, cx - r, qx, qy, qz, best, bestpos);
+                if (cx + r <= g.gw - 1) nn_try_segment<Z3>(acc, g, y, cx + r, cx + r, qx, qy, qz, best, bestpos);
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace ficp

@@ -1,0 +1,256 @@
+// Stand-alone stage kernels behind the per-method API of FractionalICP (the persistent kernel in
+// icp_persistent.cu fuses the same stages for the batched path):
+//
+//   select_fraction  <- find_optimal_fraction / get_n_first_elements  (/root/reference/ficp.py:62-63,73-86)
+//   fit_rigid2d      <- compute_optimal_transform_2d                  (ficp.py:89-110)
+//   apply_xy         <- apply_transform_2d_xy_only                    (ficp.py:112-119)
+//   sumsq            <- the sum inside frmsd                          (ficp.py:58-59)
+//
+// Each runs as ONE CTA: the inputs are a single plot (N <= 8192 trees); K = 2 Procrustes is eight
+// running sums, so there is no dense contraction for tensor cores here.
+#include "ficp_internal.h"
+
+namespace ficp {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 doubles */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += sh[i];  // same order in every thread -> identical bits
+    return s;
+}
+
+__device__ __forceinline__ double sqdiff(const double* a, const double* b, int md) {
+    const double dx = dsub(a[0], b[0]), dy = dsub(a[1], b[1]);
+    double s = dadd(dmul(dx, dx), dmul(dy, dy));
+    if (md == 3) {
+        const double dz = dsub(a[2], b[2]);
+        s = dadd(s, dmul(dz, dz));
+    }
+    return s;
+}
+
+// ---- select_fraction ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) select_fraction_kernel(const double* __restrict__ src, int ld_s,
+                                                               const double* __restrict__ corr, int ld_c,
+                                                               const double* __restrict__ dist, int n, int npad,
+                                                               int md, const double* __restrict__ w, int fixed_k,
+                                                               long long* __restrict__ k_out,
+                                                               double* __restrict__ f_out,
+                                                               int* __restrict__ order_out) {
+    extern __shared__ double sm[];
+    double* key = sm;
+    double* pre = sm + npad;
+    int* idx = reinterpret_cast<int*>(sm + 2 * npad);
+    __shared__ double red[32];
+    __shared__ double red_f[32];
+    __shared__ int red_k[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int i = tid; i < npad; i += nt) {
+        key[i] = (i < n) ? dist[i] : kInf;
+        idx[i] = i;
+    }
+    __syncthreads();
+    // bitonic sort of (distance, index): the index makes the order stable (lowest index first)
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += nt) {
+                const int i = ((t / j) * 2 * j) + (t % j);
+                const int l = i + j;
+                const bool asc = ((i & k) == 0);
+                const double ka = key[i], kb = key[l];
+                const int ia = idx[i], ib = idx[l];
+                const bool gt = (ka > kb) || (ka == kb && ia > ib);
+                if (gt == asc) {
+                    key[i] = kb; key[l] = ka;
+                    idx[i] = ib; idx[l] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (order_out)
+        for (int i = tid; i < n; i += nt) order_out[i] = idx[i];
+    if (!src) return;
+
+    // squared residuals in trim order, then an inclusive scan (thread t owns a contiguous chunk)
+    for (int i = tid; i < npad; i += nt)
+        pre[i] = (i < n) ? sqdiff(src + (size_t)idx[i] * ld_s, corr + (size_t)idx[i] * ld_c, md) : 0.0;
+    __syncthreads();
+    const int chunk = (npad + nt - 1) / nt;
+    const int b0 = tid * chunk;
+    double loc = 0.0;
+    for (int j = 0; j < chunk; ++j)
+        if (b0 + j < npad) loc += pre[b0 + j];
+    // exclusive scan of `loc` over the block
+    double inc = loc;
+    const int l = tid & 31, wq = tid >> 5, nw = (nt + 31) >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, inc, o);
+        if (l >= o) inc += t;
+    }
+    if (l == 31) red[wq] = inc;
+    __syncthreads();
+    double base = 0.0;
+    for (int i = 0; i < wq && i < nw; ++i) base += red[i];
+    double run = base + inc - loc;
+    double fbest = kInf;
+    int kbest = 0;
+    for (int j = 0; j < chunk; ++j) {
+        const int i = b0 + j;
+        if (i < npad) {
+            run += pre[i];
+            if (i < n) {
+                const int k = i + 1;
+                const double f = w[i] * sqrt(run / (double)k);
+                if (fixed_k > 0) {
+                    if (k == fixed_k) { fbest = f; kbest = k; }
+                } else if (f < fbest) {  // first strict minimum (ficp.py:84)
+                    fbest = f;
+                    kbest = k;
+                }
+            }
+        }
+    }
+    // block arg-min: smallest value, ties to the smallest k
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double of = __shfl_xor_sync(kFull, fbest, o);
+        const int ok = __shfl_xor_sync(kFull, kbest, o);
+        if (ok != 0 && (kbest == 0 || of < fbest || (of == fbest && ok < kbest))) { fbest = of; kbest = ok; }
+    }
+    if (l == 0) { red_f[wq] = fbest; red_k[wq] = kbest; }
+    __syncthreads();
+    if (tid == 0) {
+        double f = kInf; int k = 0;
+        for (int i = 0; i < nw; ++i)
+            if (red_k[i] != 0 && (k == 0 || red_f[i] < f || (red_f[i] == f && red_k[i] < k))) { f = red_f[i]; k = red_k[i]; }
+        *k_out = k;
+        *f_out = (k == 0) ? kInf : f;
+    }
+}
+
+// ---- rigid 2-D fit -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fit_rigid2d_kernel(const double* __restrict__ src, int ld_s,
+                                                          const double* __restrict__ tgt, int ld_t,
+                                                          const int* __restrict__ sel, int k, int allow_reflection,
+                                                          double* __restrict__ T9) {
+    __shared__ double red[32];
+    double sx = 0, sy = 0, tx = 0, ty = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const size_t r = sel ? (size_t)sel[i] : (size_t)i;
+        sx += src[r * ld_s]; sy += src[r * ld_s + 1];
+        tx += tgt[r * ld_t]; ty += tgt[r * ld_t + 1];
+    }
+    const double csx = block_sum(sx, red) / k, csy = block_sum(sy, red) / k;
+    const double ctx = block_sum(tx, red) / k, cty = block_sum(ty, red) / k;
+    double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const size_t r = sel ? (size_t)sel[i] : (size_t)i;
+        const double ux = src[r * ld_s] - csx, uy = src[r * ld_s + 1] - csy;
+        const double vx = tgt[r * ld_t] - ctx, vy = tgt[r * ld_t + 1] - cty;
+        h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
+    }
+    h00 = block_sum(h00, red); h01 = block_sum(h01, red); h10 = block_sum(h10, red); h11 = block_sum(h11, red);
+    if (threadIdx.x == 0) {
+        double r00, r01, r10, r11;
+        // reflection only when det(H) is negative beyond rounding noise (det == 0: SVD's choice is arbitrary)
+    if (allow_reflection && (h00 * h11 - h01 * h10) < -1e-14 * (fabs(h00 * h11) + fabs(h01 * h10))) {
+            const double a = h00 - h11, b = h01 + h10, nrm = hypot(a, b);
+            const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
+            r00 = c; r01 = s; r10 = s; r11 = -c;
+        } else {
+            const double a = h00 + h11, b = h01 - h10, nrm = hypot(a, b);
+            const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
+            r00 = c; r01 = -s; r10 = s; r11 = c;
+        }
+        T9[0] = r00; T9[1] = r01; T9[2] = ctx - (r00 * csx + r01 * csy);
+        T9[3] = r10; T9[4] = r11; T9[5] = cty - (r10 * csx + r11 * csy);
+        T9[6] = 0.0; T9[7] = 0.0; T9[8] = 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) apply_xy_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                       long long n, int ld, const double* __restrict__ T9) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i * ld], y = in[i * ld + 1];
+    for (int c = 2; c < ld; ++c) out[i * ld + c] = in[i * ld + c];  // other columns: bit-identical copy
+    out[i * ld] = dadd(dadd(dmul(T9[0], x), dmul(T9[1], y)), T9[2]);
+    out[i * ld + 1] = dadd(dadd(dmul(T9[3], x), dmul(T9[4], y)), T9[5]);
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ a, int ld_a,
+                                                    const double* __restrict__ b, int ld_b,
+                                                    const int* __restrict__ sel, int k, int md,
+                                                    double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const size_t r = sel ? (size_t)sel[i] : (size_t)i;
+        s += sqdiff(a + r * ld_a, b + r * ld_b, md);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *out = s;
+}
+
+}  // namespace
+
+int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, int ld_c, const double* d_dist,
+                           int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,
+                           double* d_frmsd_out, int* d_order_out, cudaStream_t stream) {
+    if (n <= 0) return kOk;
+    if (n > kSelectMaxN) {
+        set_error("select_fraction: more than 8192 points per plot are not supported");
+        return kErrTooLarge;
+    }
+    int npad = 2;
+    while (npad < n) npad <<= 1;
+    const size_t smem = (size_t)npad * (2 * sizeof(double) + sizeof(int));
+    static bool attr_set = false;
+    if (!attr_set) {
+        FICP_CUDA(cudaFuncSetAttribute(select_fraction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSelectMaxN * (2 * sizeof(double) + sizeof(int))));
+        attr_set = true;
+    }
+    int nt = npad / 2;
+    if (nt < 32) nt = 32;
+    if (nt > 1024) nt = 1024;
+    select_fraction_kernel<<<1, nt, smem, stream>>>(d_src, ld_s, d_corr, ld_c, d_dist, n, npad, md, d_weights, fixed_k,
+                                                    d_k_out, d_frmsd_out, d_order_out);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int launch_fit_rigid2d(const double* d_src, int ld_s, const double* d_tgt, int ld_t, const int* d_sel, int k,
+                       int allow_reflection, double* d_T9, cudaStream_t stream) {
+    fit_rigid2d_kernel<<<1, 256, 0, stream>>>(d_src, ld_s, d_tgt, ld_t, d_sel, k, allow_reflection, d_T9);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int launch_apply_xy(const double* d_in, double* d_out, long long n, int ld, const double* d_T9, cudaStream_t stream) {
+    if (n <= 0) return kOk;
+    apply_xy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_in, d_out, n, ld, d_T9);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int launch_sumsq(const double* d_a, int ld_a, const double* d_b, int ld_b, const int* d_sel, int k, int md,
+                 double* d_out, cudaStream_t stream) {
+    sumsq_kernel<<<1, 256, 0, stream>>>(d_a, ld_a, d_b, ld_b, d_sel, k, md, d_out);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+}  // namespace ficp

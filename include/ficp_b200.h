@@ -1,0 +1,150 @@
+/* libficp_b200 - C ABI of the B200-native Fractional-ICP hot path.
+ *
+ * Drop-in boundary for `FractionalICP` of Silviculturalist/CoRegistrationGame (ficp.py:5-154,
+ * called from app.py:658-661).  The reference has no native code, so there is no existing FFI to
+ * mirror symbol-for-symbol; each entry point below names the reference method it replaces.  The
+ * Python class in coregistrationgame_b200/ficp.py binds these with ctypes (INTEGRATION.md shows the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or a negative status:
+ *       -1 invalid argument   -2 non-finite coordinate   -3 CUDA failure   -4 size not supported
+ *       -5 no CUDA device
+ *     and ficp_last_error() returns a human-readable message for the calling thread.
+ *   - "host" pointers are caller-owned CPU buffers (numpy arrays); functions ending in _device
+ *     take device pointers and only enqueue work on `stream` (a cudaStream_t passed as void*,
+ *     NULL = default stream).
+ *   - point arrays are row-major float64 with `ld` doubles per row; columns 0,1 are X,Y and
+ *     column 2 (when use_z != 0) is the height Z.  Z enters distances only, it is never moved.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with -5/-3.
+ */
+#ifndef FICP_B200_H
+#define FICP_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FICP_API __attribute__((visibility("default")))
+#else
+#define FICP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ficp_target ficp_target; /* built index over the Layer-2 (CHM) points */
+typedef struct ficp_batch ficp_batch;   /* plots x start-pose hypotheses resident on the device */
+
+typedef struct {
+    int64_t m;            /* target points */
+    int32_t has_z;
+    int32_t grid_w, grid_h;
+    double cell;          /* cell edge */
+    double x0, y0;        /* grid origin */
+    double bbox[4];       /* xmin xmax ymin ymax */
+    double build_ms;      /* device time of the build kernels */
+} ficp_target_info;
+
+typedef struct {
+    int32_t n_stages;          /* 1 or 2 (run() = 2 stages, _iterate() = 1) */
+    int32_t max_iterations;    /* per stage, ficp.py:12 */
+    int32_t allow_reflection;  /* ficp.py:13 */
+    int32_t min_k;             /* hypotheses ending with fewer inliers are not ranked */
+    double threshold;          /* ficp.py:11 */
+    double window_margin;      /* metres of slack around a plot's footprint staged on-chip; <0 = auto */
+    int32_t warps_per_cta;     /* 0 = auto */
+    int32_t ctas_per_sm;       /* 0 = auto */
+    int32_t disable_window;    /* 1 = never stage a window (every query walks the global grid); for tests */
+    int32_t reserved;
+} ficp_batch_params;
+
+typedef struct {
+    double m00, m01, m10, m11; /* final = M (p - centre) + c */
+    double cx, cy;
+    double frmsd, rmse;        /* FRMSD and trimmed RMSE of the last pass */
+    int32_t k;                 /* trimmed subset size of the last pass */
+    int32_t passes;            /* NN passes executed = hypothesis-iterations */
+    int32_t flags;             /* bit0: some query used the global grid, bit1: window disabled */
+    int32_t pad;
+} ficp_hyp_result;
+
+typedef struct {
+    int32_t n_plots, n_hyp, n_hyp_local;
+    int32_t elems_per_lane, match_z, warps_per_cta, ctas, ctas_per_sm, slices_per_plot;
+    int32_t window_pts_cap, window_cells_cap;
+    int64_t smem_bytes;
+    int64_t rows;
+} ficp_batch_info;
+
+FICP_API const char* ficp_last_error(void);
+FICP_API int ficp_device_count(int32_t* n);
+FICP_API int ficp_set_device(int32_t device);
+/* sms, L2 bytes, opt-in shared memory per block, SM clock kHz */
+FICP_API int ficp_device_props(int32_t* sms, int64_t* l2_bytes, int64_t* smem_optin, int32_t* clock_khz);
+
+/* ---- kernel 1a: grid build.  Replaces cKDTree(target) (ficp.py:69), hoisted out of the loop. */
+FICP_API int ficp_target_create(const double* pts_host, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
+                       void* stream, ficp_target** out);
+FICP_API int ficp_target_create_device(const double* pts_dev, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
+                              void* stream, ficp_target** out);
+FICP_API int ficp_target_get_info(const ficp_target* t, ficp_target_info* info);
+FICP_API void ficp_target_destroy(ficp_target* t);
+
+/* ---- kernel 1b: NN query.  Replaces tree.query(source, k=1) (ficp.py:70).
+ * idx_out: original target row (lowest index among exact ties); dist_out: Euclidean distance. */
+FICP_API int ficp_nn_query(const ficp_target* t, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
+                  int64_t* idx_out, double* dist_out, void* stream);
+FICP_API int ficp_nn_query_device(const ficp_target* t, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
+                         int32_t* idx_dev, double* dist_dev, void* stream);
+
+/* ---- kernel 2: trimming.  Replaces find_optimal_fraction / get_n_first_elements (ficp.py:62-63,73-86).
+ * weights[k-1] = 1/((k/n)**lambda) (computed by the caller with the reference's own expression).
+ * fixed_k > 0 selects a fixed subset size instead of the FRMSD-optimal one.  src/corr may be NULL
+ * to obtain only the stable (distance, index) order.  n <= 8192. */
+FICP_API int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* corr_host, int32_t ld_c,
+                         const double* dist_host, int64_t n, int32_t md, const double* weights_host,
+                         int64_t fixed_k, int64_t* k_out, double* frmsd_out, int64_t* order_out);
+
+/* ---- kernel 3: closed-form rigid 2-D fit.  Replaces compute_optimal_transform_2d (ficp.py:89-110).
+ * T9: row-major 3x3 homogeneous transform. */
+FICP_API int ficp_fit_rigid2d(const double* src_host, int32_t ld_s, const double* tgt_host, int32_t ld_t, int64_t k,
+                     int32_t allow_reflection, double* T9);
+/* Replaces apply_transform_2d_xy_only (ficp.py:112-119): XY moved, other columns copied bit-identically. */
+FICP_API int ficp_apply_xy(const double* in_host, double* out_host, int64_t n, int32_t ld, const double* T9);
+/* Sum of squared coordinate differences over md columns: the sum inside frmsd (ficp.py:58-59). */
+FICP_API int ficp_sumsq(const double* a_host, int32_t ld_a, const double* b_host, int32_t ld_b, int64_t k, int32_t md,
+               double* out);
+
+/* ---- kernel 4: persistent batched ICP.  Replaces _iterate()/run() (ficp.py:122-154), batched over
+ * plots and start-pose hypotheses.
+ *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1])
+ *   centres         n_plots x 2: the point each hypothesis rotates about (trees.py:165-222)
+ *   hyp             n_hyp x 6: m00 m01 m10 m11 dx dy ; start pose = M (p - centre) + centre + d
+ *   hyp_begin/stride  this process runs hypotheses hyp_begin, hyp_begin+stride, ... (multi-GPU sharding)
+ *   weights         for table t and stage s: weights[weight_offsets[t] + s*n_t + (k-1)] = 1/((k/n_t)**lambda_s)
+ *   plot_tab        table index of each plot (plots with equal n share a table)
+ *   fixed_k         per-plot fixed subset size or NULL */
+FICP_API int ficp_batch_create(const ficp_target* t, const double* src_host, int32_t ld, int32_t use_z,
+                      const int64_t* plot_offsets, int64_t n_plots, const double* centres, const double* hyp,
+                      int64_t n_hyp, int32_t hyp_begin, int32_t hyp_stride, const double* weights,
+                      const int64_t* weight_offsets, const int32_t* plot_tab, int32_t n_tabs,
+                      const int32_t* fixed_k, const ficp_batch_params* params, int32_t want_final_xy, void* stream,
+                      ficp_batch** out);
+FICP_API int ficp_batch_get_info(const ficp_batch* b, ficp_batch_info* info);
+FICP_API int ficp_batch_run(ficp_batch* b, void* stream);  /* enqueue only */
+/* waits for `stream`, then copies out whatever is non-NULL: results [n_plots*n_hyp_local], best_keys
+ * [n_plots] ((fp32 score bits << 32) | hypothesis id, min = best), final_xy [rows*2] (only when created
+ * with want_final_xy and n_hyp_local == 1), stats [8]: passes, global-path queries, windows disabled,
+ * fix-up rounds, queries. */
+FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_t* best_keys, double* final_xy,
+                       uint64_t* stats, void* stream);
+/* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then
+ * all-reduced with MIN over NCCL). */
+FICP_API int ficp_batch_copy_best_keys_device(ficp_batch* b, void* dst_dev, void* stream);
+FICP_API void ficp_batch_destroy(ficp_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FICP_B200_H */

@@ -209,7 +209,8 @@ def fit_rigid2d_closed(src_xy, tgt_xy, allow_reflection=False):
     h01 = float(np.sum(xc[:, 0] * yc[:, 1]))
     h10 = float(np.sum(xc[:, 1] * yc[:, 0]))
     h11 = float(np.sum(xc[:, 1] * yc[:, 1]))
-    if allow_reflection and (h00 * h11 - h01 * h10) < 0:
+    # reflection only when det(H) is negative beyond rounding noise (for det(H) == 0 the SVD's pick is arbitrary)
+    if allow_reflection and (h00 * h11 - h01 * h10) < -1e-14 * (abs(h00 * h11) + abs(h01 * h10)):
         a, b = h00 - h11, h01 + h10
         nrm = math.hypot(a, b)
         c, s = (1.0, 0.0) if nrm == 0 else (a / nrm, b / nrm)

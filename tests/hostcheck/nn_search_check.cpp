@@ -1,0 +1,152 @@
+// CPU unit test of the accessor-generic grid NN search (coregistrationgame_b200/csrc/nn_search.cuh).
+// Builds the same cell-sorted layout the CUDA grid-build kernels produce, then checks
+// nn_search<GlobalAcc> and nn_search<WindowAcc> against an O(N*M) brute force with the
+// lowest-original-index tie rule.  Test infrastructure only.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include "nn_search.cuh"
+
+using namespace ficp;
+
+struct HostGrid {
+    GridGeom g;
+    std::vector<double2> xy;
+    std::vector<double> z;
+    std::vector<int> org;
+    std::vector<unsigned> cs;
+};
+
+static HostGrid build(const std::vector<double>& px, const std::vector<double>& py, const std::vector<double>& pz,
+                      double ppc) {
+    HostGrid G;
+    const size_t m = px.size();
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (size_t i = 0; i < m; ++i) {
+        x0 = std::min(x0, px[i]); x1 = std::max(x1, px[i]);
+        y0 = std::min(y0, py[i]); y1 = std::max(y1, py[i]);
+    }
+    double ex = x1 - x0, ey = y1 - y0;
+    double big = std::max(ex, ey);
+    double h;
+    if (big <= 0) h = 1.0;
+    else {
+        double exx = std::max(ex, big * 1e-6), eyy = std::max(ey, big * 1e-6);
+        h = std::sqrt(ppc * exx * eyy / (double)m);
+    }
+    G.g.x0 = x0; G.g.y0 = y0; G.g.h = h; G.g.inv_h = 1.0 / h;
+    G.g.gw = (int)std::floor(ex / h) + 1; G.g.gh = (int)std::floor(ey / h) + 1;
+    G.g.eps = h * 1e-9 + (std::fabs(x0) + std::fabs(y0) + big) * 8e-16;
+    const int nc = G.g.gw * G.g.gh;
+    std::vector<int> cell(m);
+    G.cs.assign(nc + 1, 0);
+    for (size_t i = 0; i < m; ++i) {
+        int cx = clamp_cell((px[i] - x0) * G.g.inv_h, G.g.gw), cy = clamp_cell((py[i] - y0) * G.g.inv_h, G.g.gh);
+        cell[i] = cy * G.g.gw + cx;
+        G.cs[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; ++c) G.cs[c + 1] += G.cs[c];
+    std::vector<unsigned> fill(G.cs.begin(), G.cs.end() - 1);
+    G.xy.resize(m); G.z.resize(m); G.org.resize(m);
+    for (size_t i = 0; i < m; ++i) {  // stable: ascending original index within a cell
+        unsigned p = fill[cell[i]]++;
+        G.xy[p] = make_double2(px[i], py[i]); G.z[p] = pz[i]; G.org[p] = (int)i;
+    }
+    return G;
+}
+
+template <bool Z3>
+static int check(const HostGrid& G, const std::vector<double>& px, const std::vector<double>& py,
+                 const std::vector<double>& pz, const std::vector<double>& qx, const std::vector<double>& qy,
+                 const std::vector<double>& qz, int wx0, int wy0, int wx1, int wy1, long* n_window_hits) {
+    GlobalAcc ga{G.xy.data(), G.z.data(), G.org.data(), G.cs.data(), G.g.gw};
+    // window staging exactly like the kernel does it
+    const int ww = wx1 - wx0, wh = wy1 - wy0;
+    std::vector<double2> wxy; std::vector<double> wz; std::vector<unsigned> wc(std::max(ww * wh, 1));
+    std::vector<int> rowoff(wh + 1, 0), rowdelta(std::max(wh, 1), 0);
+    for (int r = 0; r < wh; ++r) {
+        unsigned gs = G.cs[(size_t)(wy0 + r) * G.g.gw + wx0], ge = G.cs[(size_t)(wy0 + r) * G.g.gw + wx1];
+        rowoff[r + 1] = rowoff[r] + (int)(ge - gs);
+        rowdelta[r] = (int)gs - rowoff[r];
+        for (unsigned j = gs; j < ge; ++j) { wxy.push_back(G.xy[j]); wz.push_back(G.z[j]); }
+        for (int c = 0; c < ww; ++c) {
+            unsigned a = G.cs[(size_t)(wy0 + r) * G.g.gw + wx0 + c], b = G.cs[(size_t)(wy0 + r) * G.g.gw + wx0 + c + 1];
+            wc[r * ww + c] = (unsigned)(rowoff[r] + (int)(a - gs)) | ((b - a) << 16);
+        }
+    }
+    WindowAcc wa{wxy.data(), wz.data(), wc.data(), rowoff.data(), rowdelta.data(), G.org.data(), wx0, wy0, wx1, wy1, ww, wh};
+    int bad = 0;
+    for (size_t i = 0; i < qx.size(); ++i) {
+        // brute force
+        double bb = kInf; int bi = -1;
+        for (size_t j = 0; j < px.size(); ++j) {
+            double dx = qx[i] - px[j], dy = qy[i] - py[j];
+            double d2 = dx * dx + dy * dy;
+            if (Z3) { double dz = qz[i] - pz[j]; d2 = d2 + dz * dz; }
+            if (d2 < bb) { bb = d2; bi = (int)j; }
+        }
+        double best; int pos;
+        nn_search<Z3>(ga, G.g, qx[i], qy[i], qz[i], best, pos);
+        if (G.org[pos] != bi || best != bb) {
+            if (bad < 5) printf("GLOBAL mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", i, G.org[pos], best, bi, bb);
+            ++bad;
+        }
+        if (ww > 0 && wh > 0) {
+            double b2; int p2;
+            if (nn_search<Z3>(wa, G.g, qx[i], qy[i], qz[i], b2, p2)) {
+                ++*n_window_hits;
+                int gp = wa.global_pos(p2);
+                if (G.org[gp] != bi || b2 != bb) {
+                    if (bad < 5) printf("WINDOW mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", i, G.org[gp], b2, bi, bb);
+                    ++bad;
+                }
+            }
+        }
+    }
+    return bad;
+}
+
+int main() {
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    int bad = 0; long hits = 0; long total = 0;
+    for (int trial = 0; trial < 24; ++trial) {
+        const size_t m = (trial % 4 == 0) ? 37 : 3000 + 500 * trial;
+        const double side = 300.0 * (1 + trial % 3);
+        const double offx = (trial % 2) ? 420000.0 : 0.0, offy = (trial % 2) ? 6483000.0 : -50.0;
+        std::vector<double> px(m), py(m), pz(m);
+        for (size_t i = 0; i < m; ++i) { px[i] = offx + side * U(rng); py[i] = offy + side * (trial % 5 == 1 ? 0.02 : 1.0) * U(rng); pz[i] = 5 + 30 * U(rng); }
+        if (trial % 3 == 1 && m > 200) {  // lattice patch + duplicates: exact ties
+            int k = 0;
+            for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b, ++k) { px[k] = offx + side / 2 + a; py[k] = offy + side * (trial % 5 == 1 ? 0.01 : 0.5) + b * 0.25; pz[k] = 20; }
+            for (size_t i = m - m / 10; i < m; ++i) { px[i] = px[i - m / 2]; py[i] = py[i - m / 2]; pz[i] = pz[i - m / 2]; }
+        }
+        if (trial == 7) for (size_t i = 0; i < m; ++i) py[i] = offy;           // collinear
+        if (trial == 11) for (size_t i = 0; i < m; ++i) { px[i] = offx; py[i] = offy; }  // all identical
+        HostGrid G = build(px, py, pz, trial % 2 ? 2.0 : 1.0);
+        const size_t nq = 400;
+        std::vector<double> qx(nq), qy(nq), qz(nq);
+        for (size_t i = 0; i < nq; ++i) {
+            double r = U(rng);
+            if (r < 0.6) { qx[i] = offx + side * U(rng); qy[i] = offy + side * U(rng); }
+            else if (r < 0.8) { size_t j = rng() % m; qx[i] = px[j] + 0.3 * (U(rng) - 0.5); qy[i] = py[j] + 0.3 * (U(rng) - 0.5); }
+            else if (r < 0.9) { qx[i] = offx + side * (3 * U(rng) - 1); qy[i] = offy + side * (3 * U(rng) - 1); }  // outside the grid
+            else { qx[i] = offx + side / 2 + (rng() % 8) + 0.5; qy[i] = offy + side * 0.5 + (rng() % 8) * 0.25 + 0.125; }  // lattice centres
+            qz[i] = 5 + 30 * U(rng);
+        }
+        // window: central part of the grid
+        int wx0 = G.g.gw / 4, wx1 = std::max(wx0 + 1, 3 * G.g.gw / 4), wy0 = G.g.gh / 4, wy1 = std::max(wy0 + 1, 3 * G.g.gh / 4);
+        wx1 = std::min(wx1, G.g.gw); wy1 = std::min(wy1, G.g.gh);
+        size_t wpts = 0;
+        for (int r = wy0; r < wy1; ++r) wpts += G.cs[(size_t)r * G.g.gw + wx1] - G.cs[(size_t)r * G.g.gw + wx0];
+        if (wpts > 65535) { wx1 = wx0; }
+        bad += check<false>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits);
+        bad += check<true>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits);
+        total += 2 * nq;
+    }
+    printf("queries=%ld window_resolved=%ld mismatches=%d\n", total, hits, bad);
+    return bad ? 1 : 0;
+}

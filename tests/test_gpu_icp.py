@@ -1,0 +1,283 @@
+"""GPU parity tests of the persistent batched ICP kernel against the CPU oracle and against the
+golden vectors recorded from the unmodified reference (tests/golden/).
+
+Tolerances (BASELINE.json north_star): NN indices / trimmed subsets bit-exact (checked through the
+pass counts, subset sizes and final poses they determine, and directly in test_gpu_stages.py);
+rotation within 1e-6 rad; translation within 1e-5 of the scene extent; RMSE / FRMSD within 1e-6 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ficp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if not os.path.basename(p).startswith("c1_"))
+NOISE_FLOOR = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from coregistrationgame_b200 import _lib
+    _lib.require_device()
+    return _lib
+
+
+def _pose_of(src_xy, out_xy):
+    """rotation angle and translation of the rigid map src -> out (exact for a rigid map)."""
+    T = orc.fit_rigid2d_closed(src_xy, out_xy)
+    return np.arctan2(T[1, 0], T[0, 0]), T[:2, 2], T
+
+
+def _assert_same_pose(src, got, want, extent, what=""):
+    a1, t1, T1 = _pose_of(src[:, :2], got[:, :2])
+    a2, t2, T2 = _pose_of(src[:, :2], want[:, :2])
+    dang = abs(((a1 - a2 + np.pi) % (2 * np.pi)) - np.pi)
+    assert dang < 1e-6, f"{what}: rotation differs by {dang} rad"
+    # compare the translation at the plot centre (t itself is ill-conditioned far from the origin)
+    c = src[:, :2].mean(axis=0)
+    p1 = T1[:2, :2] @ c + t1
+    p2 = T2[:2, :2] @ c + t2
+    assert np.abs(p1 - p2).max() < 1e-5 * extent, f"{what}: translation differs by {np.abs(p1 - p2).max()}"
+    assert np.abs(got[:, :2] - want[:, :2]).max() < 1e-5 * extent
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_run_matches_reference_golden(gpu, case):
+    """FractionalICP.run() on the inputs the unmodified reference was run on."""
+    from ficp import FractionalICP
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    icp = FractionalICP(g["source"], g["target"], lambda_val=float(g["lambda_val"]),
+                        allow_reflection=bool(g["allow_reflection"]))
+    out = icp.run()
+    extent = max(1.0, float(np.ptp(g["target"][:, :2], axis=0).max()))
+    _assert_same_pose(g["source"], out, g["aligned"], extent, case)
+    np.testing.assert_array_equal(out[:, 2:], g["aligned"][:, 2:])
+    assert icp.lambda_val == float(g["lambda_after"])
+    if not (g["val"] < NOISE_FLOOR).any():          # see tests/test_oracle_golden.py about the noise floor
+        assert icp.n_passes_ == len(g["k"])
+        assert icp.k_ == int(g["k"][-1])
+        assert icp.frmsd_ == pytest.approx(float(g["val"][-1]), rel=1e-6)
+
+
+def test_real_data_c1_matches_reference(gpu):
+    """Config 1: Data/2014 plots vs Data/2019 layer (2-D), all 16 plots in ONE batch launch."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    g = np.load(os.path.join(GOLDEN, "c1_real_2d.npz"))
+    offs = g["offsets"]
+    plots = [g["source"][offs[p]:offs[p + 1]] for p in range(len(offs) - 1)]
+    ti = TargetIndex(g["target"])
+    b = IcpBatch(ti, plots, None, centres=np.zeros((len(plots), 2)), min_k=0, want_final_xy=True)
+    out = b.run().results()
+    np.testing.assert_array_equal(out["hyp"]["passes"][:, 0], g["passes"])
+    np.testing.assert_array_equal(out["hyp"]["k"][:, 0], g["k_final"])
+    extent = float(np.ptp(g["target"], axis=0).max())
+    for p, s in enumerate(plots):
+        _assert_same_pose(s, out["final_xy"][offs[p]:offs[p + 1]], g["aligned"][offs[p]:offs[p + 1]], extent, f"plot {p}")
+    b.close()
+    ti.close()
+
+
+def _check_batch_against_oracle(tgt, plots, hyp, atol_xy=1e-6, **kw):
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    from coregistrationgame_b200.batch import compose_world_transform
+    ti = TargetIndex(tgt)
+    b = IcpBatch(ti, plots, hyp, **kw)
+    out = b.run().results()
+    okw = {k: v for k, v in kw.items() if k in ("lambda_val", "threshold", "max_iterations", "allow_reflection", "fixed_frac")}
+    for p, src in enumerate(plots):
+        ref = orc.run_hypotheses(src, tgt, hyp, centre=b.centres[p], min_k=kw.get("min_k", 3), closed_form=True,
+                                 trace_all=True, **okw)
+        rows = out["hyp"][p]
+        sc = np.array(ref["score"])
+        # residuals at the rounding-noise floor (~1e-15 m: trees sitting exactly on CHM points) make k a coin
+        # flip for ANY two implementations (tests/test_oracle_golden.py): compare k / passes above the floor only
+        real = ~(np.array([t_.records[-1].value for t_ in ref["traces"]]) < NOISE_FLOOR)
+        np.testing.assert_array_equal(rows["passes"][real], np.array(ref["passes"])[real], err_msg=f"plot {p}: passes per hypothesis")
+        np.testing.assert_array_equal(rows["k"][real], np.array(ref["k"])[real], err_msg=f"plot {p}: trimmed subset size")
+        raw = np.array([v for v in rows["frmsd"]])
+        fin = np.isfinite(sc) & real
+        np.testing.assert_allclose(raw[fin], sc[fin], rtol=1e-6)
+        for h in range(hyp.shape[0]):
+            A = compose_world_transform(rows[h], b.centres[p])
+            got = src[:, :2] @ A[:, :2].T + A[:, 2]
+            np.testing.assert_allclose(got, ref["aligned"][h][:, :2], rtol=0, atol=atol_xy)
+        if real.all():
+            assert int(out["best_hyp"][p]) == ref["best_hyp"]
+            assert out["best_key"][p] == ref["best_key"]
+    stats = out["stats"]
+    assert stats["passes"] == int(out["hyp"]["passes"].sum())
+    b.close()
+    ti.close()
+    return out
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_batch_hypotheses_match_oracle_c2_shape(gpu, dims):
+    """Config 2 shape (200 trees vs 1e5 CHM points), a 64-hypothesis slice of the 1024 grid."""
+    tgt, plots, _ = orc.synthetic_scene(100000, 200, seed=2, dims=dims, hidden_pose=True)
+    hyp = orc.hypothesis_table(16, flips=(0, 1), translations=[(0.0, 0.0), (2.5, -2.5)])
+    out = _check_batch_against_oracle(tgt, plots, hyp)
+    assert out["stats"]["windows_disabled"] == 0
+    assert out["stats"]["global_path_queries"] < 0.05 * out["stats"]["queries"]
+
+
+def test_batch_window_and_global_paths_agree(gpu):
+    """The shared-memory window is an optimisation only: disabling it must not change one bit."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(50000, 150, seed=8, dims=3, n_plots=3, hidden_pose=True, out_frac=0.2)
+    hyp = orc.hypothesis_table(12, flips=(0, 1), translations=orc.translation_lattice(2, 3.0))
+    ti = TargetIndex(tgt)
+    outs = []
+    for kw in (dict(), dict(disable_window=True), dict(window_margin=0.0), dict(warps_per_cta=4, ctas_per_sm=2)):
+        b = IcpBatch(ti, plots, hyp, **kw)
+        outs.append(b.run().results())
+        b.close()
+    assert outs[1]["stats"]["global_path_queries"] == outs[1]["stats"]["queries"]
+    assert outs[0]["stats"]["global_path_queries"] < outs[2]["stats"]["global_path_queries"] + 1
+    for o in outs[1:]:
+        assert o["hyp"].tobytes() == outs[0]["hyp"].tobytes() or _rows_equal_except_flags(o["hyp"], outs[0]["hyp"])
+        np.testing.assert_array_equal(o["best_key"], outs[0]["best_key"])
+    ti.close()
+
+
+def _rows_equal_except_flags(a, b):
+    for f in a.dtype.names:
+        if f in ("flags", "pad"):
+            continue
+        if not np.array_equal(a[f], b[f]):
+            return False
+    return True
+
+
+def test_batch_adversarial_and_fixed_fraction(gpu):
+    """Config 5: 30 % outlier trees, omissions, duplicated and lattice-tied CHM points; FRMSD-auto mode and
+    the fixed trim-fraction sweep 0.5-0.95."""
+    tgt, plots, _ = orc.synthetic_scene(20000, 120, seed=5, dims=3, out_frac=0.3, omit_frac=0.3, dup_every=10,
+                                        lattice_patch=8, hidden_pose=True)
+    hyp = orc.hypothesis_table(8, flips=(0, 1))
+    _check_batch_against_oracle(tgt, plots, hyp)
+    for frac in (0.5, 0.6, 0.7, 0.8, 0.9, 0.95):
+        _check_batch_against_oracle(tgt, plots, hyp[:6], fixed_frac=frac)
+
+
+def test_batch_exact_ties_everywhere(gpu):
+    """Source trees sitting exactly on duplicated / lattice CHM points: many d2 == 0 and equal-distance ties."""
+    tgt, _, _ = orc.synthetic_scene(5000, 10, seed=9, dims=2, dup_every=5, lattice_patch=10, hidden_pose=False)
+    src = np.vstack([tgt[:60], tgt[:20] + np.array([0.5, 0.5])])       # on lattice nodes + on cell centres
+    src = np.vstack([src, src[:7]])                                     # duplicated trees
+    hyp = orc.hypothesis_table(4, flips=(0,), translations=[(0.0, 0.0), (1.0, 0.0)])
+    _check_batch_against_oracle(tgt, [src], hyp)
+
+
+@pytest.mark.parametrize("n", [5, 28, 33, 64, 100, 257, 500, 1000])
+def test_batch_all_plot_size_classes(gpu, n):
+    """Every elements-per-lane instantiation (N <= 32, 64, ..., 1024), 2-D and 3-D, mixed in one batch."""
+    tgt, plots, _ = orc.synthetic_scene(30000, n, seed=n, dims=3, n_plots=2, hidden_pose=True, out_frac=0.1)
+    small = plots[1][: max(3, n // 2)]
+    hyp = orc.hypothesis_table(4, flips=(0, 1))
+    _check_batch_against_oracle(tgt, [plots[0], small], hyp)
+    _check_batch_against_oracle(tgt[:, :2], [plots[0][:, :2], small[:, :2]], hyp[:3])
+
+
+def test_batch_reflection_and_single_stage(gpu):
+    tgt, plots, _ = orc.synthetic_scene(20000, 90, seed=12, dims=2, hidden_pose=True)
+    hyp = orc.hypothesis_table(6, flips=(0, 1))
+    _check_batch_against_oracle(tgt, plots, hyp, allow_reflection=True)
+    _check_batch_against_oracle(tgt, plots, hyp, lambda_val=1.0, max_iterations=3)
+
+
+def test_iterate_single_stage_and_stepwise_path(gpu):
+    """_iterate() = one stage; the host-stepped stage-kernel path (used above 1024 trees) equals the persistent kernel."""
+    from ficp import FractionalICP
+    tgt, plots, _ = orc.synthetic_scene(20000, 300, seed=14, dims=3, hidden_pose=False)
+    src = orc.pre_transform(plots[0], np.r_[orc.hypothesis_matrix(4.0, 0).ravel(), 1.0, -0.5], plots[0][:, :2].mean(0))
+    a = FractionalICP(src, tgt)
+    out_a = a._iterate()
+    tr = orc.RunTrace()
+    ref = orc.icp_stage(src.copy(), tgt, 3, 3.0, trace=tr, closed_form=True)
+    assert a.n_passes_ == tr.passes and a.k_ == tr.records[-1].k
+    np.testing.assert_allclose(out_a[:, :2], ref[:, :2], atol=1e-7)
+    b = FractionalICP(src, tgt)
+    b._iterate_stepwise()
+    assert b.n_passes_ == a.n_passes_ and b.k_ == a.k_
+    np.testing.assert_allclose(b.source[:, :2], out_a[:, :2], atol=1e-7)
+    np.testing.assert_allclose(b.transform_, a.transform_, atol=1e-7)
+
+
+def test_large_plot_uses_stepwise_path(gpu):
+    from ficp import FractionalICP
+    tgt, plots, _ = orc.synthetic_scene(40000, 1500, seed=15, dims=2, hidden_pose=False)
+    src = orc.pre_transform(plots[0], np.r_[orc.hypothesis_matrix(1.0, 0).ravel(), 0.5, 0.3], plots[0][:, :2].mean(0))
+    icp = FractionalICP(src, tgt)
+    out = icp.run()
+    tr = orc.RunTrace()
+    ref = orc.ficp_run(src, tgt, trace=tr, closed_form=True)
+    assert icp.n_passes_ == tr.passes
+    np.testing.assert_allclose(out, ref, atol=1e-6)
+
+
+def test_determinism_bitwise(gpu):
+    from coregistrationgame_b200 import register_batch
+    tgt, plots, _ = orc.synthetic_scene(30000, 200, seed=3, dims=3, n_plots=4, hidden_pose=True)
+    hyp = orc.hypothesis_table(32, flips=(0, 1))
+    a = register_batch(plots, tgt, hyp)
+    b = register_batch(plots, tgt, hyp, warps_per_cta=8)
+    assert _rows_equal_except_flags(a["hyp"], b["hyp"])
+    np.testing.assert_array_equal(a["best_key"], b["best_key"])
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_full_size_c3_properties(gpu, dims):
+    """Config 3 at full size (500 trees vs 1e6 CHM points, 4096 hypotheses): size-independent properties
+    plus a strided sample of hypotheses checked against the oracle."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    from coregistrationgame_b200.batch import compose_world_transform
+    tgt, plots, poses = orc.synthetic_scene(1000000, 500, seed=3, dims=dims, hidden_pose=True)
+    src = plots[0]
+    hyp = orc.hypothesis_table(128, flips=(0, 1), translations=orc.translation_lattice(4, 2.5))
+    assert hyp.shape[0] == 4096
+    ti = TargetIndex(tgt)
+    b = IcpBatch(ti, [src], hyp)
+    out = b.run().results()
+    rows = out["hyp"][0]
+    # (1) the winner undoes the hidden pose: the hidden pose was R(th) about the centroid + d
+    best = int(out["best_hyp"][0])
+    A = compose_world_transform(rows[best], b.centres[0])
+    ang = np.degrees(np.arctan2(A[1, 0], A[0, 0]))
+    th = poses[0][0]
+    assert abs(((ang + th + 180) % 360) - 180) < 0.5, (ang, th)
+    assert rows["k"][best] > 0.7 * 500 and rows["rmse"][best] < 1.5
+    # (2) ranking key = min over hypotheses of (fp32 score, id)
+    score = np.where(rows["k"] >= 3, rows["frmsd"], np.inf).astype(np.float32)
+    keys = (score.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(4096, dtype=np.uint64)
+    assert out["best_key"][0] == keys.min()
+    # (3) every result is a proper rotation and FRMSD = (N/k)^lambda * rmse
+    det = rows["m00"] * rows["m11"] - rows["m01"] * rows["m10"]
+    np.testing.assert_allclose(det, np.where(hyp[:, 0] * hyp[:, 3] - hyp[:, 1] * hyp[:, 2] > 0, 1.0, -1.0), atol=1e-12)
+    lam2 = orc.STAGE2_LAMBDA[dims]
+    np.testing.assert_allclose(rows["frmsd"], (500.0 / rows["k"]) ** lam2 * rows["rmse"], rtol=1e-12)
+    # (4) idempotence: restarting stage 2 from a converged pose stops almost at once and cannot get worse
+    sub = np.arange(0, 4096, 128)
+    again = np.stack([np.r_[rows["m00"][h], rows["m01"][h], rows["m10"][h], rows["m11"][h],
+                            rows["cx"][h] - b.centres[0][0], rows["cy"][h] - b.centres[0][1]] for h in sub])
+    b2 = IcpBatch(ti, [src], again, n_stages=1, lambda_val=orc.STAGE2_LAMBDA[dims])
+    r2 = b2.run().results()["hyp"][0]
+    assert np.median(r2["passes"]) <= 2 and np.mean(r2["passes"] <= 3) >= 0.9, r2["passes"]
+    assert (r2["frmsd"] <= rows["frmsd"][sub] * (1 + 1e-9) + 1e-9).all()
+    b2.close()
+    # (5) strided sample against the oracle (kd-tree NN with the same tie rule)
+    sample = np.arange(7, 4096, 512)
+    ref = orc.run_hypotheses(src, tgt, hyp[sample], centre=b.centres[0], closed_form=True)
+    np.testing.assert_array_equal(rows["passes"][sample], np.array(ref["passes"]))
+    np.testing.assert_array_equal(rows["k"][sample], np.array(ref["k"]))
+    for j, h in enumerate(sample):
+        A = compose_world_transform(rows[h], b.centres[0])
+        got = src[:, :2] @ A[:, :2].T + A[:, 2]
+        np.testing.assert_allclose(got, ref["aligned"][j][:, :2], rtol=0, atol=1e-6)
+    assert out["stats"]["passes"] == int(rows["passes"].sum())
+    b.close()
+    ti.close()

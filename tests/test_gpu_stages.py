@@ -1,0 +1,227 @@
+"""GPU parity tests of the stage kernels (through the C ABI / FractionalICP methods) against the
+CPU oracle.  Integer/index results must be bit-exact; fp64 values are compared at the tolerances
+written next to each check."""
+import numpy as np
+import pytest
+
+from oracle import ficp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from coregistrationgame_b200 import _lib
+    _lib.require_device()
+    return _lib
+
+
+def _scene(m, n, seed, dims, **kw):
+    tgt, plots, _ = orc.synthetic_scene(m, n, seed=seed, dims=dims, **kw)
+    return tgt, plots[0]
+
+
+# ------------------------------------------------------------------------------- kernel 1a/1b
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("offset", [(0.0, 0.0), (420000.0, 6483000.0)])
+def test_nn_query_bit_exact(gpu, dims, offset):
+    from coregistrationgame_b200 import TargetIndex
+    tgt, src = _scene(20000, 400, seed=21, dims=dims, dup_every=9, lattice_patch=7)
+    rng = np.random.default_rng(5)
+    lo, hi = tgt[:, :2].min(0), tgt[:, :2].max(0)
+    q = np.empty((3000, dims))
+    q[:, :2] = rng.uniform(lo - 0.3 * (hi - lo), hi + 0.3 * (hi - lo), (3000, 2))  # also outside the grid
+    if dims == 3:
+        q[:, 2] = rng.uniform(0, 40, 3000)
+    q[:400] = src
+    # exact ties: centres of lattice cells (4 equidistant targets) and exact duplicates
+    q[400:436, 0] = tgt[:36, 0] + 0.5
+    q[400:436, 1] = tgt[:36, 1] + 0.5
+    q[436:500] = tgt[-64:]
+    off = np.zeros(dims)
+    off[:2] = offset
+    tgt, q = tgt + off, q + off
+    ti = TargetIndex(tgt)
+    idx, dist = ti.query(q)
+    ref_idx, ref_d2 = orc.nn_assign_bruteforce(q, tgt, dims)
+    np.testing.assert_array_equal(idx, ref_idx)                 # bit-exact indices incl. lowest-index ties
+    np.testing.assert_array_equal(dist, np.sqrt(ref_d2))         # identical fp64 bits
+    info = ti.info()
+    assert info["m"] == len(tgt) and info["grid_w"] * info["grid_h"] >= 1
+    ti.close()
+
+
+def test_nn_query_degenerate_targets(gpu):
+    from coregistrationgame_b200 import TargetIndex
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(100, 2)) * 5
+    for tgt in (np.array([[1.0, 2.0]]),                                 # single point
+                np.repeat(np.array([[3.0, -1.0]]), 50, axis=0),          # all identical
+                np.stack([np.linspace(0, 100, 300), np.zeros(300)], 1),  # collinear
+                np.stack([np.zeros(300), np.linspace(0, 100, 300)], 1)):
+        ti = TargetIndex(tgt)
+        idx, dist = ti.query(q)
+        ref_idx, ref_d2 = orc.nn_assign_bruteforce(q, tgt, 2)
+        np.testing.assert_array_equal(idx, ref_idx)
+        np.testing.assert_array_equal(dist, np.sqrt(ref_d2))
+        ti.close()
+
+
+def test_nonfinite_inputs_raise_value_error(gpu):
+    from coregistrationgame_b200 import TargetIndex
+    from ficp import FractionalICP
+    bad = np.array([[0.0, 1.0], [np.nan, 2.0]])
+    with pytest.raises(ValueError):
+        TargetIndex(bad)
+    good = np.random.default_rng(1).normal(size=(10, 2))
+    with pytest.raises(ValueError):
+        FractionalICP(bad, good).run()
+    with pytest.raises(ValueError):
+        FractionalICP(good, bad).run()
+    with pytest.raises(ValueError):
+        FractionalICP(np.zeros(3), good)
+
+
+# ------------------------------------------------------------------------------- kernel 2
+@pytest.mark.parametrize("n", [1, 2, 31, 150, 500, 1024, 3000])
+@pytest.mark.parametrize("lam", [3.0, 1.3, 0.95])
+def test_select_fraction_matches_oracle(gpu, n, lam):
+    from ficp import FractionalICP
+    rng = np.random.default_rng(n)
+    src = rng.normal(size=(n, 3)) * 10
+    corr = src + rng.normal(size=(n, 3)) * rng.choice([0.05, 0.5, 5.0], size=(n, 1))
+    if n > 10:
+        src[3], corr[3] = src[7], corr[7]        # duplicated tree -> exact tie in the trim order (index decides)
+    icp = FractionalICP(src, corr, lambda_val=lam)
+    d2 = orc.sqdist_canonical(src, corr)
+    dist = np.sqrt(d2)
+    frac, k = icp.find_optimal_fraction(corr, dist)
+    order = orc.stable_order(dist)
+    k_ref, val_ref = orc.select_fraction_pairwise(src, corr, order, lam)
+    assert k == k_ref
+    assert frac == k_ref / n
+    np.testing.assert_array_equal(icp.get_n_first_elements(k, dist), order[:k])
+    val = icp.frmsd(frac, k, src[order[:k]], corr[order[:k]])
+    assert val == pytest.approx(val_ref, rel=1e-13)
+
+
+def test_select_fraction_zero_and_tied_distances(gpu):
+    from ficp import FractionalICP
+    src = np.arange(40, dtype=float).reshape(20, 2)
+    icp = FractionalICP(src, src.copy())
+    frac, k = icp.find_optimal_fraction(src.copy(), np.zeros(20))
+    assert (frac, k) == (1 / 20, 1)             # all FRMSD(k) == 0 -> first strict minimum is k = 1
+    np.testing.assert_array_equal(icp.get_n_first_elements(20, np.zeros(20)), np.arange(20))
+
+
+# ------------------------------------------------------------------------------- kernel 3
+@pytest.mark.parametrize("refl", [False, True])
+def test_fit_rigid2d_matches_svd(gpu, refl):
+    from ficp import FractionalICP
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 3, 17, 500, 5000):
+        a = rng.normal(size=(k, 3)) * 30 + 1000.0
+        th = rng.uniform(-np.pi, np.pi)
+        r = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        if refl and k > 2:
+            r = r @ np.diag([1.0, -1.0])
+        b = a.copy()
+        b[:, :2] = a[:, :2] @ r.T + rng.normal(size=2) * 20 + rng.normal(size=(k, 2)) * 0.1
+        icp = FractionalICP(a, b, allow_reflection=refl)
+        T = icp.compute_optimal_transform_2d(a, b)
+        if refl and k <= 2:
+            continue  # det(H) == 0: the SVD's reflection choice is arbitrary
+        T_ref = orc.fit_rigid2d_svd(a[:, :2], b[:, :2], refl)
+        np.testing.assert_allclose(T[:2, :2], T_ref[:2, :2], atol=1e-11)     # rotation: << 1e-6 rad
+        np.testing.assert_allclose(T[:2, 2], T_ref[:2, 2], atol=1e-8)
+        np.testing.assert_allclose(T[:2, :2].T @ T[:2, :2], np.eye(2), atol=1e-14)
+        np.testing.assert_array_equal(T[2], [0.0, 0.0, 1.0])
+
+
+def test_apply_xy_only_bit_exact(gpu):
+    from ficp import FractionalICP
+    rng = np.random.default_rng(8)
+    pts = rng.normal(size=(1000, 5)) * 100
+    T = orc.fit_rigid2d_closed(rng.normal(size=(5, 2)), rng.normal(size=(5, 2)))
+    icp = FractionalICP(pts, pts)
+    out = icp.apply_transform_2d_xy_only(pts, T)
+    ref = orc.apply_xy(pts, T)
+    np.testing.assert_array_equal(out, ref)           # same operation order, no FMA
+    np.testing.assert_array_equal(out[:, 2:], pts[:, 2:])
+    assert out is not pts
+
+
+# ------------------------------------------------------------------------------- reference test shapes
+def _cloud(n, seed):
+    rng = np.random.default_rng(seed)
+    xy = rng.normal(size=(n, 2)) @ np.array([[1.0, 0.3], [0.0, 0.6]]).T
+    z = np.linspace(0.0, 20.0, n)[:, None] + rng.normal(scale=0.02, size=(n, 1))
+    return np.hstack([xy, z])
+
+
+def _move(src, deg, t):
+    th = np.deg2rad(deg)
+    r = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    return np.hstack([src[:, :2] @ r.T + np.asarray(t), src[:, 2:]])
+
+
+def _nn_rmsd(a, b):
+    _, d2 = orc.nn_assign_tree(a, b, a.shape[1])
+    return np.sqrt(d2.mean())
+
+
+def test_reference_acceptance_pose_recovery(gpu):
+    """Same properties the reference's tests/test_ficp.py:39-101 assert, on the same cloud shapes."""
+    from ficp import FractionalICP
+    src = _cloud(150, 1)
+    tgt = _move(src, 27.0, [1.6, -2.2])
+    icp = FractionalICP(src.copy(), tgt)
+    out = icp.run()
+    np.testing.assert_array_equal(out[:, 2], src[:, 2])
+    ang = np.rad2deg(np.arctan2(icp.transform_[1, 0], icp.transform_[0, 0]))
+    assert abs(((ang - 27.0 + 180) % 360) - 180) < 0.2
+    assert _nn_rmsd(out, tgt) < 2e-3
+    assert icp.lambda_val == 0.95
+
+    src = _cloud(200, 2)
+    full = _move(src, 31.0, [2.5, -1.8])
+    keep = np.random.default_rng(123).choice(200, 100, replace=False)
+    out = FractionalICP(src.copy(), full[keep]).run()
+    assert _nn_rmsd(out, full[keep]) < 0.4 * _nn_rmsd(src, full[keep])
+
+    src = _cloud(200, 3)
+    clean = _move(src, -22.0, [-1.2, 2.0])
+    rng = np.random.default_rng(7)
+    t = clean[rng.choice(200, 100, replace=False)]
+    no = int(0.3 * len(t))
+    t = np.vstack([t, np.hstack([rng.uniform(-20, 20, (no, 2)), rng.uniform(-5, 25, (no, 1))])])
+    out = FractionalICP(src.copy(), t).run()
+    assert _nn_rmsd(out, t) < 0.5 * _nn_rmsd(src, t)
+    _, d2 = orc.nn_assign_tree(out[:, :2], clean[:, :2], 2)
+    assert np.mean(np.sqrt(d2) < 0.12) > 0.90
+
+
+def test_empty_inputs_follow_reference_conventions(gpu):
+    """tests/test_ficp.py:104-126 of the reference."""
+    from ficp import FractionalICP
+    tgt = _cloud(5, 42)
+    out = FractionalICP(np.empty((0, 3)), tgt).run()
+    assert out.shape == (0, 3)
+    src = _cloud(4, 24)
+    icp = FractionalICP(src.copy(), np.empty((0, 3)))
+    corr, dist = icp.find_correspondences(src, np.empty((0, 3)))
+    assert corr.shape == (0, 3) and dist.size == 0
+    assert icp.find_optimal_fraction(corr, dist) == (0.0, 0)
+    np.testing.assert_array_equal(icp.run(), src)
+    assert icp.lambda_val == 0.95
+
+
+def test_mixed_dims_fall_back_to_xy(gpu):
+    from ficp import FractionalICP
+    src = _cloud(30, 5)
+    tgt = _move(src, 5.0, [0.2, 0.1])[:, :2]
+    icp = FractionalICP(src, tgt)
+    assert icp.match_dims == 2
+    out = icp.run()
+    assert out.shape == src.shape and icp.lambda_val == 1.3
+    np.testing.assert_array_equal(out[:, 2], src[:, 2])
