@@ -410,8 +410,10 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     if (occ < 1) { set_error("ficp_batch_create: kernel does not fit on an SM with this configuration"); return kErrTooLarge; }
     const int ctas_per_sm = prm->ctas_per_sm > 0 ? std::min(occ, prm->ctas_per_sm) : occ;
     const long long resident = (long long)sms * ctas_per_sm;
+    // tickets: each plot can be worked on by up to `slices_per_plot` CTAs at once (all of them when there are
+    // few plots); tickets are dealt round-robin over the plots by the kernel
     const int max_slices_per_plot = (n_hyp_local + warps - 1) / warps;
-    int slices_per_plot = (int)std::min<long long>(max_slices_per_plot, std::max<long long>(1, (resident + n_plots - 1) / n_plots));
+    int slices_per_plot = (int)std::min<long long>(max_slices_per_plot, resident);
     const long long n_slices = (long long)n_plots * slices_per_plot;
     if (n_slices > 2000000000LL) { set_error("ficp_batch_create: too many work slices"); return kErrTooLarge; }
 

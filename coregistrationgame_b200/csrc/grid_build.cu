@@ -272,16 +272,19 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     cudaEvent_t ev0, ev1;
     FICP_CUDA(cudaEventCreate(&ev0));
     FICP_CUDA(cudaEventCreate(&ev1));
-    FICP_CUDA(cudaEventRecord(ev0, stream));
 
     // ---- bounding box + finiteness
     const int nb_bbox = (int)std::min<long long>((m + kT - 1) / kT, 148 * 8);
     FICP_CUDA(cudaMalloc(&g.part, sizeof(BBox) * (nb_bbox + 1)));
+    FICP_CUDA(cudaEventRecord(ev0, stream));
     bbox_kernel<<<nb_bbox, kT, 0, stream>>>(d_pts, m, ld, use_z, g.part);
     bbox_final_kernel<<<1, 32, 0, stream>>>(g.part, nb_bbox, g.part + nb_bbox);
+    FICP_CUDA(cudaEventRecord(ev1, stream));
     BBox bb;
     FICP_CUDA(cudaMemcpyAsync(&bb, g.part + nb_bbox, sizeof(BBox), cudaMemcpyDeviceToHost, stream));
     FICP_CUDA(cudaStreamSynchronize(stream));
+    float bbox_ms = 0.f;
+    cudaEventElapsedTime(&bbox_ms, ev0, ev1);
     if (bb.nonfinite) {
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         set_error("target contains non-finite coordinates ('x' must be finite)");
@@ -323,12 +326,13 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     FICP_CUDA(cudaMalloc(&t->d_xy, sizeof(double2) * (size_t)m));
     if (use_z) FICP_CUDA(cudaMalloc(&t->d_z, sizeof(double) * (size_t)m));
     FICP_CUDA(cudaMalloc(&t->d_orig, sizeof(int) * (size_t)m));
+    const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
+    FICP_CUDA(cudaMalloc(&g.bsum, sizeof(unsigned) * (size_t)nb_scan));
+    FICP_CUDA(cudaEventRecord(ev0, stream));   // device time of the build = bbox kernels + everything from here
     FICP_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(unsigned) * (size_t)nc, stream));
     FICP_CUDA(cudaMemsetAsync(g.fill, 0, sizeof(unsigned) * (size_t)nc, stream));
     const unsigned nb_pts = (unsigned)((m + kT - 1) / kT);
     bin_count_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, gg, g.cellid, g.counts);
-    const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
-    FICP_CUDA(cudaMalloc(&g.bsum, sizeof(unsigned) * (size_t)nb_scan));
     scan_block_sums_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum);
     scan_partials_kernel<<<1, kT, 0, stream>>>(g.bsum, nb_scan);
     scan_apply_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum, t->d_cell_start);
@@ -340,6 +344,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     FICP_CUDA(cudaEventRecord(ev1, stream));
     FICP_CUDA(cudaStreamSynchronize(stream));
     cudaEventElapsedTime(&t->build_ms, ev0, ev1);
+    t->build_ms += bbox_ms;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
 

@@ -40,7 +40,7 @@ struct LaneCfg {
 
 // ---- shared-memory carve-up (host and device use the same function) -------------------------------
 struct SmemLayout {
-    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, w_cell, rowoff, rowdelta, rowg, total;
+    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, sord, w_cell, rowoff, rowdelta, rowg, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, int wcap_pts, int wcap_cells,
                                                   int wcap_rows) {
@@ -54,6 +54,7 @@ __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, 
     L.s_g = take((size_t)kMaxStages * npad * 8);
     L.sd2 = take((size_t)warps * npad * 8);
     L.snn = take((size_t)warps * npad * 4);
+    L.sord = take((size_t)warps * npad * 2);
     L.w_cell = take((size_t)wcap_cells * 4);
     L.rowoff = take((size_t)(wcap_rows + 1) * 4);
     L.rowdelta = take((size_t)wcap_rows * 4);
@@ -68,35 +69,49 @@ __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, 
 // a numpy emulation of the same loops.
 template <int E>
 __device__ __forceinline__ void warp_bitonic_sort(unsigned (&key)[E], int lane) {
-    constexpr int N = 32 * E;
+    // phases k = 2 .. E/2: compare-exchanges between registers of one lane, directions known at compile time
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 2; k < E; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= E) {
-                const int lj = j / E;
-                const bool up = (lane & lj) != 0;
-                const bool desc = (k < N) && (((lane * E) & k) != 0);
-                const bool takemin = (up == desc);
 #pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const unsigned o = __shfl_xor_sync(kFull, key[r], lj);
-                    key[r] = takemin ? min(key[r], o) : max(key[r], o);
+            for (int r = 0; r < E; ++r) {
+                const int l = r ^ j;
+                if (l > r) {
+                    const bool desc = (r & k) != 0;
+                    const unsigned a = key[r], b = key[l];
+                    const unsigned mn = min(a, b), mx = max(a, b);
+                    key[r] = desc ? mx : mn;
+                    key[l] = desc ? mn : mx;
                 }
-            } else {
+            }
+        }
+    }
+    // phases k = E << m, m = 0..5: direction = bit m of the lane (bit 5 is always 0: the last phase ascends).
+    // Kept as RUNTIME loops (one copy of the shuffle step and one of the in-lane steps) to keep the kernel's
+    // instruction footprint small - 16 warps in different phases share one instruction cache.
+#pragma unroll 1
+    for (int m = 0; m <= 5; ++m) {
+        const bool desc = ((lane >> m) & 1) != 0;
+#pragma unroll 1
+        for (int lj = (1 << m) >> 1; lj > 0; lj >>= 1) {
+            const bool takemin = (((lane & lj) != 0) == desc);
 #pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const int l = r ^ j;
-                    if (l > r) {
-                        bool desc;
-                        if (k < E) desc = (r & k) != 0;
-                        else if (k < N) desc = ((lane * E) & k) != 0;
-                        else desc = false;
-                        const unsigned a = key[r], b = key[l];
-                        const unsigned mn = min(a, b), mx = max(a, b);
-                        key[r] = desc ? mx : mn;
-                        key[l] = desc ? mn : mx;
-                    }
+            for (int r = 0; r < E; ++r) {
+                const unsigned o = __shfl_xor_sync(kFull, key[r], lj);
+                key[r] = takemin ? min(key[r], o) : max(key[r], o);
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const int l = r ^ j;
+                if (l > r) {
+                    const unsigned a = key[r], b = key[l];
+                    const unsigned mn = min(a, b), mx = max(a, b);
+                    key[r] = desc ? mx : mn;
+                    key[l] = desc ? mn : mx;
                 }
             }
         }
@@ -133,39 +148,56 @@ __device__ __forceinline__ void pose_apply(const Pose& P, const double2 u, doubl
     qy = dadd(dadd(dmul(P.m10, u.x), dmul(P.m11, u.y)), P.cy);
 }
 
+// Global-grid form of the query (window miss): rare, so kept out of line to keep the hot loop small.
+template <bool Z3>
+__device__ __noinline__ int nn_query_global(const GridView& G, double qx, double qy, double qz, int prev, double* best_out) {
+    const GlobalAcc ga{G.xy, G.z, G.orig, G.cell_start, G.g.gw};
+    double best;
+    int pos;
+    nn_search_stream<Z3>(ga, G.g, qx, qy, qz, prev, best, pos);
+    *best_out = best;
+    return pos;
+}
+
 // One NN pass + trimming for the warp's hypothesis.
 template <int E, bool Z3>
 __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
                                             const Pose& P, const double* __restrict__ s_g,
                                             const double* __restrict__ g_c, double* __restrict__ sd2,
-                                            int* __restrict__ snn, int lane, unsigned& n_global, unsigned& n_fix) {
+                                            int* __restrict__ snn, unsigned short* __restrict__ sord, int lane,
+                                            bool have_prev, unsigned& n_global, unsigned& n_fix) {
     using C = LaneCfg<E>;
     const int n = pc.n;
-    const GlobalAcc ga{G.xy, G.z, G.orig, G.cell_start, G.g.gw};
 
-    // ---- nearest neighbours (one query per lane per round) ----
+    // ---- nearest neighbours: one query per lane per round.  Round e takes the 32 queries at positions
+    // 32e..32e+31 of the PREVIOUS pass's trim order (identity on the first pass): neighbours in that order have
+    // similar residuals, hence similar search radii and candidate counts, so the lanes of a warp finish together
+    // and the rare wide searches (ring >= 2) fall into the same rounds. ----
 #pragma unroll 1
     for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        double best = kInf;
-        int code = -1;
-        if (i < n) {
+        const int p = e * 32 + lane;
+        if (p < n) {
+            const int i = sord[p];
             double qx, qy;
             pose_apply(P, pc.s_u[i], qx, qy);
             const double qz = Z3 ? pc.s_z[i] : 0.0;
-            int pos = -1;
+            // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
+            const int pc_prev = have_prev ? snn[i] : -1;
+            double best = kInf;
+            int pos = -1, code;
             bool ok = false;
-            if (win_ok) ok = nn_search<Z3>(W, G.g, qx, qy, qz, best, pos);
+            if (win_ok) ok = nn_search_stream<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos);
             if (ok) {
                 code = pos;
             } else {
-                nn_search<Z3>(ga, G.g, qx, qy, qz, best, pos);
+                const int gprev = (pc_prev == -1) ? -1 : (pc_prev >= 0 ? W.global_pos(pc_prev) : (pc_prev & 0x7FFFFFFF));
+                pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
                 code = (int)((unsigned)pos | 0x80000000u);
                 ++n_global;
             }
+            sd2[i] = best;
+            snn[i] = code;
         }
-        sd2[i] = best;
-        snn[i] = code;
     }
     __syncwarp();
 
@@ -224,6 +256,10 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
         if (!__any_sync(kFull, sw)) break;
         ++n_fix;
     }
+
+    // publish the trim order (positions 0..n-1 hold exactly the n real points) for the next pass's rounds
+#pragma unroll
+    for (int r = 0; r < E; ++r) sord[lane * E + r] = (unsigned short)(key[r] & C::kIdxMask);
 
     // ---- inclusive prefix sums S_k of d2 in trim order ----
     double s[E];
@@ -381,11 +417,13 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
     double* s_g = reinterpret_cast<double*>(smem + L.s_g);
     double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)warp * NPAD;
     int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)warp * NPAD;
+    unsigned short* sord = reinterpret_cast<unsigned short*>(smem + L.sord) + (size_t)warp * NPAD;
     unsigned* w_cell = reinterpret_cast<unsigned*>(smem + L.w_cell);
     int* rowoff = reinterpret_cast<int*>(smem + L.rowoff);
     int* rowdelta = reinterpret_cast<int*>(smem + L.rowdelta);
     int* rowg = reinterpret_cast<int*>(smem + L.rowg);
     __shared__ int sh_slice;
+    __shared__ int sh_exhausted;
     __shared__ int sh_win_ok;
 
     const GridView& G = P.grid;
@@ -394,11 +432,18 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous slice (and with sh_slice)
-        if (threadIdx.x == 0) sh_slice = atomicAdd(P.slice_counter, 1);
+        if (threadIdx.x == 0) {
+            const int t = atomicAdd(P.slice_counter, 1);
+            sh_slice = t;
+            sh_exhausted = (t < P.n_slices) ? (atomicAdd(P.hyp_counter + (t % P.n_plots), 0) >= P.n_hyp_local) : 0;
+        }
         __syncthreads();
         const int slice = sh_slice;
         if (slice >= P.n_slices) break;
-        const int plot = slice / P.slices_per_plot;
+        // tickets are dealt round-robin over the plots: every CTA may help any plot, and a ticket for a plot
+        // whose hypotheses are all taken costs one atomic read (no staging)
+        const int plot = slice % P.n_plots;
+        if (sh_exhausted) continue;
         const PlotMeta pm = P.plots[plot];
 
         if (plot != staged_plot) {
@@ -473,6 +518,12 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
             unsigned n_global = 0, n_fix = 0;
             int passes = 0;
+            // first pass: identity order; padding slots never change
+            for (int i = lane; i < NPAD; i += 32) {
+                sord[i] = (unsigned short)i;
+                if (i >= pm.n) { sd2[i] = kInf; snn[i] = -1; }
+            }
+            __syncwarp();
             PassOut po{0, kInf, 0.0, -1.0, -1};
             for (int st = 0; st < P.n_stages; ++st) {
                 const double* sg = s_g + (size_t)st * NPAD;
@@ -483,7 +534,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
                 int it = 0;
                 bool first = true;
                 for (;;) {
-                    po = icp_pass<E, Z3>(G, W, win_ok, pc, pose, sg, gc, sd2, snn, lane, n_global, n_fix);
+                    po = icp_pass<E, Z3>(G, W, win_ok, pc, pose, sg, gc, sd2, snn, sord, lane, passes > 0, n_global, n_fix);
                     ++passes;
                     if (first) {
                         if (po.k == 0) break;  // ficp.py:125-126

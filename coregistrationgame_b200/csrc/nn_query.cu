@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     const GlobalAcc acc{v.xy, v.z, v.orig, v.cell_start, v.g.gw};
     double best;
     int pos;
-    nn_search<Z3>(acc, v.g, qx, qy, qz, best, pos);
+    nn_search_stream<Z3>(acc, v.g, qx, qy, qz, -1, best, pos);
     idx[i] = __ldg(v.orig + pos);
     if (dist) dist[i] = sqrt(best);
     if (d2out) d2out[i] = best;

@@ -85,28 +85,57 @@ struct WindowAcc {
     FICP_HD int orig(int j) const { return FICP_LDG(gorg + global_pos(j)); }
 };
 
+// ---- one candidate ---------------------------------------------------------------------------------
+template <bool Z3, class Acc>
+FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, double& best, int& bestpos) {
+    double tx, ty, tz = 0.0;
+    acc.template load<Z3>(j, tx, ty, tz);
+    const double dx = dsub(qx, tx);
+    const double dy = dsub(qy, ty);
+    double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+    if (Z3) {
+        const double dz = dsub(qz, tz);
+        d2 = dadd(d2, dmul(dz, dz));
+    }
+    if (d2 < best) {
+        best = d2;
+        bestpos = j;
+    } else if (d2 == best && j != bestpos) {  // exact tie (rare): lowest original index wins
+        if (bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) bestpos = j;
+    }
+}
+
+// squared distance only (used by the two-at-a-time stream loop)
+template <bool Z3, class Acc>
+FICP_HD double nn_dist2(const Acc& acc, int j, double qx, double qy, double qz) {
+    double tx, ty, tz = 0.0;
+    acc.template load<Z3>(j, tx, ty, tz);
+    const double dx = dsub(qx, tx);
+    const double dy = dsub(qy, ty);
+    double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+    if (Z3) {
+        const double dz = dsub(qz, tz);
+        d2 = dadd(d2, dmul(dz, dz));
+    }
+    return d2;
+}
+
+template <class Acc>
+FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpos) {
+    if (d2 < best) {
+        best = d2;
+        bestpos = j;
+    } else if (d2 == best && j != bestpos) {
+        if (bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) bestpos = j;
+    }
+}
+
 template <bool Z3, class Acc>
 FICP_HD void nn_scan_segment(const Acc& acc, int y, int xa, int xb, double qx, double qy, double qz,
                              double& best, int& bestpos) {
     int s, e;
     acc.seg(y, xa, xb, s, e);
-    for (int j = s; j < e; ++j) {
-        double tx, ty, tz = 0.0;
-        acc.template load<Z3>(j, tx, ty, tz);
-        const double dx = dsub(qx, tx);
-        const double dy = dsub(qy, ty);
-        double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
-        if (Z3) {
-            const double dz = dsub(qz, tz);
-            d2 = dadd(d2, dmul(dz, dz));
-        }
-        if (d2 <= best) {
-            if (d2 < best || bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) {
-                best = d2;
-                bestpos = j;
-            }
-        }
-    }
+    for (int j = s; j < e; ++j) nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
 }
 
 template <bool Z3, class Acc>
@@ -122,20 +151,13 @@ FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, in
     nn_scan_segment<Z3>(acc, y, xa, xb, qx, qy, qz, best, bestpos);
 }
 
-// Returns false when the search needs cells the accessor does not cover (window miss): the
-// caller then repeats the query with GlobalAcc.  On success best = squared distance (canonical
-// arithmetic) and bestpos = accessor-local position of the winner.
+// Rings r_start, r_start+1, ... around cell (cx, cy); every cell of Chebyshev radius < r_start has been
+// visited already.  Stops when the best distance is strictly below the distance to the border of the
+// visited block (so no unvisited point can be closer or tie).  Returns false on a window miss.
 template <bool Z3, class Acc>
-FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, double& best,
-                       int& bestpos) {
-    const int cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
-    const int cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
-    best = kInf;
-    bestpos = -1;
-    if (!acc.covers(cx, cx, cy, cy)) return false;
-    nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
-    for (int r = 1;; ++r) {
-        // every unvisited point lies outside the block of radius r-1: lower-bound its distance
+FICP_HD bool nn_ring_loop(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
+                          int r_start, double& best, int& bestpos) {
+    for (int r = r_start;; ++r) {
         const int xl = cx - (r - 1), xh = cx + (r - 1), yl = cy - (r - 1), yh = cy + (r - 1);
         double b = kInf;
         if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
@@ -160,6 +182,97 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
         }
     }
     return true;
+}
+
+// Reference form of the search (ring by ring from the query's own cell).  Returns false when the search
+// needs cells the accessor does not cover (window miss): the caller then repeats the query with
+// GlobalAcc.  On success best = squared distance (canonical arithmetic) and bestpos = accessor-local
+// position of the winner.
+template <bool Z3, class Acc>
+FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, double& best,
+                       int& bestpos) {
+    const int cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+    const int cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+    best = kInf;
+    bestpos = -1;
+    if (!acc.covers(cx, cx, cy, cy)) return false;
+    nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
+    return nn_ring_loop<Z3>(acc, g, qx, qy, qz, cx, cy, 1, best, bestpos);
+}
+
+FICP_HD double nn_box_gap(double lo, double hi, double q) {  // distance from q to the interval [lo, hi]
+    return fmax(fmax(lo - q, q - hi), 0.0);
+}
+
+// Production form used by the kernels: the 3x3 block around the query's cell is visited as ONE flat
+// stream of candidates, so that the 32 lanes of a warp (one query each, in lock-step) pay the largest
+// TOTAL candidate count among them instead of the largest count of every cell separately.
+//   1. `prev` (the neighbour found by the previous ICP pass, or -1) is scored first: it bounds the
+//      search from the start (temporal coherence; the result is still the exact NN);
+//   2. per row of the block, the run of cells whose box lies within that bound is one contiguous range
+//      of the cell-sorted array: three (start, end) pairs;
+//   3. one loop over the concatenation of the three ranges;
+//   4. if the border of the block is not provably farther than the best distance, the ring loop goes on
+//      from radius 2 (rare).
+template <bool Z3, class Acc>
+FICP_HD bool nn_search_stream(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
+                              double& best, int& bestpos) {
+    const int cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+    const int cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+    const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
+    const int yl = (cy > 0) ? cy - 1 : 0, yh = (cy < g.gh - 1) ? cy + 1 : g.gh - 1;
+    if (!acc.covers(xl, xh, yl, yh)) return false;
+    best = kInf;
+    bestpos = -1;
+    if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
+    // squared gaps between the query and the three cell columns / rows (boxes inflated by eps)
+    const double X0 = g.x0 + cx * g.h, Y0 = g.y0 + cy * g.h, h = g.h, eps = g.eps;
+    double gx[3], gy[3];
+    gx[0] = nn_box_gap(X0 - h - eps, X0 + eps, qx);
+    gx[1] = nn_box_gap(X0 - eps, X0 + h + eps, qx);
+    gx[2] = nn_box_gap(X0 + h - eps, X0 + 2.0 * h + eps, qx);
+    gy[0] = nn_box_gap(Y0 - h - eps, Y0 + eps, qy);
+    gy[1] = nn_box_gap(Y0 - eps, Y0 + h + eps, qy);
+    gy[2] = nn_box_gap(Y0 + h - eps, Y0 + 2.0 * h + eps, qy);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+    int s[3], n[3];
+#pragma unroll
+    for (int ry = 0; ry < 3; ++ry) {
+        const int y = cy - 1 + ry;
+        s[ry] = 0;
+        n[ry] = 0;
+        if (y < yl || y > yh) continue;
+        // columns of this row whose box can hold a point at distance <= best (a contiguous run)
+        int xa = cx + 2, xb = cx - 2;
+#pragma unroll
+        for (int rx = 0; rx < 3; ++rx) {
+            const int x = cx - 1 + rx;
+            if (x >= xl && x <= xh && gx[rx] + gy[ry] <= best) {
+                if (x < xa) xa = x;
+                xb = x;
+            }
+        }
+        if (xa <= xb) {
+            int e;
+            acc.seg(y, xa, xb, s[ry], e);
+            n[ry] = e - s[ry];
+        }
+    }
+    // flat index t -> position: t + (offset of the run t falls in); two candidates per iteration so that two
+    // independent load/arithmetic chains are in flight (the fold into `best` stays in stream order)
+    const int n01 = n[0] + n[1], total = n01 + n[2];
+    const int o1 = s[1] - n[0], o2 = s[2] - n01;
+    for (int t = 0; t < total; t += 2) {
+        const int t1 = (t + 1 < total) ? t + 1 : t;
+        const int j0 = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+        const int j1 = t1 + ((t1 < n[0]) ? s[0] : (t1 < n01) ? o1 : o2);
+        const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
+        const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
+        nn_fold(acc, j0, da, best, bestpos);
+        nn_fold(acc, j1, db, best, bestpos);
+    }
+    return nn_ring_loop<Z3>(acc, g, qx, qy, qz, cx, cy, 2, best, bestpos);
 }
 
 }  // namespace ficp

@@ -94,6 +94,19 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
             if (bad < 5) printf("GLOBAL mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", i, G.org[pos], best, bi, bb);
             ++bad;
         }
+        // streamed 3x3 form, seeded with: nothing, the true NN, an arbitrary point, a near point
+        for (int variant = 0; variant < 4; ++variant) {
+            int prev = -1;
+            if (variant == 1) prev = pos;
+            if (variant == 2) prev = (int)((i * 7919u + 13u) % px.size());
+            if (variant == 3) prev = std::min<int>((int)px.size() - 1, pos + 1);
+            double b3; int p3;
+            nn_search_stream<Z3>(ga, G.g, qx[i], qy[i], qz[i], prev, b3, p3);
+            if (G.org[p3] != bi || b3 != bb) {
+                if (bad < 5) printf("STREAM(global,v%d) mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", variant, i, G.org[p3], b3, bi, bb);
+                ++bad;
+            }
+        }
         if (ww > 0 && wh > 0) {
             double b2; int p2;
             if (nn_search<Z3>(wa, G.g, qx[i], qy[i], qz[i], b2, p2)) {
@@ -102,6 +115,21 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
                 if (G.org[gp] != bi || b2 != bb) {
                     if (bad < 5) printf("WINDOW mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", i, G.org[gp], b2, bi, bb);
                     ++bad;
+                }
+            }
+            for (int variant = 0; variant < 3; ++variant) {
+                int prev = -1;
+                const int wtot = rowoff[wh];
+                if (variant == 1 && wtot > 0) prev = (int)((i * 104729u + 7u) % (unsigned)wtot);
+                if (variant == 2 && wtot > 0) prev = wtot - 1;
+                double b4; int p4;
+                if (nn_search_stream<Z3>(wa, G.g, qx[i], qy[i], qz[i], prev, b4, p4)) {
+                    ++*n_window_hits;
+                    int gp = wa.global_pos(p4);
+                    if (G.org[gp] != bi || b4 != bb) {
+                        if (bad < 5) printf("STREAM(window,v%d) mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", variant, i, G.org[gp], b4, bi, bb);
+                        ++bad;
+                    }
                 }
             }
         }
