@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--trees", type=int, default=500)
     ap.add_argument("--dims", type=int, default=3, choices=[2, 3])
-    ap.add_argument("--plots-per-gpu", type=int, default=8)
+    ap.add_argument("--plots-per-gpu", type=int, default=16)
     ap.add_argument("--rotations", type=int, default=128)
     ap.add_argument("--tside", type=int, default=4, help="translation lattice side (tside^2 translations)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the CPU baseline sample (0 = one per core, <= 32)")
@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--window-margin", type=float, default=-1.0)
-    ap.add_argument("--pts-per-cell", type=float, default=2.0)
+    ap.add_argument("--pts-per-cell", type=float, default=0.0, help="0 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -198,7 +198,7 @@ def run_b200(args):
     props = _lib.device_props()
 
     # ---- resident inputs
-    index = TargetIndex(tgt, pts_per_cell=args.pts_per_cell)
+    index = TargetIndex(tgt, pts_per_cell=(args.pts_per_cell or None))
     tinfo = index.info()
     batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), warps_per_cta=args.warps,
                      ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libficp_b200.so")
+LIB_PATH = os.environ.get("FICP_B200_LIB") or os.path.join(_HERE, "libficp_b200.so")  # env override: A/B builds
 
 c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 P = C.POINTER

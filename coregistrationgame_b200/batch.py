@@ -71,13 +71,17 @@ class TargetIndex:
     """Device-resident uniform-grid index over the Layer-2 (CHM) points; built once, reused by
     every pass of every hypothesis (the reference rebuilds its kd-tree on every pass, ficp.py:69)."""
 
-    def __init__(self, target, use_z=None, pts_per_cell=2.0, stream=None):
+    def __init__(self, target, use_z=None, pts_per_cell=None, stream=None):
         lib = _lib.load()
         arr = np.ascontiguousarray(np.asarray(target, dtype=np.float64))
         if arr.ndim != 2 or arr.shape[1] < 2:
             raise ValueError("source and target must be 2D arrays (N, D).")
         self.m, self.ld = int(arr.shape[0]), int(arr.shape[1])
         self.has_z = bool(arr.shape[1] >= 3) if use_z is None else bool(use_z)
+        if pts_per_cell is None:
+            # measured on B200 (profiles/): ~3 points per cell when matching in XYZ (larger search radii),
+            # ~2 when matching in XY
+            pts_per_cell = 3.0 if self.has_z else 2.0
         self._h = C.c_void_p()
         _lib.require_device()
         _lib.check(lib.ficp_target_create(_lib.ptr(arr), self.m, self.ld, int(self.has_z), float(pts_per_cell),

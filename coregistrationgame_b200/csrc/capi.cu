@@ -389,10 +389,10 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
                 const int x0 = clamp_cell((bx0 - g.x0) * g.inv_h, g.gw), x1 = clamp_cell((bx1 - g.x0) * g.inv_h, g.gw) + 1;
                 const int y0 = clamp_cell((by0 - g.y0) * g.inv_h, g.gh), y1 = clamp_cell((by1 - g.y0) * g.inv_h, g.gh) + 1;
                 const long long cells = (long long)(x1 - x0) * (y1 - y0);
-                const double est = cells * mean_cell_pts * 1.25 + 64;
+                const double est = cells * mean_cell_pts * 1.15 + 96;
                 if (cells <= wcap_pts && (y1 - y0) <= wcap_rows && est <= wcap_pts) {
                     pm.wx0 = x0; pm.wx1 = x1; pm.wy0 = y0; pm.wy1 = y1;
-                    need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est * 1.2 + 256));
+                    need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est));
                     need_pts = std::max<long long>(need_pts, cells);
                     break;
                 }

@@ -149,8 +149,14 @@ __device__ __forceinline__ void pose_apply(const Pose& P, const double2 u, doubl
 }
 
 // Global-grid form of the query (window miss): rare, so kept out of line to keep the hot loop small.
+// measured (profiles/r01_variants.md): inlining the rare global-grid / tie / ring paths beats calling them
+#if defined(FICP_NOINLINE_GLOBAL)
+#define FICP_GLOBAL_ATTR __device__ __noinline__
+#else
+#define FICP_GLOBAL_ATTR __device__ __forceinline__
+#endif
 template <bool Z3>
-__device__ __noinline__ int nn_query_global(const GridView& G, double qx, double qy, double qz, int prev, double* best_out) {
+FICP_GLOBAL_ATTR int nn_query_global(const GridView& G, double qx, double qy, double qz, int prev, double* best_out) {
     const GlobalAcc ga{G.xy, G.z, G.orig, G.cell_start, G.g.gw};
     double best;
     int pos;
@@ -261,11 +267,10 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
 #pragma unroll
     for (int r = 0; r < E; ++r) sord[lane * E + r] = (unsigned short)(key[r] & C::kIdxMask);
 
-    // ---- inclusive prefix sums S_k of d2 in trim order ----
-    double s[E];
+    // ---- inclusive prefix sums S_k of d2 in trim order (in place: dd[r] becomes S at position lane*E + r) ----
     double run = 0.0;
 #pragma unroll
-    for (int r = 0; r < E; ++r) { run += dd[r]; s[r] = run; }
+    for (int r = 0; r < E; ++r) { run += dd[r]; dd[r] = run; }
     double inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -275,7 +280,8 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
     double excl = __shfl_up_sync(kFull, inc, 1);
     if (lane == 0) excl = 0.0;
 #pragma unroll
-    for (int r = 0; r < E; ++r) s[r] = excl + s[r];
+    for (int r = 0; r < E; ++r) dd[r] = excl + dd[r];
+    double (&s)[E] = dd;
 
     // ---- subset size ----
     PassOut out;
@@ -296,13 +302,24 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
         // ... then evaluate the reference's exact expression c_k * sqrt(S_k / k) only for the k whose G is
         // within rounding distance of the minimum; first strict minimum wins (ficp.py:84)
         const double gthr = gbest * (1.0 + 1e-12);
-        int kb = INT_MAX;
+        unsigned cand = 0u;  // bit r: position lane*E + r is within rounding distance of the minimum
 #pragma unroll
         for (int r = 0; r < E; ++r) {
             const int p = lane * E + r;
-            if (p < n && s[r] * s_g[r * 32 + lane] <= gthr) {
-                const int k = p + 1;
-                const double rm = sqrt(s[r] / (double)k);
+            if (p < n && s[r] * s_g[r * 32 + lane] <= gthr) cand |= (1u << r);
+        }
+        int kb = INT_MAX;
+        // one copy of the divide + square root: lanes walk their (almost always single) candidates in ascending k
+        while (__any_sync(kFull, cand != 0u)) {
+            if (cand != 0u) {
+                const int r = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                double sr = s[0];
+#pragma unroll
+                for (int rr = 1; rr < E; ++rr)
+                    if (rr == r) sr = s[rr];
+                const int k = lane * E + r + 1;
+                const double rm = sqrt(sr / (double)k);
                 const double f = __ldg(g_c + r * 32 + lane) * rm;
                 if (f < fstar) { fstar = f; kb = k; rstar = rm; }
             }
@@ -323,13 +340,13 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
     }
     // the k-th element in trim order defines the inlier set {(d2, i) <= (thr, thr_idx)}
     const int pstar = kstar - 1, lstar = pstar / E, rsel = pstar % E;
-    double tsel = dd[0], ssel = s[0];
+    double ssel = s[0];
     unsigned ksel = key[0];
 #pragma unroll
     for (int r = 1; r < E; ++r)
-        if (r == rsel) { tsel = dd[r]; ksel = key[r]; ssel = s[r]; }
-    out.thr = __shfl_sync(kFull, tsel, lstar);
+        if (r == rsel) { ksel = key[r]; ssel = s[r]; }
     out.thr_idx = (int)(__shfl_sync(kFull, ksel, lstar) & C::kIdxMask);
+    out.thr = sd2[out.thr_idx];
     if (pc.fixed_k > 0) {
         const double sk = __shfl_sync(kFull, ssel, lstar);
         rstar = sqrt(sk / (double)kstar);
@@ -590,7 +607,10 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
 template <int E, bool Z3>
 struct KernelFor {
     // threads per CTA the kernel is compiled for (register budget = 64K / NT)
-    static constexpr int kNT = (E >= 32) ? 384 : (E >= 16) ? 512 : 512;
+#ifndef FICP_NT16
+#define FICP_NT16 512
+#endif
+    static constexpr int kNT = (E >= 32) ? 384 : (E >= 16) ? FICP_NT16 : 512;
 };
 
 template <int E, bool Z3>
@@ -622,7 +642,7 @@ size_t icp_smem_bytes(int e, bool z3, int warps, int wcap_pts, int wcap_cells, i
     return smem_layout(32 * e, z3, warps, wcap_pts, wcap_cells, wcap_rows).total;
 }
 
-int icp_max_warps(int e) { return (e >= 32) ? 12 : 16; }  // = KernelFor<E>::kNT / 32
+int icp_max_warps(int e) { return (e >= 32) ? 12 : (e >= 16) ? FICP_NT16 / 32 : 16; }  // = KernelFor<E>::kNT / 32
 
 #define FICP_DISPATCH(FN, ...)                                                                    \
     switch (e) {                                                                                  \

@@ -85,6 +85,27 @@ struct WindowAcc {
     FICP_HD int orig(int j) const { return FICP_LDG(gorg + global_pos(j)); }
 };
 
+// Rare paths can be kept out of line (smaller hot loop) or inlined (no call ABI inside divergent code);
+// which is faster was measured, see profiles/.
+#if defined(__CUDA_ARCH__) && defined(FICP_NOINLINE_TIE)
+#define FICP_COLD_TIE __device__ __noinline__
+#else
+#define FICP_COLD_TIE FICP_HD
+#endif
+#if defined(__CUDA_ARCH__) && defined(FICP_NOINLINE_RING)
+#define FICP_COLD_RING __device__ __noinline__
+#else
+#define FICP_COLD_RING FICP_HD
+#endif
+
+// Exact distance tie between candidate j and the current best (rare): the lower ORIGINAL index wins.
+// Out of line: it sits behind every distance comparison and would otherwise be inlined a dozen times.
+template <class Acc>
+FICP_COLD_TIE int nn_tie_winner(const Acc& acc, int j, int bestpos) {
+    if (bestpos < 0 || j == bestpos) return j;
+    return (acc.orig(j) < acc.orig(bestpos)) ? j : bestpos;
+}
+
 // ---- one candidate ---------------------------------------------------------------------------------
 template <bool Z3, class Acc>
 FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, double& best, int& bestpos) {
@@ -97,11 +118,9 @@ FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, dou
         const double dz = dsub(qz, tz);
         d2 = dadd(d2, dmul(dz, dz));
     }
-    if (d2 < best) {
+    if (d2 <= best) {  // rare after the first few candidates
+        if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
         best = d2;
-        bestpos = j;
-    } else if (d2 == best && j != bestpos) {  // exact tie (rare): lowest original index wins
-        if (bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) bestpos = j;
     }
 }
 
@@ -122,11 +141,9 @@ FICP_HD double nn_dist2(const Acc& acc, int j, double qx, double qy, double qz) 
 
 template <class Acc>
 FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpos) {
-    if (d2 < best) {
+    if (d2 <= best) {
+        if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
         best = d2;
-        bestpos = j;
-    } else if (d2 == best && j != bestpos) {
-        if (bestpos < 0 || acc.orig(j) < acc.orig(bestpos)) bestpos = j;
     }
 }
 
@@ -155,8 +172,8 @@ FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, in
 // visited already.  Stops when the best distance is strictly below the distance to the border of the
 // visited block (so no unvisited point can be closer or tie).  Returns false on a window miss.
 template <bool Z3, class Acc>
-FICP_HD bool nn_ring_loop(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
-                          int r_start, double& best, int& bestpos) {
+FICP_HD bool nn_ring_loop_impl(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
+                               int r_start, double& best, int& bestpos) {
     for (int r = r_start;; ++r) {
         const int xl = cx - (r - 1), xh = cx + (r - 1), yl = cy - (r - 1), yh = cy + (r - 1);
         double b = kInf;
@@ -184,6 +201,37 @@ FICP_HD bool nn_ring_loop(const Acc& acc, const GridGeom& g, double qx, double q
     return true;
 }
 
+// Quick exit when the visited block of radius r_start-1 already bounds the search (the common case), else the
+// out-of-line ring loop.
+struct NNState { double best; int pos; int ok; };
+template <bool Z3, class Acc>
+FICP_COLD_RING NNState nn_ring_loop_cold(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
+                                    int r_start, double best, int bestpos) {
+    NNState st;
+    st.ok = nn_ring_loop_impl<Z3>(acc, g, qx, qy, qz, cx, cy, r_start, best, bestpos) ? 1 : 0;
+    st.best = best;
+    st.pos = bestpos;
+    return st;
+}
+template <bool Z3, class Acc>
+FICP_HD bool nn_ring_loop(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
+                          int r_start, double& best, int& bestpos) {
+    // same termination test as the first iteration of the ring loop
+    const int xl = cx - (r_start - 1), xh = cx + (r_start - 1), yl = cy - (r_start - 1), yh = cy + (r_start - 1);
+    double b = kInf;
+    if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
+    if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
+    if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
+    if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
+    if (b == kInf) return true;
+    b -= g.eps;
+    if (b > 0.0 && best < b * b) return true;
+    const NNState st = nn_ring_loop_cold<Z3>(acc, g, qx, qy, qz, cx, cy, r_start, best, bestpos);
+    best = st.best;
+    bestpos = st.pos;
+    return st.ok != 0;
+}
+
 // Reference form of the search (ring by ring from the query's own cell).  Returns false when the search
 // needs cells the accessor does not cover (window miss): the caller then repeats the query with
 // GlobalAcc.  On success best = squared distance (canonical arithmetic) and bestpos = accessor-local
@@ -198,10 +246,6 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
     if (!acc.covers(cx, cx, cy, cy)) return false;
     nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
     return nn_ring_loop<Z3>(acc, g, qx, qy, qz, cx, cy, 1, best, bestpos);
-}
-
-FICP_HD double nn_box_gap(double lo, double hi, double q) {  // distance from q to the interval [lo, hi]
-    return fmax(fmax(lo - q, q - hi), 0.0);
 }
 
 // Production form used by the kernels: the 3x3 block around the query's cell is visited as ONE flat
@@ -225,15 +269,17 @@ FICP_HD bool nn_search_stream(const Acc& acc, const GridGeom& g, double qx, doub
     best = kInf;
     bestpos = -1;
     if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
-    // squared gaps between the query and the three cell columns / rows (boxes inflated by eps)
-    const double X0 = g.x0 + cx * g.h, Y0 = g.y0 + cy * g.h, h = g.h, eps = g.eps;
+    // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
+    // query from the lower-left corner of its (clamped) cell; it lies in [0, h] unless the query is off the grid.
+    const double h = g.h, eps = g.eps;
+    const double ux = qx - (g.x0 + cx * h), uy = qy - (g.y0 + cy * h);
     double gx[3], gy[3];
-    gx[0] = nn_box_gap(X0 - h - eps, X0 + eps, qx);
-    gx[1] = nn_box_gap(X0 - eps, X0 + h + eps, qx);
-    gx[2] = nn_box_gap(X0 + h - eps, X0 + 2.0 * h + eps, qx);
-    gy[0] = nn_box_gap(Y0 - h - eps, Y0 + eps, qy);
-    gy[1] = nn_box_gap(Y0 - eps, Y0 + h + eps, qy);
-    gy[2] = nn_box_gap(Y0 + h - eps, Y0 + 2.0 * h + eps, qy);
+    gx[0] = fmax(ux - eps, 0.0);
+    gx[1] = fmax(fmax(-ux, ux - h) - eps, 0.0);
+    gx[2] = fmax(h - ux - eps, 0.0);
+    gy[0] = fmax(uy - eps, 0.0);
+    gy[1] = fmax(fmax(-uy, uy - h) - eps, 0.0);
+    gy[2] = fmax(h - uy - eps, 0.0);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
     int s[3], n[3];
