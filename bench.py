@@ -378,10 +378,15 @@ def run_b200(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        if _POOL is not None:
+            _POOL[0].terminate()
+            _POOL[0].join()
 
 
 if __name__ == "__main__":

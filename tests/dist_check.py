@@ -1,0 +1,42 @@
+"""Run under torchrun on >= 2 GPUs: the sharded search must pick exactly the winner the single-GPU search picks.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from coregistrationgame_b200 import _lib, register_batch  # noqa: E402
+from coregistrationgame_b200.dist import register_batch_distributed  # noqa: E402
+from oracle import ficp_oracle as orc  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.check(_lib.load().ficp_set_device(local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    tgt, plots, _ = orc.synthetic_scene(200000, 200, seed=7, dims=3, n_plots=5, hidden_pose=True)
+    hyp = orc.hypothesis_table(32, flips=(0, 1), translations=orc.translation_lattice(2, 2.5))
+    d = register_batch_distributed(plots, tgt, hyp)
+    s = register_batch(plots, tgt, hyp)
+    np.testing.assert_array_equal(d["best_key"], s["best_key"])
+    np.testing.assert_array_equal(d["best_hyp"], s["best_hyp"])
+    np.testing.assert_array_equal(d["best_transform"], s["best_transform"])
+    np.testing.assert_array_equal(d["k"], s["best_row"]["k"])
+    assert d["passes_global"] == s["stats"]["passes"], (d["passes_global"], s["stats"]["passes"])
+    assert d["passes_local"] < s["stats"]["passes"]
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_check ok: world={world} plots={len(plots)} hyps={hyp.shape[0]} winners={d['best_hyp'].tolist()} "
+              f"passes global={d['passes_global']}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, argument validation mirrors the reference, and the host helpers agree with the oracle.
+No compute call is made here (there is no GPU in the build container and no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ficp_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "ficp_b200.h")).read()
+    return sorted(set(re.findall(r"FICP_API\s+[\w\s\*]+?\b(ficp_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from coregistrationgame_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and include/ficp_b200.h disagree"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\bT (ficp_\w+)", out)))
+    assert exported == declared, "exported symbols differ from the header"
+
+
+def test_abi_struct_sizes():
+    import ctypes as C
+    from coregistrationgame_b200 import _lib
+    assert _lib.HYP_RESULT_DTYPE.itemsize == 80
+    assert C.sizeof(_lib.BatchParams) == 48
+    assert C.sizeof(_lib.TargetInfo) == 88
+
+
+def test_no_device_fails_loudly():
+    from coregistrationgame_b200 import _lib, TargetIndex
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.FicpError):
+        _lib.require_device()
+    with pytest.raises(_lib.FicpError):
+        TargetIndex(np.zeros((4, 2)))
+    from ficp import FractionalICP
+    icp = FractionalICP(np.random.default_rng(0).normal(size=(5, 3)), np.random.default_rng(1).normal(size=(6, 3)))
+    with pytest.raises(_lib.FicpError):          # no silent CPU path
+        icp.run()
+
+
+def test_constructor_and_degenerate_inputs_without_gpu():
+    """ficp.py:34-44 and the empty-input conventions (ficp.py:66-68,76-77,125-126) need no device."""
+    from ficp import FractionalICP
+    with pytest.raises(ValueError, match="2D arrays"):
+        FractionalICP(np.zeros(3), np.zeros((3, 2)))
+    icp = FractionalICP([[0, 0, 1], [1, 1, 2]], [[0.0, 0.0], [1.0, 1.0]])
+    assert icp.match_dims == 2 and icp.source.dtype == np.float64
+    assert (icp.lambda_val, icp.threshold, icp.max_iterations, icp.allow_reflection) == (3.0, 1e-6, 1000, False)
+    e = FractionalICP(np.empty((0, 3)), np.ones((4, 3)))
+    assert e.run().shape == (0, 3) and e.lambda_val == 0.95
+    src = np.arange(12, dtype=float).reshape(4, 3)
+    t = FractionalICP(src, np.empty((0, 3)))
+    corr, dist = t.find_correspondences(src, np.empty((0, 3)))
+    assert corr.shape == (0, 3) and dist.size == 0 and t.find_optimal_fraction(corr, dist) == (0.0, 0)
+    np.testing.assert_array_equal(t.run(), src)
+    assert t.frmsd(0.5, 0, src, src) == float("inf")
+
+
+def test_host_helpers_match_oracle():
+    from coregistrationgame_b200 import batch
+    np.testing.assert_array_equal(batch.hypothesis_table(16, (0, 1), batch.translation_lattice(3, 2.5)),
+                                  orc.hypothesis_table(16, (0, 1), orc.translation_lattice(3, 2.5)))
+    for n, lam in ((1, 3.0), (17, 1.3), (500, 0.95)):
+        np.testing.assert_array_equal(batch.frmsd_weights(n, lam), orc.frmsd_weights(n, lam))
+    for n in (1, 9, 150, 500):
+        for f in (0.5, 0.6, 0.7, 0.8, 0.9, 0.95, 1.0):
+            assert batch.fixed_fraction_k(n, f) == orc.fixed_fraction_k(n, f)
+    keys = np.array([orc.pack_best_key(0.25, 7), orc.pack_best_key(np.inf, 0), orc.pack_best_key(0.0, 4095)], dtype=np.uint64)
+    dec = batch.decode_best_keys(keys)
+    np.testing.assert_array_equal(dec["best_hyp"], [7, 0, 4095])
+    np.testing.assert_array_equal(dec["best_score"], [0.25, np.inf, 0.0])
+    # key order = (score, id) order
+    assert orc.pack_best_key(0.25, 9) > orc.pack_best_key(0.25, 7) > orc.pack_best_key(0.2499, 4000)
+
+
+def test_product_path_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "coregistrationgame_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", "").replace("as the oracle", ""), f
+    assert "oracle" not in open(os.path.join(ROOT, "ficp.py")).read()
+
+
+def test_nn_search_host_check(tmp_path):
+    """The grid NN search (ring/termination/tie logic, window + global accessors, streamed form with arbitrary
+    seeds) is host-compilable: build it with g++ and compare 19 200 queries against brute force."""
+    exe = tmp_path / "nn_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "coregistrationgame_b200", "csrc"),
+                           "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "hostcheck", "nn_search_check.cpp"),
+                           "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "mismatches=0" in out.stdout
