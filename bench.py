@@ -310,8 +310,13 @@ def run_b200(args):
         b.record(stream)
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
+        l2 = C.c_double(0.0)
+        _lib.check(lib.ficp_measure_l2_read_gbs(32 << 20, 20, C.byref(l2)))
+        alg = nq * ALG_BYTES_PER_QUERY / (ms * 1e-3) / 1e9
         extra["nn_query_kernel"] = {"queries": nq, "ms": ms, "queries_per_s": nq / (ms * 1e-3),
-                                    "alg_GBps_L2_level": nq * ALG_BYTES_PER_QUERY / (ms * 1e-3) / 1e9}
+                                    "alg_GBps_L2_level": alg, "l2_read_peak_GBps_measured": l2.value,
+                                    "frac_of_l2_peak": alg / l2.value if l2.value else None,
+                                    "hbm_compulsory_GBps": nq * 24.0 / (ms * 1e-3) / 1e9}
         extra["grid_build"] = {"points": int(tinfo["m"]), "ms": tinfo["build_ms"],
                                "alg_GBps": tinfo["m"] * GRID_BYTES_PER_POINT / (tinfo["build_ms"] * 1e-3) / 1e9,
                                "grid": [tinfo["grid_w"], tinfo["grid_h"]], "cell_m": tinfo["cell"]}

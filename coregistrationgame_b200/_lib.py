@@ -47,6 +47,7 @@ SIGNATURES = {
     "ficp_device_count": (c_i32, [P(c_i32)]),
     "ficp_set_device": (c_i32, [c_i32]),
     "ficp_device_props": (c_i32, [P(c_i32), P(c_i64), P(c_i64), P(c_i32)]),
+    "ficp_measure_l2_read_gbs": (c_i32, [c_i64, c_i32, P(c_f64)]),
     "ficp_target_create": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_f64, c_vp, P(c_vp)]),
     "ficp_target_create_device": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_f64, c_vp, P(c_vp)]),
     "ficp_target_get_info": (c_i32, [c_vp, P(TargetInfo)]),

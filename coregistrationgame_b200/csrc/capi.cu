@@ -103,6 +103,11 @@ int ficp_device_props(int32_t* sms, int64_t* l2_bytes, int64_t* smem_optin, int3
     return kOk;
 }
 
+int ficp_measure_l2_read_gbs(int64_t bytes, int32_t iters, double* gbs) {
+    if (!gbs || bytes < 4096 || iters < 1) { set_error("ficp_measure_l2_read_gbs: bad arguments"); return kErrInvalid; }
+    return measure_l2_read_gbs((size_t)bytes, iters, gbs);
+}
+
 // ------------------------------------------------------------------------------------------ target
 int ficp_target_create(const double* pts_host, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
                        void* stream, ficp_target** out) {

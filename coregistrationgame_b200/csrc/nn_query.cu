@@ -31,7 +31,47 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     if (d2out) d2out[i] = best;
 }
 
+// Measurement aid: read-only sweep over a buffer that fits in L2, 16 B per thread per step.
+__global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int iters,
+                                                      unsigned* __restrict__ sink) {
+    unsigned acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it)
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) *sink = acc;  // keeps the loads alive
+}
+
 }  // namespace
+
+int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
+    uint4* buf = nullptr;
+    unsigned* sink = nullptr;
+    const size_t n_vec = bytes / sizeof(uint4);
+    FICP_CUDA(cudaMalloc(&buf, n_vec * sizeof(uint4)));
+    FICP_CUDA(cudaMalloc(&sink, sizeof(unsigned)));
+    FICP_CUDA(cudaMemset(buf, 1, n_vec * sizeof(uint4)));
+    cudaEvent_t a, b;
+    FICP_CUDA(cudaEventCreate(&a));
+    FICP_CUDA(cudaEventCreate(&b));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    l2_read_kernel<<<sms * 8, 256>>>(buf, n_vec, 2, sink);  // warm the L2
+    FICP_CUDA(cudaEventRecord(a));
+    l2_read_kernel<<<sms * 8, 256>>>(buf, n_vec, iters, sink);
+    FICP_CUDA(cudaEventRecord(b));
+    FICP_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *gbs = (double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    cudaFree(sink);
+    return kOk;
+}
 
 int launch_nn_query(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
                     double* d_d2, cudaStream_t stream) {

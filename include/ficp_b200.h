@@ -83,6 +83,9 @@ FICP_API int ficp_set_device(int32_t device);
 /* sms, L2 bytes, opt-in shared memory per block, SM clock kHz */
 FICP_API int ficp_device_props(int32_t* sms, int64_t* l2_bytes, int64_t* smem_optin, int32_t* clock_khz);
 
+/* measurement aid for bench.py: read bandwidth of a buffer of `bytes` that stays in L2, GB/s */
+FICP_API int ficp_measure_l2_read_gbs(int64_t bytes, int32_t iters, double* gbs);
+
 /* ---- kernel 1a: grid build.  Replaces cKDTree(target) (ficp.py:69), hoisted out of the loop. */
 FICP_API int ficp_target_create(const double* pts_host, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
                        void* stream, ficp_target** out);

@@ -281,3 +281,35 @@ def test_full_size_c3_properties(gpu, dims):
     assert out["stats"]["passes"] == int(rows["passes"].sum())
     b.close()
     ti.close()
+
+
+def test_many_plots_one_pose_each_c4_shape(gpu):
+    """Config 4 shape, scaled to the test budget: 600 plots x 150 trees against one shared 2e6-point CHM, ONE ICP per
+    plot (the pose the user dragged it to), all in one launch.  A strided sample is checked against the oracle."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(2_000_000, 150, seed=4, dims=3, n_plots=600, hidden_pose=False)
+    rng = np.random.default_rng(0)
+    starts = []
+    for p in plots:
+        row = np.r_[orc.hypothesis_matrix(rng.uniform(-6.0, 6.0), 0).ravel(), rng.uniform(-2.0, 2.0, 2)]
+        starts.append(orc.pre_transform(p, row, p[:, :2].mean(axis=0)))
+    ti = TargetIndex(tgt)
+    b = IcpBatch(ti, starts, None, centres=np.zeros((len(starts), 2)), min_k=0, want_final_xy=True)
+    assert b.info["n_hyp_local"] == 1 and b.info["warps_per_cta"] == 1
+    out = b.run().results()
+    rows = out["hyp"][:, 0]
+    offs = b.offsets
+    from scipy.spatial import cKDTree
+    tree = cKDTree(tgt)
+    for p in range(0, len(starts), 25):
+        tr = orc.RunTrace()
+        ref = starts[p]
+        for lam in (3.0, orc.STAGE2_LAMBDA[3]):
+            ref = orc.icp_stage(ref, tgt, 3, lam, nn="tree", tree=tree, trace=tr, closed_form=True)
+        assert rows["passes"][p] == tr.passes and rows["k"][p] == tr.records[-1].k, p
+        np.testing.assert_allclose(out["final_xy"][offs[p]:offs[p + 1]], ref[:, :2], rtol=0, atol=1e-6)
+    # most plots snap back onto their trees (position noise 0.3 m in XY, 1 m in Z)
+    assert np.mean(rows["rmse"] < 1.6) > 0.9
+    assert out["stats"]["passes"] == int(rows["passes"].sum())
+    b.close()
+    ti.close()
