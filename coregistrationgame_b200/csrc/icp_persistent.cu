@@ -366,7 +366,7 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
     // shift point: the plot centroid under the current pose (keeps the running sums well conditioned)
     const double ax = P.m00 * pc.ubx + P.m01 * pc.uby + P.cx;
     const double ay = P.m10 * pc.ubx + P.m11 * pc.uby + P.cy;
-    double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+    double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0, habs = 0;
 #pragma unroll 2
     for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
@@ -380,11 +380,13 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
                 const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
                 su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
                 h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
+                habs += (fabs(ux) + fabs(uy)) * (fabs(vx) + fabs(vy));  // magnitude of the terms (noise scale)
             }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        habs += __shfl_xor_sync(kFull, habs, o);
         su0 += __shfl_xor_sync(kFull, su0, o); su1 += __shfl_xor_sync(kFull, su1, o);
         sv0 += __shfl_xor_sync(kFull, sv0, o); sv1 += __shfl_xor_sync(kFull, sv1, o);
         h00 += __shfl_xor_sync(kFull, h00, o); h01 += __shfl_xor_sync(kFull, h01, o);
@@ -394,11 +396,10 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
     const double mu0 = su0 * inv_k, mu1 = su1 * inv_k, mv0 = sv0 * inv_k, mv1 = sv1 * inv_k;
     // centred cross-covariance H = sum (u - mu)(v - mv)^T, from the shifted sums.  When the exact H is zero
     // (k == 1, or all inlier trees coincide - the reference's centred sums are then exactly 0 and its SVD
-    // returns R = I) the subtraction below leaves only rounding noise: detect that and use H = 0.
-    const double hscale = fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) +
-                          (fabs(su0) + fabs(su1)) * (fabs(mv0) + fabs(mv1));
+    // returns R = I) the subtraction below leaves only rounding noise, of the order 1e-16 * sum |u||v|: detect
+    // that (against the magnitude sum `habs`, not the signed sums, which may cancel too) and use H = 0.
     h00 -= su0 * mv0; h01 -= su0 * mv1; h10 -= su1 * mv0; h11 -= su1 * mv1;
-    if (fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) <= 1e-12 * hscale) h00 = h01 = h10 = h11 = 0.0;
+    if (fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) <= 1e-12 * habs) h00 = h01 = h10 = h11 = 0.0;
     double r00, r01, r10, r11;
     // reflection only when det(H) is negative beyond rounding noise (det == 0: SVD's choice is arbitrary)
     if (allow_reflection && (h00 * h11 - h01 * h10) < -1e-14 * (fabs(h00 * h11) + fabs(h01 * h10))) {

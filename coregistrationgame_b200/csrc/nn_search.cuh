@@ -168,6 +168,23 @@ FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, in
     nn_scan_segment<Z3>(acc, y, xa, xb, qx, qy, qz, best, bestpos);
 }
 
+// Squared lower bound on the distance from the query to ANY point outside the block of cells of Chebyshev
+// radius `rad` around (cx, cy); +inf when the block already spans the whole grid.  A point beyond the block's
+// left/right side is at least that side's distance away in x AND at least the query's gap to the grid's
+// y-extent away in y (every point lies inside the grid), and vice versa - this keeps searches of queries far
+// off the map (a start pose thrown off the stand) from walking the whole grid.
+FICP_HD double nn_block_bound2(const GridGeom& g, double qx, double qy, int cx, int cy, int rad) {
+    const int xl = cx - rad, xh = cx + rad, yl = cy - rad, yh = cy + rad;
+    const double ox = fmax(fmax(g.x0 - qx, qx - (g.x0 + g.gw * g.h)) - g.eps, 0.0);  // gap to the grid's x-extent
+    const double oy = fmax(fmax(g.y0 - qy, qy - (g.y0 + g.gh * g.h)) - g.eps, 0.0);
+    double b2 = kInf;
+    if (xl > 0) { const double b = fmax(qx - (g.x0 + xl * g.h) - g.eps, 0.0); b2 = fmin(b2, b * b + oy * oy); }
+    if (xh < g.gw - 1) { const double b = fmax((g.x0 + (xh + 1) * g.h) - qx - g.eps, 0.0); b2 = fmin(b2, b * b + oy * oy); }
+    if (yl > 0) { const double b = fmax(qy - (g.y0 + yl * g.h) - g.eps, 0.0); b2 = fmin(b2, b * b + ox * ox); }
+    if (yh < g.gh - 1) { const double b = fmax((g.y0 + (yh + 1) * g.h) - qy - g.eps, 0.0); b2 = fmin(b2, b * b + ox * ox); }
+    return b2;
+}
+
 // Rings r_start, r_start+1, ... around cell (cx, cy); every cell of Chebyshev radius < r_start has been
 // visited already.  Stops when the best distance is strictly below the distance to the border of the
 // visited block (so no unvisited point can be closer or tie).  Returns false on a window miss.
@@ -175,15 +192,9 @@ template <bool Z3, class Acc>
 FICP_HD bool nn_ring_loop_impl(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
                                int r_start, double& best, int& bestpos) {
     for (int r = r_start;; ++r) {
-        const int xl = cx - (r - 1), xh = cx + (r - 1), yl = cy - (r - 1), yh = cy + (r - 1);
-        double b = kInf;
-        if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
-        if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
-        if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
-        if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
-        if (b == kInf) break;  // the block already spans the whole grid
-        b -= g.eps;
-        if (b > 0.0 && best < b * b) break;
+        const double b2 = nn_block_bound2(g, qx, qy, cx, cy, r - 1);
+        if (b2 == kInf) break;        // the block already spans the whole grid
+        if (best < b2) break;         // strict: an unvisited point can neither beat nor tie the best
         const int nxl = (cx - r > 0) ? cx - r : 0;
         const int nxh = (cx + r < g.gw - 1) ? cx + r : g.gw - 1;
         const int nyl = (cy - r > 0) ? cy - r : 0;
@@ -216,16 +227,20 @@ FICP_COLD_RING NNState nn_ring_loop_cold(const Acc& acc, const GridGeom& g, doub
 template <bool Z3, class Acc>
 FICP_HD bool nn_ring_loop(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
                           int r_start, double& best, int& bestpos) {
-    // same termination test as the first iteration of the ring loop
-    const int xl = cx - (r_start - 1), xh = cx + (r_start - 1), yl = cy - (r_start - 1), yh = cy + (r_start - 1);
-    double b = kInf;
-    if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
-    if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
-    if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
-    if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
-    if (b == kInf) return true;
-    b -= g.eps;
-    if (b > 0.0 && best < b * b) return true;
+    // cheap form of the bound first (side distances only; it never exceeds the exact block bound, so exiting on
+    // it is safe) - this is the per-query common case
+    {
+        const int rad = r_start - 1;
+        const int xl = cx - rad, xh = cx + rad, yl = cy - rad, yh = cy + rad;
+        double b = kInf;
+        if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
+        if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
+        if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
+        if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
+        if (b == kInf) return true;
+        b -= g.eps;
+        if (b > 0.0 && best < b * b) return true;
+    }
     const NNState st = nn_ring_loop_cold<Z3>(acc, g, qx, qy, qz, cx, cy, r_start, best, bestpos);
     best = st.best;
     bestpos = st.pos;

@@ -161,7 +161,8 @@ int main() {
             double r = U(rng);
             if (r < 0.6) { qx[i] = offx + side * U(rng); qy[i] = offy + side * U(rng); }
             else if (r < 0.8) { size_t j = rng() % m; qx[i] = px[j] + 0.3 * (U(rng) - 0.5); qy[i] = py[j] + 0.3 * (U(rng) - 0.5); }
-            else if (r < 0.9) { qx[i] = offx + side * (3 * U(rng) - 1); qy[i] = offy + side * (3 * U(rng) - 1); }  // outside the grid
+            else if (r < 0.88) { qx[i] = offx + side * (3 * U(rng) - 1); qy[i] = offy + side * (3 * U(rng) - 1); }  // outside the grid
+            else if (r < 0.9) { qx[i] = offx + side * (40 * U(rng) - 20); qy[i] = offy + side * (40 * U(rng) - 20); }  // far off the map
             else { qx[i] = offx + side / 2 + (rng() % 8) + 0.5; qy[i] = offy + side * 0.5 + (rng() % 8) * 0.25 + 0.125; }  // lattice centres
             qz[i] = 5 + 30 * U(rng);
         }

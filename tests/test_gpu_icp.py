@@ -313,3 +313,31 @@ def test_many_plots_one_pose_each_c4_shape(gpu):
     assert out["stats"]["passes"] == int(rows["passes"].sum())
     b.close()
     ti.close()
+
+
+def test_batch_tiny_targets_and_off_map_poses(gpu):
+    """Degenerate scenes: 1-3 CHM points; and start poses thrown kilometres off the stand (the exact search must
+    stay bounded and still agree with the oracle)."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    rng = np.random.default_rng(3)
+    src = rng.normal(size=(12, 2)) * 4.0
+    hyp = orc.hypothesis_table(4, flips=(0,))
+    for m in (1, 2, 3):
+        # When every inlier maps to the SAME CHM point the reference's centred targets are +-1 ulp instead of 0 and
+        # its SVD returns a rounding-noise rotation (parity unpinned); the kernel treats that H as 0 -> R = I, i.e. a
+        # pure translation.  Check that, not the noise.
+        tgt = rng.normal(size=(m, 2)) * 3.0
+        ti = TargetIndex(tgt)
+        b = IcpBatch(ti, [src], hyp, min_k=0)
+        rows = b.run().results()["hyp"][0]
+        assert np.isfinite(rows["frmsd"]).all() and (rows["passes"] >= 2).all() and (rows["k"] >= 1).all()
+        det = rows["m00"] * rows["m11"] - rows["m01"] * rows["m10"]
+        np.testing.assert_allclose(det, 1.0, atol=1e-12)
+        if m == 1:   # rotation part untouched: only translations are ever fitted
+            np.testing.assert_allclose(np.stack([rows["m00"], rows["m01"], rows["m10"], rows["m11"]], 1), hyp[:, :4], atol=1e-15)
+        b.close()
+        ti.close()
+    tgt, plots, _ = orc.synthetic_scene(200000, 60, seed=6, dims=3, hidden_pose=True)
+    far = orc.hypothesis_table(3, flips=(0,), translations=[(0.0, 0.0), (25000.0, -18000.0), (-400.0, 90000.0)])
+    out = _check_batch_against_oracle(tgt, plots, far)
+    assert out["stats"]["global_path_queries"] > 0
