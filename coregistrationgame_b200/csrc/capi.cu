@@ -21,15 +21,34 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return kErrCuda;
 }
 
+cudaError_t dev_alloc(void** p, size_t bytes) {
+    static thread_local int pool_ready_for = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (pool_ready_for != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;  // never trim: freed blocks stay in the pool for the next index / batch
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready_for = dev;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0);
+}
+void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}
+
 static_assert(sizeof(ficp_hyp_result) == sizeof(HypResult), "ABI struct mismatch");
 
 // RAII device buffer for the host-buffer convenience calls
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    ~DevBuf() { dev_free(p); }
     int alloc(size_t n) {
-        FICP_CUDA(cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)));
+        FICP_CUDA(dev_alloc_t(&p, n));
         return kOk;
     }
 };
@@ -54,8 +73,8 @@ struct Batch {
     int* d_counters = nullptr;  // [0] slice counter, [1..n_plots] hypothesis counters
     unsigned long long* d_stats = nullptr;
     ~Batch() {
-        cudaFree(d_src_u); cudaFree(d_src_z); cudaFree(d_plots); cudaFree(d_hyp); cudaFree(d_tabs);
-        cudaFree(d_results); cudaFree(d_best); cudaFree(d_final); cudaFree(d_counters); cudaFree(d_stats);
+        dev_free(d_src_u); dev_free(d_src_z); dev_free(d_plots); dev_free(d_hyp); dev_free(d_tabs);
+        dev_free(d_results); dev_free(d_best); dev_free(d_final); dev_free(d_counters); dev_free(d_stats);
     }
 };
 
@@ -442,16 +461,16 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     }
 
     // ---- device buffers
-    FICP_CUDA(cudaMalloc(&b->d_src_u, sizeof(double2) * (size_t)rows));
-    if (z3) FICP_CUDA(cudaMalloc(&b->d_src_z, sizeof(double) * (size_t)rows));
-    FICP_CUDA(cudaMalloc(&b->d_plots, sizeof(PlotMeta) * (size_t)n_plots));
-    FICP_CUDA(cudaMalloc(&b->d_hyp, sizeof(double) * 6 * (size_t)n_hyp));
-    FICP_CUDA(cudaMalloc(&b->d_tabs, sizeof(double) * h_tabs.size()));
-    FICP_CUDA(cudaMalloc(&b->d_results, sizeof(HypResult) * (size_t)n_plots * n_hyp_local));
-    FICP_CUDA(cudaMalloc(&b->d_best, sizeof(unsigned long long) * (size_t)n_plots));
-    if (b->want_final) FICP_CUDA(cudaMalloc(&b->d_final, sizeof(double) * 2 * (size_t)rows));
-    FICP_CUDA(cudaMalloc(&b->d_counters, sizeof(int) * (size_t)(n_plots + 1)));
-    FICP_CUDA(cudaMalloc(&b->d_stats, sizeof(unsigned long long) * 8));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows));
+    if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_plots), sizeof(PlotMeta) * (size_t)n_plots));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_hyp), sizeof(double) * 6 * (size_t)n_hyp));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tabs), sizeof(double) * h_tabs.size()));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_results), sizeof(HypResult) * (size_t)n_plots * n_hyp_local));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_best), sizeof(unsigned long long) * (size_t)n_plots));
+    if (b->want_final) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_final), sizeof(double) * 2 * (size_t)rows));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_counters), sizeof(int) * (size_t)(n_plots + 1)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_stats), sizeof(unsigned long long) * 8));
     FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.data(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
     if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.data(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));

@@ -24,6 +24,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return ::ficp::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
 
+// ---- device memory: stream-ordered allocator with a retaining pool -----------------------------------------
+// cudaMalloc/cudaFree of the tens-of-MB index buffers cost 30-150 ms per call pair on B200 (measured, driver
+// 580); the default mempool with a raised release threshold makes repeated index / batch creation reuse memory.
+cudaError_t dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+template <class T>
+inline cudaError_t dev_alloc_t(T** p, size_t count) { return dev_alloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1)); }
+
 // ---- target index -----------------------------------------------------------------------------
 struct Target {
     int device = 0;

@@ -221,10 +221,10 @@ __global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsig
 
 void target_free(Target* t) {
     if (!t) return;
-    cudaFree(t->d_xy);
-    cudaFree(t->d_z);
-    cudaFree(t->d_orig);
-    cudaFree(t->d_cell_start);
+    dev_free(t->d_xy);
+    dev_free(t->d_z);
+    dev_free(t->d_orig);
+    dev_free(t->d_cell_start);
     delete t;
 }
 
@@ -250,8 +250,8 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
         double* raw = nullptr; unsigned* cellid = nullptr; unsigned* counts = nullptr; unsigned* fill = nullptr;
         unsigned* bsum = nullptr; BBox* part = nullptr;
         ~Guard() {
-            cudaFree(cellid); cudaFree(counts); cudaFree(fill); cudaFree(bsum); cudaFree(part);
-            if (raw) cudaFree(raw);
+            dev_free(cellid); dev_free(counts); dev_free(fill); dev_free(bsum); dev_free(part);
+            dev_free(raw);
             if (armed) target_free(t);
         }
     } g{t};
@@ -265,7 +265,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
 
     const double* d_pts = pts;
     if (!on_device) {
-        FICP_CUDA(cudaMalloc(&g.raw, sizeof(double) * (size_t)m * ld));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.raw), sizeof(double) * (size_t)m * ld));
         FICP_CUDA(cudaMemcpyAsync(g.raw, pts, sizeof(double) * (size_t)m * ld, cudaMemcpyHostToDevice, stream));
         d_pts = g.raw;
     }
@@ -275,7 +275,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
 
     // ---- bounding box + finiteness
     const int nb_bbox = (int)std::min<long long>((m + kT - 1) / kT, 148 * 8);
-    FICP_CUDA(cudaMalloc(&g.part, sizeof(BBox) * (nb_bbox + 1)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.part), sizeof(BBox) * (nb_bbox + 1)));
     FICP_CUDA(cudaEventRecord(ev0, stream));
     bbox_kernel<<<nb_bbox, kT, 0, stream>>>(d_pts, m, ld, use_z, g.part);
     bbox_final_kernel<<<1, 32, 0, stream>>>(g.part, nb_bbox, g.part + nb_bbox);
@@ -319,15 +319,15 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     const long long nc = (long long)gg.gw * gg.gh;
 
     // ---- counting sort
-    FICP_CUDA(cudaMalloc(&g.cellid, sizeof(unsigned) * (size_t)m));
-    FICP_CUDA(cudaMalloc(&g.counts, sizeof(unsigned) * (size_t)nc));
-    FICP_CUDA(cudaMalloc(&g.fill, sizeof(unsigned) * (size_t)nc));
-    FICP_CUDA(cudaMalloc(&t->d_cell_start, sizeof(unsigned) * (size_t)(nc + 1)));
-    FICP_CUDA(cudaMalloc(&t->d_xy, sizeof(double2) * (size_t)m));
-    if (use_z) FICP_CUDA(cudaMalloc(&t->d_z, sizeof(double) * (size_t)m));
-    FICP_CUDA(cudaMalloc(&t->d_orig, sizeof(int) * (size_t)m));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.cellid), sizeof(unsigned) * (size_t)m));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.fill), sizeof(unsigned) * (size_t)nc));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc + 1)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m));
+    if (use_z) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_z), sizeof(double) * (size_t)m));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m));
     const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
-    FICP_CUDA(cudaMalloc(&g.bsum, sizeof(unsigned) * (size_t)nb_scan));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.bsum), sizeof(unsigned) * (size_t)nb_scan));
     FICP_CUDA(cudaEventRecord(ev0, stream));   // device time of the build = bbox kernels + everything from here
     FICP_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(unsigned) * (size_t)nc, stream));
     FICP_CUDA(cudaMemsetAsync(g.fill, 0, sizeof(unsigned) * (size_t)nc, stream));

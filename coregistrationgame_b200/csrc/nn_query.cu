@@ -50,8 +50,8 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     uint4* buf = nullptr;
     unsigned* sink = nullptr;
     const size_t n_vec = bytes / sizeof(uint4);
-    FICP_CUDA(cudaMalloc(&buf, n_vec * sizeof(uint4)));
-    FICP_CUDA(cudaMalloc(&sink, sizeof(unsigned)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&buf), n_vec * sizeof(uint4)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&sink), sizeof(unsigned)));
     FICP_CUDA(cudaMemset(buf, 1, n_vec * sizeof(uint4)));
     cudaEvent_t a, b;
     FICP_CUDA(cudaEventCreate(&a));
@@ -68,8 +68,8 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     *gbs = (double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    cudaFree(buf);
-    cudaFree(sink);
+    dev_free(buf);
+    dev_free(sink);
     return kOk;
 }
 

@@ -341,3 +341,48 @@ def test_batch_tiny_targets_and_off_map_poses(gpu):
     far = orc.hypothesis_table(3, flips=(0,), translations=[(0.0, 0.0), (25000.0, -18000.0), (-400.0, 90000.0)])
     out = _check_batch_against_oracle(tgt, plots, far)
     assert out["stats"]["global_path_queries"] > 0
+
+
+def test_full_size_c4_properties(gpu):
+    """Config 4 at full size: 10^4 plots x 150 trees against one shared 10^7-point CHM, one ICP per plot, one
+    launch.  Size-independent properties + a strided oracle sample."""
+    from scipy.spatial import cKDTree
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(10_000_000, 150, seed=4, dims=3, n_plots=10000, hidden_pose=False)
+    rng = np.random.default_rng(1)
+    starts, rows_in = [], []
+    for p in plots:
+        row = np.r_[orc.hypothesis_matrix(rng.uniform(-5.0, 5.0), 0).ravel(), rng.uniform(-1.5, 1.5, 2)]
+        starts.append(orc.pre_transform(p, row, p[:, :2].mean(axis=0)))
+        rows_in.append(row)
+    ti = TargetIndex(tgt)
+    info = ti.info()
+    assert info["m"] == 10_000_000
+    b = IcpBatch(ti, starts, None, centres=np.zeros((len(starts), 2)), min_k=0, want_final_xy=True)
+    out = b.run().results()
+    rows = out["hyp"][:, 0]
+    offs = b.offsets
+    # proper rotations, FRMSD = (N/k)^lambda * rmse, Z untouched by construction, every plot did >= 2 passes
+    np.testing.assert_allclose(rows["m00"] * rows["m11"] - rows["m01"] * rows["m10"], 1.0, atol=1e-12)
+    np.testing.assert_allclose(rows["frmsd"], (150.0 / rows["k"]) ** orc.STAGE2_LAMBDA[3] * rows["rmse"], rtol=1e-12)
+    assert (rows["passes"] >= 2).all() and out["stats"]["passes"] == int(rows["passes"].sum())
+    # the start perturbation is undone: rotation recovered to < 1 degree for the vast majority of plots
+    ang = np.degrees(np.arctan2(rows["m10"], rows["m00"]))
+    want = -np.array([np.degrees(np.arctan2(r[2], r[0])) for r in rows_in])
+    assert np.mean(np.abs(ang - want) < 1.0) > 0.9
+    assert np.mean(rows["rmse"] < 1.6) > 0.9
+    # rigid: pairwise distances of a plot are preserved by its final pose
+    for p in (0, 4999, 9999):
+        a, f = starts[p][:, :2], out["final_xy"][offs[p]:offs[p + 1]]
+        np.testing.assert_allclose(np.linalg.norm(a[1:] - a[:-1], axis=1), np.linalg.norm(f[1:] - f[:-1], axis=1), atol=1e-9)
+    # strided oracle sample (kd-tree NN with the same tie rule)
+    tree = cKDTree(tgt)
+    for p in range(0, 10000, 1250):
+        tr = orc.RunTrace()
+        ref = starts[p]
+        for lam in (3.0, orc.STAGE2_LAMBDA[3]):
+            ref = orc.icp_stage(ref, tgt, 3, lam, nn="tree", tree=tree, trace=tr, closed_form=True)
+        assert rows["passes"][p] == tr.passes and rows["k"][p] == tr.records[-1].k, p
+        np.testing.assert_allclose(out["final_xy"][offs[p]:offs[p + 1]], ref[:, :2], rtol=0, atol=1e-6)
+    b.close()
+    ti.close()
