@@ -179,9 +179,15 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
     // 32e..32e+31 of the PREVIOUS pass's trim order (identity on the first pass): neighbours in that order have
     // similar residuals, hence similar search radii and candidate counts, so the lanes of a warp finish together
     // and the rare wide searches (ring >= 2) fall into the same rounds. ----
+    // Queries whose 3x3 block does not settle the search (wide search radius, or the block is not inside the
+    // shared-memory window) are NOT finished inline - a handful of lanes would drag the whole warp through the
+    // ring loop in almost every round.  They are appended (ballot-compacted) to a per-warp list that reuses the
+    // already-consumed slots of `sord`, and finished afterwards with all lanes busy.
+    int n_def = 0;
 #pragma unroll 1
     for (int e = 0; e < E; ++e) {
         const int p = e * 32 + lane;
+        int defer = -1;  // >= 0: (point index | 0x8000 if it must run on the global grid)
         if (p < n) {
             const int i = sord[p];
             double qx, qy;
@@ -190,13 +196,46 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
             // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
             const int pc_prev = have_prev ? snn[i] : -1;
             double best = kInf;
-            int pos = -1, code;
+            int pos = -1, cx, cy;
             bool ok = false;
-            if (win_ok) ok = nn_search_stream<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos);
+            if (win_ok) ok = nn_search_block3<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy);
             if (ok) {
-                code = pos;
+                sd2[i] = best;
+                snn[i] = pos;
+                if (!nn_block_settles(G.g, qx, qy, cx, cy, 1, best)) defer = i;
             } else {
-                const int gprev = (pc_prev == -1) ? -1 : (pc_prev >= 0 ? W.global_pos(pc_prev) : (pc_prev & 0x7FFFFFFF));
+                if (!have_prev) snn[i] = -1;  // keep the previous pass's code as the seed of the deferred query
+                defer = i | 0x8000;
+            }
+        }
+        const unsigned m = __ballot_sync(kFull, defer >= 0);
+        if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
+        n_def += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < n_def; base += 32) {
+        if (base + lane < n_def) {
+            const int d = sord[base + lane];
+            const int i = d & 0x7FFF;
+            double qx, qy;
+            pose_apply(P, pc.s_u[i], qx, qy);
+            const double qz = Z3 ? pc.s_z[i] : 0.0;
+            double best = kInf;
+            int pos = -1;
+            bool ok = false;
+            if (!(d & 0x8000)) {
+                best = sd2[i];
+                pos = snn[i];
+                const int cx = clamp_cell((qx - G.g.x0) * G.g.inv_h, G.g.gw);
+                const int cy = clamp_cell((qy - G.g.y0) * G.g.inv_h, G.g.gh);
+                ok = nn_ring_loop_impl<Z3>(W, G.g, qx, qy, qz, cx, cy, 2, best, pos);
+            }
+            int code = pos;
+            if (!ok) {
+                // window miss: whole query on the global grid, seeded with the best candidate known so far
+                const int seed = snn[i];
+                const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed) : (seed & 0x7FFFFFFF));
                 pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
                 code = (int)((unsigned)pos | 0x80000000u);
                 ++n_global;

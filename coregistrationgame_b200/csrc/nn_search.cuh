@@ -274,10 +274,10 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
 //   4. if the border of the block is not provably farther than the best distance, the ring loop goes on
 //      from radius 2 (rare).
 template <bool Z3, class Acc>
-FICP_HD bool nn_search_stream(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
-                              double& best, int& bestpos) {
-    const int cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
-    const int cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
+                              double& best, int& bestpos, int& cx, int& cy) {
+    cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+    cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
     const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
     const int yl = (cy > 0) ? cy - 1 : 0, yh = (cy < g.gh - 1) ? cy + 1 : g.gh - 1;
     if (!acc.covers(xl, xh, yl, yh)) return false;
@@ -333,6 +333,28 @@ FICP_HD bool nn_search_stream(const Acc& acc, const GridGeom& g, double qx, doub
         nn_fold(acc, j0, da, best, bestpos);
         nn_fold(acc, j1, db, best, bestpos);
     }
+    return true;
+}
+
+// True when the visited block of Chebyshev radius `rad` around (cx, cy) provably bounds the search (cheap form of
+// the bound: side distances only; it never exceeds nn_block_bound2, so stopping on it is safe).
+FICP_HD bool nn_block_settles(const GridGeom& g, double qx, double qy, int cx, int cy, int rad, double best) {
+    const int xl = cx - rad, xh = cx + rad, yl = cy - rad, yh = cy + rad;
+    double b = kInf;
+    if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
+    if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
+    if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
+    if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
+    if (b == kInf) return true;
+    b -= g.eps;
+    return b > 0.0 && best < b * b;
+}
+
+template <bool Z3, class Acc>
+FICP_HD bool nn_search_stream(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
+                              double& best, int& bestpos) {
+    int cx, cy;
+    if (!nn_search_block3<Z3>(acc, g, qx, qy, qz, prev, best, bestpos, cx, cy)) return false;
     return nn_ring_loop<Z3>(acc, g, qx, qy, qz, cx, cy, 2, best, bestpos);
 }
 
