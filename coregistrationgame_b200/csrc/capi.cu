@@ -192,6 +192,37 @@ int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_
     return kOk;
 }
 
+// ------------------------------------------------------------------------------------------ match & remove
+int ficp_match_remove(const ficp_target* th, const double* trees_host, const int64_t* offsets, int64_t n_plots,
+                      int32_t ld, int32_t use_z, const double* thr_host, int64_t* matched_out, void* stream) {
+    if (n_plots <= 0) return kOk;
+    if (!th || !trees_host || !offsets || !thr_host || !matched_out) { set_error("ficp_match_remove: null pointer"); return kErrInvalid; }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    if (ld < 2 || (use_z && (ld < 3 || !t->has_z))) { set_error("ficp_match_remove: Z requested but not available on both sides"); return kErrInvalid; }
+    if (n_plots > 100000000) { set_error("ficp_match_remove: too many plots"); return kErrTooLarge; }
+    const long long rows = offsets[n_plots];
+    for (int64_t p = 0; p < n_plots; ++p)
+        if (offsets[p + 1] < offsets[p]) { set_error("ficp_match_remove: offsets must be non-decreasing"); return kErrInvalid; }
+    if (rows <= 0) return kOk;
+    if (t->m <= 0) { for (long long i = 0; i < rows; ++i) matched_out[i] = -1; return kOk; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<double> dt, dthr;
+    DevBuf<long long> doff, dout;
+    DevBuf<int> dscr;
+    int rc;
+    if ((rc = dt.alloc((size_t)rows * ld)) || (rc = dthr.alloc(rows)) || (rc = doff.alloc(n_plots + 1)) || (rc = dout.alloc(rows)) ||
+        (rc = dscr.alloc(rows)))
+        return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    FICP_CUDA(cudaMemcpyAsync(dt.p, trees_host, sizeof(double) * (size_t)rows * ld, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(dthr.p, thr_host, sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(doff.p, offsets, sizeof(int64_t) * (size_t)(n_plots + 1), cudaMemcpyHostToDevice, s));
+    if ((rc = launch_match_remove(t->view, use_z != 0, dt.p, doff.p, (int)n_plots, ld, dthr.p, dout.p, dscr.p, s))) return rc;
+    FICP_CUDA(cudaMemcpyAsync(matched_out, dout.p, sizeof(int64_t) * (size_t)rows, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
+    return kOk;
+}
+
 // ------------------------------------------------------------------------------------------ trimming
 int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* corr_host, int32_t ld_c,
                          const double* dist_host, int64_t n, int32_t md, const double* weights_host, int64_t fixed_k,

@@ -31,6 +31,36 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     if (d2out) d2out[i] = best;
 }
 
+// Greedy match-and-remove (replaces CHMPlot.remove_matches, chm_plot.py:223-285): the plot's
+// trees are visited IN ORDER; each takes its nearest remaining CHM point and removes it when the distance is below
+// the tree's threshold.  The order dependence makes it sequential per plot: one thread per plot, plots in parallel.
+template <bool Z3>
+__global__ void match_remove_kernel(GridView v, const double* __restrict__ trees, const long long* __restrict__ offsets,
+                                    int n_plots, int ld, const double* __restrict__ thr, long long* __restrict__ out,
+                                    int* __restrict__ scratch) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_plots) return;
+    const long long lo = offsets[p], hi = offsets[p + 1];
+    MaskedGlobalAcc acc;
+    acc.xy = v.xy; acc.z = v.z; acc.org = v.orig; acc.cell_start = v.cell_start; acc.gw = v.g.gw;
+    acc.removed = scratch + lo;
+    acc.n_removed = 0;
+    int* rem = scratch + lo;
+    for (long long t = lo; t < hi; ++t) {
+        out[t] = -1;
+        if ((long long)acc.n_removed >= v.m) continue;  // nothing left (the reference breaks out of its loop)
+        const double qx = trees[t * ld], qy = trees[t * ld + 1];
+        const double qz = Z3 ? trees[t * ld + 2] : 0.0;
+        double best;
+        int pos;
+        nn_search_stream<Z3>(acc, v.g, qx, qy, qz, -1, best, pos);
+        if (pos >= 0 && sqrt(best) < thr[t]) {
+            rem[acc.n_removed++] = pos;
+            out[t] = __ldg(v.orig + pos);
+        }
+    }
+}
+
 // Measurement aid: read-only sweep over a buffer that fits in L2, 16 B per thread per step.
 __global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int iters,
                                                       unsigned* __restrict__ sink) {
@@ -70,6 +100,19 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     cudaEventDestroy(b);
     dev_free(buf);
     dev_free(sink);
+    return kOk;
+}
+
+int launch_match_remove(const GridView& v, bool z3, const double* d_trees, const long long* d_offsets, int n_plots,
+                        int ld, const double* d_thr, long long* d_out, int* d_scratch, cudaStream_t stream) {
+    if (n_plots <= 0) return kOk;
+    const int t = 32;
+    const unsigned nb = (unsigned)((n_plots + t - 1) / t);
+    if (z3)
+        match_remove_kernel<true><<<nb, t, 0, stream>>>(v, d_trees, d_offsets, n_plots, ld, d_thr, d_out, d_scratch);
+    else
+        match_remove_kernel<false><<<nb, t, 0, stream>>>(v, d_trees, d_offsets, n_plots, ld, d_thr, d_out, d_scratch);
+    FICP_CUDA(cudaGetLastError());
     return kOk;
 }
 

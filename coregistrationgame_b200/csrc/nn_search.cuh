@@ -30,6 +30,7 @@ struct GlobalAcc {
     int gw;
 
     FICP_HD bool covers(int, int, int, int) const { return true; }
+    FICP_HD bool admit(int) const { return true; }
     FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
         const unsigned* row = cell_start + (size_t)y * gw;
         s = (int)FICP_LDG(row + xa);
@@ -43,6 +44,19 @@ struct GlobalAcc {
         if (Z3) zz = FICP_LDG(z + j);
     }
     FICP_HD int orig(int j) const { return FICP_LDG(org + j); }
+};
+
+// Global grid minus a (small) set of removed points: used by the greedy match-and-remove pass that follows a
+// confirmed registration (chm_plot.py:223-285).  `admit` is consulted only for candidates that would become the
+// best, so the linear scan over the removed list is cheap.
+struct MaskedGlobalAcc : GlobalAcc {
+    const int* removed;  // sorted positions already taken
+    int n_removed;
+    FICP_HD bool admit(int j) const {
+        for (int i = 0; i < n_removed; ++i)
+            if (removed[i] == j) return false;
+        return true;
+    }
 };
 
 // Window of cells [wx0,wx1) x [wy0,wy1) copied to shared memory.  cell[] packs
@@ -60,6 +74,7 @@ struct WindowAcc {
     FICP_HD bool covers(int xl, int xh, int yl, int yh) const {
         return xl >= wx0 && xh < wx1 && yl >= wy0 && yh < wy1;
     }
+    FICP_HD bool admit(int) const { return true; }
     FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
         const unsigned* row = cell + (y - wy0) * ww - wx0;
         const unsigned c0 = row[xa];
@@ -118,7 +133,7 @@ FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, dou
         const double dz = dsub(qz, tz);
         d2 = dadd(d2, dmul(dz, dz));
     }
-    if (d2 <= best) {  // rare after the first few candidates
+    if (d2 <= best && acc.admit(j)) {  // rare after the first few candidates
         if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
         best = d2;
     }
@@ -141,7 +156,7 @@ FICP_HD double nn_dist2(const Acc& acc, int j, double qx, double qy, double qz) 
 
 template <class Acc>
 FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpos) {
-    if (d2 <= best) {
+    if (d2 <= best && acc.admit(j)) {
         if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
         best = d2;
     }

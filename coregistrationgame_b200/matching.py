@@ -1,0 +1,89 @@
+"""Steps right after the Fractional ICP in the reference application.
+
+``remove_matches``   - ``CHMPlot.remove_matches`` (chm_plot.py:223-285): each tree of a confirmed plot, in order,
+                       takes its nearest remaining CHM tree and removes it when it is closer than
+                       ``min_dist_percent`` % of the tree's height.  CUDA: one exact grid search per tree with the
+                       already-removed points masked out (``ficp_match_remove``).
+``transform_record`` - ``Plot.get_transform`` + ``App.store_transformations`` (trees.py:248-280, app.py:884-924): the
+                       rigid transform original -> final coordinates as the CSV record
+                       ``{tx, ty, r00, r01, r10, r11, flip}``; the Procrustes fit runs in ``ficp_fit_rigid2d``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .batch import TargetIndex, _stream_ptr
+
+
+def _heights_ok(h):
+    h = np.asarray(h, dtype=np.float64)
+    return bool(np.isfinite(h).all())
+
+
+def match_thresholds(heights, min_dist_percent, use_3d):
+    """Per-tree distance threshold, the expression of chm_plot.py:262,281: ``(pct / 100.0) * height``; in the XY
+    fallback a missing height counts as 10 m (chm_plot.py:274-280)."""
+    h = np.asarray(heights, dtype=np.float64).copy()
+    if not use_3d:
+        h[~np.isfinite(h)] = 10.0
+    return np.array([(min_dist_percent / 100.0) * float(v) for v in h], dtype=np.float64)
+
+
+def remove_matches(plot_trees, chm, min_dist_percent=15, index=None, stream=None):
+    """Greedy match-and-remove for ONE plot.
+
+    plot_trees : (n, 3) rows ``[currentx, currenty, height]`` in plot order (height may be NaN).
+    chm        : (M, 3) rows ``[currentx, currenty, height]`` of the CHM layer in its current order.
+    Returns ``matched`` (n,) int64: the CHM row removed by each tree or -1; the removed rows in removal order are
+    ``matched[matched >= 0]`` (what the reference appends to ``removed_stems``)."""
+    out = remove_matches_batch([plot_trees], chm, min_dist_percent, index=index, stream=stream)
+    return out[0]
+
+
+def remove_matches_batch(plots, chm, min_dist_percent=15, index=None, stream=None):
+    """Same for many plots at once, each against the SAME (unmodified) CHM layer: plots do not see each other's
+    removals - use it for plots that cannot compete for the same CHM trees, or call ``remove_matches`` plot by plot
+    like the reference does."""
+    plots = [np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(-1, 3)) for p in plots]
+    chm = np.ascontiguousarray(np.asarray(chm, dtype=np.float64).reshape(-1, 3))
+    # 3-D only when every height on both sides is present (chm_plot.py:240-249)
+    use_3d = all(_heights_ok(p[:, 2]) for p in plots) and _heights_ok(chm[:, 2])
+    sizes = np.array([len(p) for p in plots], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    rows = int(offsets[-1])
+    matched = np.full(rows, -1, dtype=np.int64)
+    if rows and len(chm):
+        trees = np.ascontiguousarray(np.vstack(plots))
+        thr = np.concatenate([match_thresholds(p[:, 2], min_dist_percent, use_3d) for p in plots])
+        if not use_3d:
+            trees = np.ascontiguousarray(trees[:, :2])
+        own = index is None
+        if own:
+            index = TargetIndex(chm[:, :3] if use_3d else chm[:, :2], use_z=use_3d)
+        try:
+            _lib.check(_lib.load().ficp_match_remove(index.handle, _lib.ptr(trees), _lib.ptr(offsets), len(plots),
+                                                     trees.shape[1], int(use_3d), _lib.ptr(thr), _lib.ptr(matched),
+                                                     _stream_ptr(stream)), "ficp_match_remove")
+        finally:
+            if own:
+                index.close()
+    return [matched[offsets[i]:offsets[i + 1]] for i in range(len(plots))]
+
+
+def transform_record(original_xy, current_xy, flipped=False):
+    """Rigid transform original -> current as the reference's CSV record (app.py:901-912).  ``current ~ R @ original + t``;
+    a reflection is allowed only when the plot was flipped (trees.py:273-276)."""
+    a = np.ascontiguousarray(np.asarray(original_xy, dtype=np.float64)[:, :2])
+    b = np.ascontiguousarray(np.asarray(current_xy, dtype=np.float64)[:, :2])
+    if a.shape != b.shape or a.shape[0] == 0:
+        raise ValueError("No trees available to compute transform.")
+    t9 = np.empty(9, dtype=np.float64)
+    _lib.require_device()
+    _lib.check(_lib.load().ficp_fit_rigid2d(_lib.ptr(a), 2, _lib.ptr(b), 2, a.shape[0], int(bool(flipped)), _lib.ptr(t9)),
+               "ficp_fit_rigid2d")
+    T = t9.reshape(3, 3)
+    return {"tx": float(T[0, 2]), "ty": float(T[1, 2]), "r00": float(T[0, 0]), "r01": float(T[0, 1]),
+            "r10": float(T[1, 0]), "r11": float(T[1, 1]), "flip": bool(flipped)}

@@ -101,6 +101,13 @@ FICP_API int ficp_nn_query(const ficp_target* t, const double* q_host, int64_t n
 FICP_API int ficp_nn_query_device(const ficp_target* t, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
                          int32_t* idx_dev, double* dist_dev, void* stream);
 
+/* ---- greedy match-and-remove.  Replaces CHMPlot.remove_matches (chm_plot.py:223-285).
+ * For every plot (rows [offsets[p], offsets[p+1]) of trees_host) the trees are visited in order; a tree takes its
+ * nearest REMAINING target point (lowest index among ties) and removes it iff distance < thr[row].
+ * matched_out[row] = original target index removed by that tree, or -1.  Plots are independent of each other. */
+FICP_API int ficp_match_remove(const ficp_target* t, const double* trees_host, const int64_t* offsets, int64_t n_plots,
+                      int32_t ld, int32_t use_z, const double* thr_host, int64_t* matched_out, void* stream);
+
 /* ---- kernel 2: trimming.  Replaces find_optimal_fraction / get_n_first_elements (ficp.py:62-63,73-86).
  * weights[k-1] = 1/((k/n)**lambda) (computed by the caller with the reference's own expression).
  * fixed_k > 0 selects a fixed subset size instead of the FRMSD-optimal one.  src/corr may be NULL

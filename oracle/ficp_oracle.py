@@ -493,3 +493,32 @@ def synthetic_scene(m, n, seed=0, density=0.05, dims=3, pos_noise=0.3, z_noise=1
         dup = tgt[::dup_every].copy()
         tgt = np.vstack([tgt, dup])   # duplicates carry the HIGHER index
     return tgt[:, :dims].copy(), plots, poses
+
+
+# --------------------------------------------------------------------------- after the ICP
+def remove_matches_oracle(plot_trees, chm, min_dist_percent=15):
+    """CHMPlot.remove_matches (chm_plot.py:223-285) on arrays.  plot_trees (n,3) / chm (M,3): x, y, height.
+    Returns matched (n,) int64: index (into the ORIGINAL chm rows) removed by each tree, or -1."""
+    plot_trees = np.asarray(plot_trees, dtype=float).reshape(-1, 3)
+    chm = np.asarray(chm, dtype=float).reshape(-1, 3)
+    use_3d = bool(np.isfinite(plot_trees[:, 2]).all() and np.isfinite(chm[:, 2]).all())
+    md = 3 if use_3d else 2
+    alive = np.arange(len(chm))
+    matched = np.full(len(plot_trees), -1, dtype=np.int64)
+    for t, row in enumerate(plot_trees):
+        if len(alive) == 0:
+            break
+        d = np.sqrt(sqdist_canonical(row[None, :md], chm[alive, :md]))
+        j = int(np.argmin(d))                      # first minimum = lowest remaining index
+        h = row[2] if (use_3d or np.isfinite(row[2])) else 10.0
+        if d[j] < (min_dist_percent / 100.0) * float(h):
+            matched[t] = alive[j]
+            alive = np.delete(alive, j)
+    return matched
+
+
+def transform_record_oracle(original_xy, current_xy, flipped=False):
+    """Plot.get_transform (trees.py:248-280) + the record of App.store_transformations (app.py:901-912)."""
+    T = fit_rigid2d_svd(np.asarray(original_xy, dtype=float)[:, :2], np.asarray(current_xy, dtype=float)[:, :2], bool(flipped))
+    return {"tx": float(T[0, 2]), "ty": float(T[1, 2]), "r00": float(T[0, 0]), "r01": float(T[0, 1]),
+            "r10": float(T[1, 0]), "r11": float(T[1, 1]), "flip": bool(flipped)}

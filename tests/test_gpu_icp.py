@@ -15,7 +15,7 @@ from oracle import ficp_oracle as orc
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith("c1_"))
+               if not os.path.basename(p).startswith(("c1_", "next_")))
 NOISE_FLOOR = 1e-9
 
 

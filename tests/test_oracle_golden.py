@@ -10,7 +10,7 @@ from oracle import ficp_oracle as orc
 
 NOISE_FLOOR = 1e-9
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not os.path.basename(p).startswith("c1_"))
+               if not os.path.basename(p).startswith(("c1_", "next_")))
 
 
 def _run(g, **kw):
@@ -106,3 +106,25 @@ def test_empty_inputs_follow_reference_conventions():
     np.testing.assert_array_equal(out, s2)
     with pytest.raises(ValueError):
         orc.ficp_run(np.zeros(3), tgt)
+
+
+# ---- steps after the ICP: golden vectors from the reference's CHMPlot.remove_matches / Plot.get_transform
+NEXT_REMOVE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "next_remove_*.npz")))
+
+
+@pytest.mark.parametrize("case", NEXT_REMOVE)
+def test_remove_matches_oracle_matches_reference(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    matched = orc.remove_matches_oracle(g["plot"], g["chm"], float(g["pct"]))
+    np.testing.assert_array_equal(matched[matched >= 0], g["removed"])         # same CHM trees, same removal order
+    np.testing.assert_array_equal(np.setdiff1d(np.arange(len(g["chm"])), matched[matched >= 0]), np.sort(g["remaining"]))
+
+
+def test_transform_record_oracle_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "next_get_transform.npz"))
+    for i in range(int(g["n"])):
+        rec = orc.transform_record_oracle(g[f"orig_{i}"], g[f"cur_{i}"], bool(g[f"flipped_{i}"]))
+        R, t = g[f"R_{i}"], g[f"t_{i}"]
+        np.testing.assert_allclose([rec["r00"], rec["r01"], rec["r10"], rec["r11"]], R.ravel(), atol=1e-12)
+        np.testing.assert_allclose([rec["tx"], rec["ty"]], t, atol=1e-6)      # |t| ~ 6.5e6 (UTM), ulp ~ 1e-9
+        assert rec["flip"] == bool(g[f"flipped_{i}"]) and (np.linalg.det(R) < 0) == rec["flip"]
