@@ -55,6 +55,7 @@ SIGNATURES = {
     "ficp_nn_query": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ficp_nn_query_device": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ficp_match_remove": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "ficp_radial_crop": (c_i32, [c_vp, c_f64, c_f64, c_f64, c_vp, c_vp]),
     "ficp_select_fraction": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, P(c_i64), P(c_f64), c_vp]),
     "ficp_fit_rigid2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp]),
     "ficp_apply_xy": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),

@@ -223,6 +223,23 @@ int ficp_match_remove(const ficp_target* th, const double* trees_host, const int
     return kOk;
 }
 
+// ------------------------------------------------------------------------------------------ radial crop
+int ficp_radial_crop(const ficp_target* th, double cx, double cy, double dist, uint8_t* mask_out, void* stream) {
+    if (!th || !mask_out) { set_error("ficp_radial_crop: null pointer"); return kErrInvalid; }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    if (t->m <= 0) return kOk;
+    if (!std::isfinite(cx) || !std::isfinite(cy) || std::isnan(dist)) { set_error("ficp_radial_crop: non-finite centre or radius"); return kErrNonFinite; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<unsigned char> dm;
+    int rc;
+    if ((rc = dm.alloc((size_t)t->m))) return rc;
+    FICP_CUDA(cudaMemsetAsync(dm.p, 0, (size_t)t->m, s));
+    if ((rc = launch_radial_crop(t->view, cx, cy, dist, dm.p, s))) return rc;
+    FICP_CUDA(cudaMemcpyAsync(mask_out, dm.p, (size_t)t->m, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
+    return kOk;
+}
+
 // ------------------------------------------------------------------------------------------ trimming
 int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* corr_host, int32_t ld_c,
                          const double* dist_host, int64_t n, int32_t md, const double* weights_host, int64_t fixed_k,

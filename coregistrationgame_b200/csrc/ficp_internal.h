@@ -57,6 +57,7 @@ void target_free(Target* t);
 // ---- standalone stage kernels (host launchers; all pointers are DEVICE pointers) ----------------
 int launch_nn_query(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
                     double* d_d2, cudaStream_t stream);
+int launch_radial_crop(const GridView& v, double cx, double cy, double dist, unsigned char* d_mask, cudaStream_t stream);
 int launch_match_remove(const GridView& v, bool z3, const double* d_trees, const long long* d_offsets, int n_plots,
                         int ld, const double* d_thr, long long* d_out, int* d_scratch, cudaStream_t stream);
 int measure_l2_read_gbs(size_t bytes, int iters, double* gbs);

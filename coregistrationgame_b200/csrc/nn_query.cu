@@ -61,6 +61,21 @@ __global__ void match_remove_kernel(GridView v, const double* __restrict__ trees
     }
 }
 
+// Radial crop (replaces `cdist(coords, centre) <= dist`, chm_plot.py:144-148, :306-311): marks the
+// points within `dist` of (cx, cy).  Only the grid rows / cell runs the disc can touch are visited (one CTA per row,
+// the row's run of cells is one contiguous range), i.e. O(points near the disc), not O(M).
+__global__ void __launch_bounds__(128) radial_crop_kernel(GridView v, double cx, double cy, double dist, int row0, int col0,
+                                                          int col1, unsigned char* __restrict__ mask) {
+    const int y = row0 + blockIdx.x;
+    const unsigned* row = v.cell_start + (size_t)y * v.g.gw;
+    const unsigned s = row[col0], e = row[col1 + 1];
+    for (unsigned j = s + threadIdx.x; j < e; j += blockDim.x) {
+        const double2 p = __ldg(v.xy + j);
+        const double dx = dsub(p.x, cx), dy = dsub(p.y, cy);
+        if (sqrt(dadd(dmul(dx, dx), dmul(dy, dy))) <= dist) mask[__ldg(v.orig + j)] = 1;
+    }
+}
+
 // Measurement aid: read-only sweep over a buffer that fits in L2, 16 B per thread per step.
 __global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int iters,
                                                       unsigned* __restrict__ sink) {
@@ -100,6 +115,18 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     cudaEventDestroy(b);
     dev_free(buf);
     dev_free(sink);
+    return kOk;
+}
+
+int launch_radial_crop(const GridView& v, double cx, double cy, double dist, unsigned char* d_mask, cudaStream_t stream) {
+    if (v.m <= 0 || !(dist >= 0.0)) return kOk;
+    const GridGeom& g = v.g;
+    const double pad = dist + g.eps + g.h * 1e-6;
+    if (cx + pad < g.x0 || cy + pad < g.y0 || cx - pad > g.x0 + g.gw * g.h || cy - pad > g.y0 + g.gh * g.h) return kOk;
+    const int col0 = clamp_cell((cx - pad - g.x0) * g.inv_h, g.gw), col1 = clamp_cell((cx + pad - g.x0) * g.inv_h, g.gw);
+    const int row0 = clamp_cell((cy - pad - g.y0) * g.inv_h, g.gh), row1 = clamp_cell((cy + pad - g.y0) * g.inv_h, g.gh);
+    radial_crop_kernel<<<row1 - row0 + 1, 128, 0, stream>>>(v, cx, cy, dist, row0, col0, col1, d_mask);
+    FICP_CUDA(cudaGetLastError());
     return kOk;
 }
 

@@ -87,3 +87,36 @@ def transform_record(original_xy, current_xy, flipped=False):
     T = t9.reshape(3, 3)
     return {"tx": float(T[0, 2]), "ty": float(T[1, 2]), "r00": float(T[0, 0]), "r01": float(T[0, 1]),
             "r10": float(T[1, 0]), "r11": float(T[1, 1]), "flip": bool(flipped)}
+
+
+def radial_crop(index_or_points, x, y, dist, stream=None):
+    """Rows of the CHM layer within `dist` of (x, y) in XY, in their original order - the crop of
+    ``CHMPlot`` / ``SavedPlot`` (chm_plot.py:144-148, :306-311: ``cdist(coordinates, [[x, y]]) <= dist``).
+    Accepts a built ``TargetIndex`` (cell-range query, O(points near the disc)) or an (M, >=2) array."""
+    own = not isinstance(index_or_points, TargetIndex)
+    index = TargetIndex(np.asarray(index_or_points, dtype=np.float64)[:, :2], use_z=False) if own else index_or_points
+    try:
+        mask = np.zeros(index.m, dtype=np.uint8)
+        if index.m:
+            _lib.check(_lib.load().ficp_radial_crop(index.handle, float(x), float(y), float(dist), _lib.ptr(mask),
+                                                    _stream_ptr(stream)), "ficp_radial_crop")
+        return np.flatnonzero(mask)
+    finally:
+        if own:
+            index.close()
+
+
+def gui_hypothesis_table(rot_steps=range(-36, 36), trans_steps=(0,), flips=(0,), rot_step_deg=5.0, translate_step=0.5):
+    """Start poses reachable with the reference's keys: rotations in multiples of 5 degrees
+    (``App.rotate_plot``, app.py:618-624), translations in multiples of ``TRANSLATE_STEP`` = 0.5 m
+    (``App.shift_plot``, app.py:604-616), optional flip (``Plot.coordinate_flip``, trees.py:213-222).
+    Rows ``[m00 m01 m10 m11 dx dy]`` in the order translation (dy-major) x flip x rotation."""
+    from .batch import hypothesis_matrix
+    rows = []
+    for ty in trans_steps:
+        for tx in trans_steps:
+            for f in flips:
+                for r in rot_steps:
+                    m = hypothesis_matrix(rot_step_deg * r, f)
+                    rows.append([m[0, 0], m[0, 1], m[1, 0], m[1, 1], translate_step * tx, translate_step * ty])
+    return np.array(rows, dtype=np.float64).reshape(-1, 6)

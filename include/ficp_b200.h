@@ -108,6 +108,10 @@ FICP_API int ficp_nn_query_device(const ficp_target* t, const double* q_dev, int
 FICP_API int ficp_match_remove(const ficp_target* t, const double* trees_host, const int64_t* offsets, int64_t n_plots,
                       int32_t ld, int32_t use_z, const double* thr_host, int64_t* matched_out, void* stream);
 
+/* ---- radial crop.  Replaces `cdist(coordinates, centre) <= dist` (chm_plot.py:144-148, :306-311).
+ * mask_out[i] = 1 iff target row i lies within `dist` of (cx, cy) in XY (Euclidean distance, <=).  m bytes. */
+FICP_API int ficp_radial_crop(const ficp_target* t, double cx, double cy, double dist, uint8_t* mask_out, void* stream);
+
 /* ---- kernel 2: trimming.  Replaces find_optimal_fraction / get_n_first_elements (ficp.py:62-63,73-86).
  * weights[k-1] = 1/((k/n)**lambda) (computed by the caller with the reference's own expression).
  * fixed_k > 0 selects a fixed subset size instead of the FRMSD-optimal one.  src/corr may be NULL

@@ -80,3 +80,34 @@ def test_identity_record_for_unmoved_plot(gpu):
     rec = transform_record(xy, xy.copy())
     assert np.isclose(rec["tx"], 0.0) and np.isclose(rec["ty"], 0.0)
     assert np.isclose(rec["r00"], 1.0) and np.isclose(rec["r01"], 0.0) and np.isclose(rec["r10"], 0.0) and np.isclose(rec["r11"], 1.0)
+
+
+def test_radial_crop_matches_cdist_semantics(gpu):
+    """chm_plot.py:144-148: keep rows with Euclidean XY distance <= dist, original order."""
+    from coregistrationgame_b200 import TargetIndex
+    from coregistrationgame_b200.matching import radial_crop
+    rng = np.random.default_rng(4)
+    pts = np.column_stack([rng.uniform(420000, 420400, 200000), rng.uniform(6483000, 6483400, 200000)])
+    pts[:50] = pts[50:100]                                    # duplicates
+    pts[100] = [420200.0 + 70.0, 6483200.0]                   # exactly on the circle (3-4-5 style exactness)
+    ti = TargetIndex(pts, use_z=False)
+    for (x, y, d) in ((420200.0, 6483200.0, 70.0), (420000.0, 6483000.0, 35.5), (419000.0, 6483200.0, 10.0),
+                      (420200.0, 6483200.0, 0.0), (420200.0, 6483200.0, 1e6)):
+        got = radial_crop(ti, x, y, d)
+        dx, dy = pts[:, 0] - x, pts[:, 1] - y
+        want = np.flatnonzero(np.sqrt(dx * dx + dy * dy) <= d)
+        np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(radial_crop(pts[:1000], 420200.0, 6483200.0, 150.0),
+                                  np.flatnonzero(np.hypot(pts[:1000, 0] - 420200.0, pts[:1000, 1] - 6483200.0) <= 150.0))
+    ti.close()
+
+
+def test_gui_hypotheses_follow_plot_key_semantics(gpu):
+    """A start pose from the GUI-step table equals pressing the reference's keys: rotate in 5-degree steps about the
+    plot centroid, flip about it, shift in 0.5 m steps (trees.py:165-222 restated by oracle.pre_transform)."""
+    from coregistrationgame_b200.matching import gui_hypothesis_table
+    tab = gui_hypothesis_table(rot_steps=(-2, 0, 3), trans_steps=(-1, 0, 2), flips=(0, 1))
+    assert tab.shape == (3 * 3 * 3 * 2, 6)
+    np.testing.assert_array_equal(np.unique(tab[:, 4]), [-0.5, 0.0, 1.0])
+    row = tab[np.flatnonzero((tab[:, 4] == 1.0) & (tab[:, 5] == -0.5))[5]]     # flip=1, rotation +15 deg
+    np.testing.assert_allclose(row[:4], orc.hypothesis_matrix(15.0, 1).ravel(), atol=0)
