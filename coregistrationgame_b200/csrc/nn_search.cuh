@@ -121,6 +121,22 @@ FICP_COLD_TIE int nn_tie_winner(const Acc& acc, int j, int bestpos) {
     return (acc.orig(j) < acc.orig(bestpos)) ? j : bestpos;
 }
 
+// Fold one scored candidate into the running best.  The common events are "worse" and "better": both are handled
+// without a branch (predicated moves), because in a lock-step warp SOME lane improves in almost every iteration
+// and a divergent branch would be paid by all 32.  Only an exact tie with a DIFFERENT point (rare; re-meeting the
+// seed has j == bestpos) takes a branch, to apply the lowest-original-index rule.
+template <class Acc>
+FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpos) {
+    const bool lt = d2 < best;
+    if (d2 == best && j != bestpos) {
+        if (acc.admit(j)) bestpos = nn_tie_winner(acc, j, bestpos);
+    }
+    if (lt && acc.admit(j)) {
+        best = d2;
+        bestpos = j;
+    }
+}
+
 // ---- one candidate ---------------------------------------------------------------------------------
 template <bool Z3, class Acc>
 FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, double& best, int& bestpos) {
@@ -133,10 +149,7 @@ FICP_HD void nn_eval(const Acc& acc, int j, double qx, double qy, double qz, dou
         const double dz = dsub(qz, tz);
         d2 = dadd(d2, dmul(dz, dz));
     }
-    if (d2 <= best && acc.admit(j)) {  // rare after the first few candidates
-        if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
-        best = d2;
-    }
+    nn_fold(acc, j, d2, best, bestpos);
 }
 
 // squared distance only (used by the two-at-a-time stream loop)
@@ -152,14 +165,6 @@ FICP_HD double nn_dist2(const Acc& acc, int j, double qx, double qy, double qz) 
         d2 = dadd(d2, dmul(dz, dz));
     }
     return d2;
-}
-
-template <class Acc>
-FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpos) {
-    if (d2 <= best && acc.admit(j)) {
-        if (d2 < best) bestpos = j; else bestpos = nn_tie_winner(acc, j, bestpos);
-        best = d2;
-    }
 }
 
 template <bool Z3, class Acc>
