@@ -15,6 +15,15 @@
 #define FICP_HD inline
 #endif
 
+// Bounds / invariant checks of the kernels: compiled in only with -DFICP_DEBUG (compute-sanitizer is not
+// available on the target pool, so the debug build is how out-of-range indices are hunted).
+#if defined(FICP_DEBUG) && defined(__CUDA_ARCH__)
+#include <cassert>
+#define FICP_ASSERT(c) assert(c)
+#else
+#define FICP_ASSERT(c) ((void)0)
+#endif
+
 namespace ficp {
 
 #if defined(__CUDA_ARCH__)

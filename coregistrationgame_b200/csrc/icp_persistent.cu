@@ -190,6 +190,7 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
         int defer = -1;  // >= 0: (point index | 0x8000 if it must run on the global grid)
         if (p < n) {
             const int i = sord[p];
+            FICP_ASSERT(i >= 0 && i < n);
             double qx, qy;
             pose_apply(P, pc.s_u[i], qx, qy);
             const double qz = Z3 ? pc.s_z[i] : 0.0;
@@ -209,6 +210,7 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
             }
         }
         const unsigned m = __ballot_sync(kFull, defer >= 0);
+        FICP_ASSERT(n_def + __popc(m) <= e * 32 + 32);
         if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
         n_def += __popc(m);
     }
@@ -218,6 +220,7 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
         if (base + lane < n_def) {
             const int d = sord[base + lane];
             const int i = d & 0x7FFF;
+            FICP_ASSERT(i < n);
             double qx, qy;
             pose_apply(P, pc.s_u[i], qx, qy);
             const double qz = Z3 ? pc.s_z[i] : 0.0;
@@ -385,6 +388,7 @@ __device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& 
     for (int r = 1; r < E; ++r)
         if (r == rsel) { ksel = key[r]; ssel = s[r]; }
     out.thr_idx = (int)(__shfl_sync(kFull, ksel, lstar) & C::kIdxMask);
+    FICP_ASSERT(out.thr_idx < n && kstar >= 1 && kstar <= n);
     out.thr = sd2[out.thr_idx];
     if (pc.fixed_k > 0) {
         const double sk = __shfl_sync(kFull, ssel, lstar);
@@ -415,6 +419,7 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
                 double qx, qy;
                 pose_apply(P, pc.s_u[i], qx, qy);
                 const int code = snn[i];
+                FICP_ASSERT(code != -1 && ((code < 0) ? ((code & 0x7FFFFFFF) < G.m) : (code < W.rowoff[W.wh])));
                 const double2 t = (code < 0) ? __ldg(G.xy + (code & 0x7FFFFFFF)) : W.xy[code];
                 const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
                 su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
@@ -545,6 +550,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
                     const int r = c / ww, col = c - r * ww;
                     const size_t g = (size_t)(pm.wy0 + r) * G.g.gw + pm.wx0 + col;
                     const unsigned a = G.cell_start[g], b = G.cell_start[g + 1];
+                    FICP_ASSERT(b - a < 65536u && rowoff[r] + (int)(a - (unsigned)rowg[r]) < 65536);
                     w_cell[c] = (unsigned)(rowoff[r] + (int)(a - (unsigned)rowg[r])) | ((b - a) << 16);
                 }
                 for (int r = warp; r < wh; r += nwarps) {

@@ -32,6 +32,7 @@ struct GlobalAcc {
     FICP_HD bool covers(int, int, int, int) const { return true; }
     FICP_HD bool admit(int) const { return true; }
     FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
+        FICP_ASSERT(y >= 0 && xa >= 0 && xb < gw && xa <= xb);
         const unsigned* row = cell_start + (size_t)y * gw;
         s = (int)FICP_LDG(row + xa);
         e = (int)FICP_LDG(row + xb + 1);
@@ -76,6 +77,7 @@ struct WindowAcc {
     }
     FICP_HD bool admit(int) const { return true; }
     FICP_HD void seg(int y, int xa, int xb, int& s, int& e) const {
+        FICP_ASSERT(y >= wy0 && y < wy1 && xa >= wx0 && xb < wx1 && xa <= xb);
         const unsigned* row = cell + (y - wy0) * ww - wx0;
         const unsigned c0 = row[xa];
         s = (int)(c0 & 0xFFFFu);
@@ -84,6 +86,7 @@ struct WindowAcc {
     }
     template <bool Z3>
     FICP_HD void load(int j, double& x, double& y, double& zz) const {
+        FICP_ASSERT(j >= 0 && j < rowoff[wh]);
         const double2 p = xy[j];
         x = p.x;
         y = p.y;
