@@ -47,15 +47,38 @@ struct GridGeom {
     int gw, gh;        // cells per row / number of rows
 };
 
-// Device view of a built target index (cell-sorted copy of the target + CSR cell table).
+// Device view of a built target index (cell-sorted copy of the target + CSR cell table).  Two layouts:
+//   XY  targets: xy[M] (16 B) + orig[M] (4 B)
+//   XYZ targets: rec[M] = {x, y, z, bits(original index)} - 32 B, 32 B aligned, i.e. exactly one L2 sector per
+//                candidate (the split 16 B + 8 B + 4 B arrays pulled 2-3 sectors each; profiles/r01_summary.md)
 struct GridView {
     GridGeom g;
-    const double2* xy;          // [M] cell-sorted XY
-    const double* z;            // [M] cell-sorted Z (nullptr when the target has no 3rd column)
-    const int* orig;            // [M] original row index of each sorted point
+    const double2* xy;          // XY layout only
+    const double4* rec;         // XYZ layout only (nullptr otherwise)
+    const int* orig;            // XY layout only
     const unsigned* cell_start; // [gw*gh + 1] exclusive prefix of per-cell counts
     long long m;
 };
+
+FICP_HD double index_to_bits(int i) {
+    long long v = i;
+    double d;
+#if defined(__CUDA_ARCH__)
+    d = __longlong_as_double(v);
+#else
+    __builtin_memcpy(&d, &v, sizeof d);
+#endif
+    return d;
+}
+FICP_HD int bits_to_index(double d) {
+#if defined(__CUDA_ARCH__)
+    return (int)__double_as_longlong(d);
+#else
+    long long v;
+    __builtin_memcpy(&v, &d, sizeof v);
+    return (int)v;
+#endif
+}
 
 FICP_HD int clamp_cell(double f, int n) {
     // f = (coord - origin) * inv_h ; robust to huge magnitudes (clamped before conversion)

@@ -41,9 +41,9 @@ struct Target {
     double bbox[4] = {0, 0, 0, 0};  // xmin xmax ymin ymax
     double pts_per_cell = 2.0;
     // owned device buffers
-    double2* d_xy = nullptr;
-    double* d_z = nullptr;
-    int* d_orig = nullptr;
+    double2* d_xy = nullptr;   // XY layout
+    double4* d_rec = nullptr;  // XYZ layout
+    int* d_orig = nullptr;     // XY layout
     unsigned* d_cell_start = nullptr;
     float build_ms = 0.f;  // device time of the build kernels (CUDA events)
 };

@@ -7,7 +7,7 @@
 //   bbox      read xyz                     -> min/max + finiteness flag
 //   bin_count read xy, write cell id       -> per-cell histogram (L2 atomics)
 //   scan      exclusive prefix of the histogram -> cell_start (CSR)
-//   scatter   read xyz + cell id           -> cell-sorted double2 xy / z / original index
+//   scatter   read xyz + cell id           -> cell-sorted records (XY: double2 + index; XYZ: one 32 B record)
 //   cell_sort orders each cell by original index, so the layout is deterministic (stable sort)
 #include <cmath>
 #include <cstdio>
@@ -182,38 +182,51 @@ __global__ void __launch_bounds__(kT) scatter_kernel(const double* __restrict__ 
                                                      const unsigned* __restrict__ cellid,
                                                      const unsigned* __restrict__ cell_start,
                                                      unsigned* __restrict__ fill, double2* __restrict__ xy,
-                                                     double* __restrict__ z, int* __restrict__ orig) {
+                                                     double4* __restrict__ rec, int* __restrict__ orig) {
     const long long i = blockIdx.x * (long long)kT + threadIdx.x;
     if (i >= m) return;
     const unsigned c = cellid[i];
     const unsigned p = cell_start[c] + atomicAdd(fill + c, 1u);
-    xy[p] = make_double2(pts[i * ld], pts[i * ld + 1]);
-    if (use_z) z[p] = pts[i * ld + 2];
-    orig[p] = (int)i;
+    if (use_z) {
+        rec[p] = make_double4(pts[i * ld], pts[i * ld + 1], pts[i * ld + 2], index_to_bits((int)i));
+    } else {
+        xy[p] = make_double2(pts[i * ld], pts[i * ld + 1]);
+        orig[p] = (int)i;
+    }
 }
 
-// Orders every cell by original index (insertion sort; cells hold ~2 points).  Makes the
+// Orders every cell by original index (insertion sort; cells hold ~2-3 points).  Makes the
 // cell-sorted layout independent of atomic ordering, i.e. a stable counting sort.
 __global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsigned* __restrict__ cell_start,
-                                                       double2* __restrict__ xy, double* __restrict__ z,
+                                                       double2* __restrict__ xy, double4* __restrict__ rec,
                                                        int* __restrict__ orig, int use_z) {
     const long long c = blockIdx.x * (long long)kT + threadIdx.x;
     if (c >= nc) return;
     const unsigned s = cell_start[c], e = cell_start[c + 1];
-    for (unsigned a = s + 1; a < e; ++a) {
-        const int key = orig[a];
-        const double2 kxy = xy[a];
-        const double kz = use_z ? z[a] : 0.0;
-        unsigned b = a;
-        while (b > s && orig[b - 1] > key) {
-            orig[b] = orig[b - 1];
-            xy[b] = xy[b - 1];
-            if (use_z) z[b] = z[b - 1];
-            --b;
+    if (use_z) {
+        for (unsigned a = s + 1; a < e; ++a) {
+            const double4 kr = rec[a];
+            const int key = bits_to_index(kr.w);
+            unsigned b = a;
+            while (b > s && bits_to_index(rec[b - 1].w) > key) {
+                rec[b] = rec[b - 1];
+                --b;
+            }
+            rec[b] = kr;
         }
-        orig[b] = key;
-        xy[b] = kxy;
-        if (use_z) z[b] = kz;
+    } else {
+        for (unsigned a = s + 1; a < e; ++a) {
+            const int key = orig[a];
+            const double2 kxy = xy[a];
+            unsigned b = a;
+            while (b > s && orig[b - 1] > key) {
+                orig[b] = orig[b - 1];
+                xy[b] = xy[b - 1];
+                --b;
+            }
+            orig[b] = key;
+            xy[b] = kxy;
+        }
     }
 }
 
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsig
 void target_free(Target* t) {
     if (!t) return;
     dev_free(t->d_xy);
-    dev_free(t->d_z);
+    dev_free(t->d_rec);
     dev_free(t->d_orig);
     dev_free(t->d_cell_start);
     delete t;
@@ -323,9 +336,12 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.fill), sizeof(unsigned) * (size_t)nc));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc + 1)));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m));
-    if (use_z) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_z), sizeof(double) * (size_t)m));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m));
+    if (use_z) {
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_rec), sizeof(double4) * (size_t)m));
+    } else {
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m));
+    }
     const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.bsum), sizeof(unsigned) * (size_t)nb_scan));
     FICP_CUDA(cudaEventRecord(ev0, stream));   // device time of the build = bbox kernels + everything from here
@@ -336,10 +352,10 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     scan_block_sums_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum);
     scan_partials_kernel<<<1, kT, 0, stream>>>(g.bsum, nb_scan);
     scan_apply_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum, t->d_cell_start);
-    scatter_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, use_z, g.cellid, t->d_cell_start, g.fill, t->d_xy, t->d_z,
+    scatter_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, use_z, g.cellid, t->d_cell_start, g.fill, t->d_xy, t->d_rec,
                                               t->d_orig);
     const unsigned nb_cells = (unsigned)((nc + kT - 1) / kT);
-    cell_sort_kernel<<<nb_cells, kT, 0, stream>>>(nc, t->d_cell_start, t->d_xy, t->d_z, t->d_orig, use_z);
+    cell_sort_kernel<<<nb_cells, kT, 0, stream>>>(nc, t->d_cell_start, t->d_xy, t->d_rec, t->d_orig, use_z);
     FICP_CUDA(cudaGetLastError());
     FICP_CUDA(cudaEventRecord(ev1, stream));
     FICP_CUDA(cudaStreamSynchronize(stream));
@@ -350,7 +366,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
 
     t->view.g = gg;
     t->view.xy = t->d_xy;
-    t->view.z = t->d_z;
+    t->view.rec = t->d_rec;
     t->view.orig = t->d_orig;
     t->view.cell_start = t->d_cell_start;
     t->view.m = m;

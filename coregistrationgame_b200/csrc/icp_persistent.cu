@@ -157,7 +157,7 @@ __device__ __forceinline__ void pose_apply(const Pose& P, const double2 u, doubl
 #endif
 template <bool Z3>
 FICP_GLOBAL_ATTR int nn_query_global(const GridView& G, double qx, double qy, double qz, int prev, double* best_out) {
-    const GlobalAcc ga{G.xy, G.z, G.orig, G.cell_start, G.g.gw};
+    const GlobalAcc ga = make_global_acc(G);
     double best;
     int pos;
     nn_search_stream<Z3>(ga, G.g, qx, qy, qz, prev, best, pos);
@@ -420,7 +420,7 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
                 pose_apply(P, pc.s_u[i], qx, qy);
                 const int code = snn[i];
                 FICP_ASSERT(code != -1 && ((code < 0) ? ((code & 0x7FFFFFFF) < G.m) : (code < W.rowoff[W.wh])));
-                const double2 t = (code < 0) ? __ldg(G.xy + (code & 0x7FFFFFFF)) : W.xy[code];
+                const double2 t = (code < 0) ? grid_xy(G, code & 0x7FFFFFFF) : W.xy[code];
                 const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
                 su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
                 h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
@@ -556,8 +556,8 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
                 for (int r = warp; r < wh; r += nwarps) {
                     const int cnt = rowoff[r + 1] - rowoff[r], gs = rowg[r], lo = rowoff[r];
                     for (int j = lane; j < cnt; j += 32) {
-                        w_xy[lo + j] = G.xy[gs + j];
-                        if (Z3) w_z[lo + j] = G.z[gs + j];
+                        w_xy[lo + j] = grid_xy(G, gs + j);
+                        if (Z3) w_z[lo + j] = grid_z(G, gs + j);
                     }
                 }
             }
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             __syncthreads();
         }
         const bool win_ok = (sh_win_ok != 0);
-        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G.orig,
+        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G.orig, G.rec,
                           pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0};
         const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
         const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NPAD;  // [stage][0]=g [stage][1]=c

@@ -22,11 +22,11 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     if (i >= n) return;
     const double qx = q[i * ld], qy = q[i * ld + 1];
     const double qz = Z3 ? q[i * ld + 2] : 0.0;
-    const GlobalAcc acc{v.xy, v.z, v.orig, v.cell_start, v.g.gw};
+    const GlobalAcc acc = make_global_acc(v);
     double best;
     int pos;
     nn_search_stream<Z3>(acc, v.g, qx, qy, qz, -1, best, pos);
-    idx[i] = __ldg(v.orig + pos);
+    idx[i] = grid_orig(v, pos);
     if (dist) dist[i] = sqrt(best);
     if (d2out) d2out[i] = best;
 }
@@ -42,7 +42,7 @@ __global__ void match_remove_kernel(GridView v, const double* __restrict__ trees
     if (p >= n_plots) return;
     const long long lo = offsets[p], hi = offsets[p + 1];
     MaskedGlobalAcc acc;
-    acc.xy = v.xy; acc.z = v.z; acc.org = v.orig; acc.cell_start = v.cell_start; acc.gw = v.g.gw;
+    acc.xy = v.xy; acc.rec = v.rec; acc.org = v.orig; acc.cell_start = v.cell_start; acc.gw = v.g.gw;
     acc.removed = scratch + lo;
     acc.n_removed = 0;
     int* rem = scratch + lo;
@@ -56,7 +56,7 @@ __global__ void match_remove_kernel(GridView v, const double* __restrict__ trees
         nn_search_stream<Z3>(acc, v.g, qx, qy, qz, -1, best, pos);
         if (pos >= 0 && sqrt(best) < thr[t]) {
             rem[acc.n_removed++] = pos;
-            out[t] = __ldg(v.orig + pos);
+            out[t] = grid_orig(v, pos);
         }
     }
 }
@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(128) radial_crop_kernel(GridView v, double cx,
     const unsigned* row = v.cell_start + (size_t)y * v.g.gw;
     const unsigned s = row[col0], e = row[col1 + 1];
     for (unsigned j = s + threadIdx.x; j < e; j += blockDim.x) {
-        const double2 p = __ldg(v.xy + j);
+        const double2 p = grid_xy(v, j);
         const double dx = dsub(p.x, cx), dy = dsub(p.y, cy);
-        if (sqrt(dadd(dmul(dx, dx), dmul(dy, dy))) <= dist) mask[__ldg(v.orig + j)] = 1;
+        if (sqrt(dadd(dmul(dx, dx), dmul(dy, dy))) <= dist) mask[grid_orig(v, j)] = 1;
     }
 }
 

@@ -22,9 +22,30 @@ namespace ficp {
 #define FICP_LDG(p) (*(p))
 #endif
 
+// One 32 B record = one L2 sector = ONE load request: sm_100 has 256-bit global loads (SASS LDG.E.ENL2.256).
+FICP_HD void grid_load_rec(const double4* rec, int j, double& x, double& y, double& z, double& w) {
+#if defined(__CUDA_ARCH__)
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(rec + j));
+#else
+    const double4 r = rec[j];
+    x = r.x; y = r.y; z = r.z; w = r.w;
+#endif
+}
+FICP_HD double2 grid_xy(const GridView& v, long long j) {
+    if (v.rec) return FICP_LDG(reinterpret_cast<const double2*>(v.rec + j));
+    return FICP_LDG(v.xy + j);
+}
+FICP_HD double grid_z(const GridView& v, long long j) {   // XYZ layout only
+    return FICP_LDG(reinterpret_cast<const double2*>(v.rec + j) + 1).x;
+}
+FICP_HD int grid_orig(const GridView& v, long long j) {
+    if (v.rec) return bits_to_index(FICP_LDG(reinterpret_cast<const double2*>(v.rec + j) + 1).y);
+    return FICP_LDG(v.orig + j);
+}
+
 struct GlobalAcc {
     const double2* xy;
-    const double* z;
+    const double4* rec;
     const int* org;
     const unsigned* cell_start;
     int gw;
@@ -39,13 +60,25 @@ struct GlobalAcc {
     }
     template <bool Z3>
     FICP_HD void load(int j, double& x, double& y, double& zz) const {
-        const double2 p = FICP_LDG(xy + j);
-        x = p.x;
-        y = p.y;
-        if (Z3) zz = FICP_LDG(z + j);
+        if (Z3) {
+            double w;
+            grid_load_rec(rec, j, x, y, zz, w);
+        } else if (rec) {  // XY query against an XYZ-built index
+            const double2 p = FICP_LDG(reinterpret_cast<const double2*>(rec + j));
+            x = p.x;
+            y = p.y;
+        } else {
+            const double2 p = FICP_LDG(xy + j);
+            x = p.x;
+            y = p.y;
+        }
     }
-    FICP_HD int orig(int j) const { return FICP_LDG(org + j); }
+    FICP_HD int orig(int j) const {
+        if (rec) return bits_to_index(FICP_LDG(reinterpret_cast<const double2*>(rec + j) + 1).y);
+        return FICP_LDG(org + j);
+    }
 };
+FICP_HD GlobalAcc make_global_acc(const GridView& v) { return GlobalAcc{v.xy, v.rec, v.orig, v.cell_start, v.g.gw}; }
 
 // Global grid minus a (small) set of removed points: used by the greedy match-and-remove pass that follows a
 // confirmed registration (chm_plot.py:223-285).  `admit` is consulted only for candidates that would become the
@@ -69,7 +102,8 @@ struct WindowAcc {
     const unsigned* cell;  // shared
     const int* rowoff;     // shared: first local position of each window row (+ total at [wh])
     const int* rowdelta;   // shared: global sorted position = local position + rowdelta[row]
-    const int* gorg;       // global: original indices of the sorted target
+    const int* gorg;       // global: original indices of the sorted target (XY layout)
+    const double4* grec;   // global: packed records (XYZ layout) or nullptr
     int wx0, wy0, wx1, wy1, ww, wh;
 
     FICP_HD bool covers(int xl, int xh, int yl, int yh) const {
@@ -100,7 +134,11 @@ struct WindowAcc {
         }
         return j + rowdelta[lo];
     }
-    FICP_HD int orig(int j) const { return FICP_LDG(gorg + global_pos(j)); }
+    FICP_HD int orig(int j) const {
+        const int gp = global_pos(j);
+        if (grec) return bits_to_index(FICP_LDG(reinterpret_cast<const double2*>(grec + gp) + 1).y);
+        return FICP_LDG(gorg + gp);
+    }
 };
 
 // Rare paths can be kept out of line (smaller hot loop) or inlined (no call ABI inside divergent code);

@@ -62,7 +62,10 @@ template <bool Z3>
 static int check(const HostGrid& G, const std::vector<double>& px, const std::vector<double>& py,
                  const std::vector<double>& pz, const std::vector<double>& qx, const std::vector<double>& qy,
                  const std::vector<double>& qz, int wx0, int wy0, int wx1, int wy1, long* n_window_hits) {
-    GlobalAcc ga{G.xy.data(), G.z.data(), G.org.data(), G.cs.data(), G.g.gw};
+    // XYZ instantiation reads the packed 32 B records, XY the split arrays (exactly like the device layouts)
+    std::vector<double4> rec(G.xy.size());
+    for (size_t i = 0; i < rec.size(); ++i) rec[i] = make_double4(G.xy[i].x, G.xy[i].y, G.z[i], index_to_bits(G.org[i]));
+    GlobalAcc ga{Z3 ? nullptr : G.xy.data(), Z3 ? rec.data() : nullptr, Z3 ? nullptr : G.org.data(), G.cs.data(), G.g.gw};
     // window staging exactly like the kernel does it
     const int ww = wx1 - wx0, wh = wy1 - wy0;
     std::vector<double2> wxy; std::vector<double> wz; std::vector<unsigned> wc(std::max(ww * wh, 1));
@@ -77,7 +80,8 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
             wc[r * ww + c] = (unsigned)(rowoff[r] + (int)(a - gs)) | ((b - a) << 16);
         }
     }
-    WindowAcc wa{wxy.data(), wz.data(), wc.data(), rowoff.data(), rowdelta.data(), G.org.data(), wx0, wy0, wx1, wy1, ww, wh};
+    WindowAcc wa{wxy.data(), wz.data(), wc.data(), rowoff.data(), rowdelta.data(), Z3 ? nullptr : G.org.data(), Z3 ? rec.data() : nullptr,
+                 wx0, wy0, wx1, wy1, ww, wh};
     int bad = 0;
     for (size_t i = 0; i < qx.size(); ++i) {
         // brute force
