@@ -44,6 +44,26 @@ def shard_of(rank, world):
     return (int(rank), int(world))
 
 
+def plot_shard(n_plots, rank, world):
+    """Plots owned by a rank when the batch is sharded over plots (fewer hypotheses than ranks, e.g. one start pose
+    per plot): plot ids rank, rank + world, ..."""
+    return np.arange(int(rank), int(n_plots), int(world))
+
+
+def gather_plot_shards(local_detail, local_plots, n_plots, group=None):
+    """Assemble per-plot rows computed on different ranks: every rank contributes the rows of the plots it owns,
+    everything else is zero, one all-reduce(SUM) puts the table together on all ranks (no arg-min needed)."""
+    import torch
+    import torch.distributed as dist
+
+    full = torch.zeros((int(n_plots), local_detail.shape[1]), dtype=local_detail.dtype, device=local_detail.device)
+    if len(local_plots):
+        full[torch.as_tensor(np.asarray(local_plots), device=local_detail.device, dtype=torch.long)] = local_detail
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
 def local_best_detail(batch, out):
     """(n_plots, len(DETAIL_FIELDS)) float64 rows of this rank's best hypothesis per plot."""
     det = np.zeros((batch.n_plots, len(DETAIL_FIELDS)), dtype=np.float64)
@@ -64,38 +84,70 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    hyp_table = np.asarray(hyp_table, dtype=np.float64).reshape(-1, 6)
+    if isinstance(sources, np.ndarray) and sources.ndim == 2:
+        sources = [sources]
     own = index is None
     if own:
         index = TargetIndex(target)
     try:
-        batch = IcpBatch(index, sources, hyp_table, hyp_shard=shard_of(rank, world), **kw)
-        try:
-            stream = torch.cuda.current_stream()
-            batch.run(stream)
-            out = batch.results(stream)
-            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-            keys = torch.from_numpy(out["best_key"].astype(np.int64)).to(dev)
-            detail = torch.from_numpy(local_best_detail(batch, out)).to(dev)
-            passes = torch.tensor([out["stats"]["passes"]], dtype=torch.int64, device=dev)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        stream = torch.cuda.current_stream()
+        n_plots = len(sources)
+        if hyp_table.shape[0] >= world:
+            # ---- shard the hypotheses of every plot; winner = all-reduce(MIN) over packed keys
+            batch = IcpBatch(index, sources, hyp_table, hyp_shard=shard_of(rank, world), **kw)
+            try:
+                batch.run(stream)
+                out = batch.results(stream)
+                keys = torch.from_numpy(out["best_key"].astype(np.int64)).to(dev)
+                detail = torch.from_numpy(local_best_detail(batch, out)).to(dev)
+                centres = batch.centres
+                h2d, d2h, local_passes = batch.h2d_bytes, batch.d2h_bytes, out["stats"]["passes"]
+            finally:
+                batch.close()
             gkeys, gdetail = reduce_best(keys, detail, group)
-            if world > 1:
-                dist.all_reduce(passes, op=dist.ReduceOp.SUM, group=group)
             gk = gkeys.cpu().numpy().astype(np.uint64)
             gd = gdetail.cpu().numpy()
-            res = decode_best_keys(gk)
-            res["best_key"] = gk
-            rows = {f: gd[:, i] for i, f in enumerate(DETAIL_FIELDS)}
-            res["best_transform"] = np.stack([compose_world_transform({f: rows[f][p] for f in DETAIL_FIELDS},
-                                                                      batch.centres[p]) for p in range(batch.n_plots)])
-            res["k"] = rows["k"].astype(np.int64)
-            res["rmse"], res["frmsd"] = rows["rmse"], rows["frmsd"]
-            res["passes_local"] = out["stats"]["passes"]
-            res["passes_global"] = int(passes.item())
-            res["h2d_bytes"] = batch.h2d_bytes + (int(np.asarray(target).nbytes) if own else 0)
-            res["d2h_bytes"] = batch.d2h_bytes + int(gk.nbytes + gd.nbytes)
-            return res
-        finally:
-            batch.close()
+        else:
+            # ---- fewer hypotheses than ranks (e.g. one start pose per plot): shard the PLOTS, gather the rows
+            mine = plot_shard(n_plots, rank, world)
+            centres_all = kw.pop("centres", None)
+            if centres_all is None:
+                centres_all = np.array([np.asarray(s, dtype=np.float64)[:, :2].mean(axis=0) for s in sources])
+            centres = np.asarray(centres_all, dtype=np.float64).reshape(n_plots, 2)
+            ncol = len(DETAIL_FIELDS) + 2   # + the packed key as two exactly-representable halves
+            if len(mine):
+                batch = IcpBatch(index, [sources[p] for p in mine], hyp_table, centres=centres[mine], **kw)
+                try:
+                    batch.run(stream)
+                    out = batch.results(stream)
+                    k64 = out["best_key"].astype(np.uint64)
+                    local = np.concatenate([local_best_detail(batch, out), (k64 >> np.uint64(32)).astype(np.float64)[:, None],
+                                            (k64 & np.uint64(0xFFFFFFFF)).astype(np.float64)[:, None]], axis=1)
+                    h2d, d2h, local_passes = batch.h2d_bytes, batch.d2h_bytes, out["stats"]["passes"]
+                finally:
+                    batch.close()
+            else:
+                local, h2d, d2h, local_passes = np.zeros((0, ncol)), 0, 0, 0
+            full = gather_plot_shards(torch.from_numpy(local).to(dev), mine, n_plots, group).cpu().numpy()
+            gd = full[:, :len(DETAIL_FIELDS)]
+            gk = (full[:, -2].astype(np.uint64) << np.uint64(32)) | full[:, -1].astype(np.uint64)
+        passes = torch.tensor([local_passes], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(passes, op=dist.ReduceOp.SUM, group=group)
+        res = decode_best_keys(gk)
+        res["best_key"] = gk
+        rows = {f: gd[:, i] for i, f in enumerate(DETAIL_FIELDS)}
+        res["best_transform"] = np.stack([compose_world_transform({f: rows[f][p] for f in DETAIL_FIELDS}, centres[p])
+                                          for p in range(n_plots)])
+        res["k"] = rows["k"].astype(np.int64)
+        res["rmse"], res["frmsd"] = rows["rmse"], rows["frmsd"]
+        res["passes_local"] = local_passes
+        res["passes_global"] = int(passes.item())
+        res["h2d_bytes"] = h2d + (int(np.asarray(target).nbytes) if own else 0)
+        res["d2h_bytes"] = d2h + int(gk.nbytes + gd.nbytes)
+        return res
     finally:
         if own:
             index.close()

@@ -31,6 +31,17 @@ def main():
     np.testing.assert_array_equal(d["k"], s["best_row"]["k"])
     assert d["passes_global"] == s["stats"]["passes"], (d["passes_global"], s["stats"]["passes"])
     assert d["passes_local"] < s["stats"]["passes"]
+    # one start pose per plot (config 4 shape): sharded over PLOTS, rows gathered
+    tgt2, plots2, _ = orc.synthetic_scene(200000, 150, seed=9, dims=3, n_plots=21, hidden_pose=False)
+    rng = np.random.default_rng(5)
+    starts = [orc.pre_transform(p, np.r_[orc.hypothesis_matrix(rng.uniform(-5, 5), 0).ravel(), rng.uniform(-1, 1, 2)], p[:, :2].mean(0)) for p in plots2]
+    ident = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
+    d2 = register_batch_distributed(starts, tgt2, ident, min_k=0)
+    s2 = register_batch(starts, tgt2, ident, min_k=0)
+    np.testing.assert_array_equal(d2["best_key"], s2["best_key"])
+    np.testing.assert_array_equal(d2["best_transform"], s2["best_transform"])
+    np.testing.assert_array_equal(d2["k"], s2["best_row"]["k"])
+    assert d2["passes_global"] == s2["stats"]["passes"]
     dist.barrier()
     if rank == 0:
         print(f"dist_check ok: world={world} plots={len(plots)} hyps={hyp.shape[0]} winners={d['best_hyp'].tolist()} "

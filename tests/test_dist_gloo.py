@@ -68,9 +68,41 @@ def test_reduce_best_two_ranks_gloo():
     assert (outs[0][1].astype(np.uint64)[1] & np.uint64(0xFFFFFFFF)) == 0   # all disqualified -> id 0, score inf
 
 
+def _gather_worker(rank, world, port, n_plots, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coregistrationgame_b200.dist import gather_plot_shards, plot_shard
+    mine = plot_shard(n_plots, rank, world)
+    local = np.stack([np.array([p, 10.0 * p + 0.5, rank], dtype=np.float64) for p in mine]) if len(mine) else np.zeros((0, 3))
+    full = gather_plot_shards(torch.from_numpy(local), mine, n_plots)
+    q.put((rank, full.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_plot_sharding_gather_two_ranks_gloo():
+    world, n_plots = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, n_plots, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([np.array([p, 10.0 * p + 0.5, p % world]) for p in range(n_plots)])
+    for _, full in outs:
+        np.testing.assert_array_equal(full, want)          # every plot exactly once, from its owner
+
+
 def test_shards_partition_the_hypotheses():
-    from coregistrationgame_b200.dist import shard_of
+    from coregistrationgame_b200.dist import plot_shard, shard_of
     for world in (1, 2, 4, 8):
+        allp = np.concatenate([plot_shard(10001, r, world) for r in range(world)])
+        assert sorted(allp.tolist()) == list(range(10001))
         seen = np.concatenate([np.arange(*((b, 4096, s))) for b, s in (shard_of(r, world) for r in range(world))])
         assert sorted(seen.tolist()) == list(range(4096))
 
