@@ -55,17 +55,44 @@ def parse():
     ap.add_argument("--window-margin", type=float, default=-1.0)
     ap.add_argument("--pts-per-cell", type=float, default=0.0, help="0 = library default")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"],
+                    help="c3 (default, the metric's config) | c2: 200 trees vs 1e5 points, 1024 hypotheses | "
+                         "c4: 1250 plots/GPU x 150 trees vs 1e7 points, one start pose per plot")
     return ap.parse_args()
 
 
 def workload(args, n_plots):
     from oracle import ficp_oracle as orc      # scene generator only (synthetic data), not the timed path
+    if args.workload == "c4":
+        tgt, plots, _ = orc.synthetic_scene(args.points, args.trees, seed=4, dims=args.dims, n_plots=n_plots,
+                                            hidden_pose=False)
+        rng = np.random.default_rng(1)
+        plots = [orc.pre_transform(p, np.r_[orc.hypothesis_matrix(rng.uniform(-5.0, 5.0), 0).ravel(), rng.uniform(-1.5, 1.5, 2)],
+                                   p[:, :2].mean(axis=0)) for p in plots]
+        hyp = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
+        name = (f"C4 batched breakout: {n_plots} plots x {args.trees} trees vs a shared {args.points}-point CHM, one ICP per plot, "
+                f"{'XYZ' if args.dims == 3 else 'XY'} matching")
+        return tgt, plots, hyp, name
     tgt, plots, _ = orc.synthetic_scene(args.points, args.trees, seed=3, dims=args.dims, n_plots=n_plots,
                                         hidden_pose=True)
     hyp = orc.hypothesis_table(args.rotations, flips=(0, 1), translations=orc.translation_lattice(args.tside, 2.5))
-    name = (f"C3 synthetic stand: {args.trees} trees vs {args.points} CHM points, {hyp.shape[0]} hypotheses "
+    tag = "C3 synthetic stand" if args.workload == "c3" else "C2 synthetic plot"
+    name = (f"{tag}: {args.trees} trees vs {args.points} CHM points, {hyp.shape[0]} hypotheses "
             f"({args.rotations} rot x 2 flips x {args.tside}x{args.tside} translations), {'XYZ' if args.dims == 3 else 'XY'} matching")
     return tgt, plots, hyp, name
+
+
+def apply_workload_defaults(args):
+    """BASELINE.json configs other than the metric's own: only fills values the user left at the c3 defaults."""
+    if args.workload == "c2":
+        if args.points == 1_000_000: args.points = 100_000
+        if args.trees == 500: args.trees = 200
+        if args.rotations == 128: args.rotations = 512
+        if args.tside == 4: args.tside = 1
+    elif args.workload == "c4":
+        if args.points == 1_000_000: args.points = 10_000_000
+        if args.trees == 500: args.trees = 150
+        if args.plots_per_gpu == 16: args.plots_per_gpu = 1250
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
@@ -195,14 +222,21 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     n_plots = args.plots_per_gpu * world
     tgt, plots, hyp, name = workload(args, n_plots)
+    by_plots = hyp.shape[0] < world or args.workload == "c4"     # one pose per plot: shard the plots, not the poses
     props = _lib.device_props()
 
     # ---- resident inputs
     index = TargetIndex(tgt, pts_per_cell=(args.pts_per_cell or None))
     tinfo = index.info()
-    batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), warps_per_cta=args.warps,
-                     ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)
-    keys = torch.empty(n_plots, dtype=torch.int64, device=dev)
+    if by_plots:
+        mine = list(range(rank, n_plots, world))
+        batch = IcpBatch(index, [plots[p] for p in mine], hyp, min_k=0, warps_per_cta=args.warps,
+                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)
+    else:
+        batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), warps_per_cta=args.warps,
+                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)
+    keys = torch.empty(batch.n_plots, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(n_plots, dtype=torch.int64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
 
@@ -211,7 +245,12 @@ def run_b200(args):
         if evk is not None:
             evk.record(stream)
         batch.copy_best_keys_to(keys.data_ptr(), stream)
-        if world > 1:
+        if by_plots:
+            gathered.zero_()
+            gathered[rank::world] = keys
+            if world > 1:
+                dist.all_reduce(gathered, op=dist.ReduceOp.SUM)      # gather of the per-plot rows
+        elif world > 1:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN)
 
     for _ in range(max(args.warmup, 3)):
@@ -256,10 +295,14 @@ def run_b200(args):
     h_tgt, h_plots, h_hyp = pinned(tgt), [pinned(p) for p in plots], pinned(hyp)
     e2e_steps = args.e2e_steps or args.steps
 
+    ekw = dict(warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm)
+    if by_plots:
+        ekw["min_k"] = 0
+
     def e2e_step():
         if world > 1:
-            return register_batch_distributed(h_plots, h_tgt, h_hyp, warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm)
-        r = register_batch(h_plots, h_tgt, h_hyp, warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm)
+            return register_batch_distributed(h_plots, h_tgt, h_hyp, **ekw)
+        r = register_batch(h_plots, h_tgt, h_hyp, **ekw)
         r["passes_global"] = r["stats"]["passes"]
         return r
     if args.no_e2e:
@@ -361,8 +404,8 @@ def run_b200(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": name, "plots_per_gpu": args.plots_per_gpu, "plots": n_plots,
-                           "icps_per_gpu_per_step": args.plots_per_gpu * hyp.shape[0],
-                           "hyp_iterations_per_step": passes_all, "parallelism": f"hypotheses round-robin over {world} GPU(s)",
+                           "icps_per_gpu_per_step": (args.plots_per_gpu if by_plots else args.plots_per_gpu * hyp.shape[0]),
+                           "hyp_iterations_per_step": passes_all, "parallelism": (f"plots round-robin over {world} GPU(s)" if by_plots else f"hypotheses round-robin over {world} GPU(s)"),
                            "l2": "flushed between timed steps (256 MB write)", "launch": batch.info,
                            "device": props},
                 "nn_queries_per_s": value * args.trees,
@@ -383,6 +426,7 @@ def run_b200(args):
 
 def main():
     args = parse()
+    apply_workload_defaults(args)
     try:
         if args.impl == "reference":
             run_reference(args)

@@ -388,29 +388,12 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         dymin = std::min(dymin, hyp[h * 6 + 5]); dymax = std::max(dymax, hyp[h * 6 + 5]);
     }
 
-    // ---- launch shape: warps per CTA, shared-memory budget, window capacity
-    int dev = 0, sms = 0, smem_optin = 0;
-    FICP_CUDA(cudaGetDevice(&dev));
-    FICP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FICP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int warps = prm->warps_per_cta > 0 ? prm->warps_per_cta : std::min(icp_max_warps(e), 16);
-    warps = std::max(1, std::min(warps, std::min(icp_max_warps(e), n_hyp_local)));
-    int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));
-    const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
-    size_t budget = std::min<size_t>((size_t)smem_optin, sm_total / want_ctas_per_sm - 1024);
-    const int wcap_rows = 256;
-    const size_t fixed_bytes = icp_smem_bytes(e, z3, warps, 0, 0, wcap_rows);
-    const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
-    int wcap_pts = 0;
-    if (!prm->disable_window && budget > fixed_bytes + 4096) wcap_pts = (int)std::min<size_t>(65535, (budget - fixed_bytes - 256) / per_pt);
-
-    // ---- per-plot metadata: local coordinates u = p - centre, shift point, window rectangle
+    // ---- per-plot geometry: local coordinates u = p - centre, shift point, footprint of the start poses
     std::vector<PlotMeta> plots((size_t)n_plots);
     std::vector<double2> h_u((size_t)rows);
     std::vector<double> h_z(z3 ? (size_t)rows : 0);
-    const double mean_cell_pts = (double)t->m / ((double)g.gw * g.gh);
-    double margin0 = prm->window_margin >= 0.0 ? prm->window_margin : (3.0 * g.h + 5.0);
-    int need_pts = 0;
+    struct Foot { double rho, fx0, fx1, fy0, fy1; };
+    std::vector<Foot> foot((size_t)n_plots);
     for (int64_t p = 0; p < n_plots; ++p) {
         PlotMeta& pm = plots[(size_t)p];
         pm.off = plot_offsets[p];
@@ -419,6 +402,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         pm.cinx = centres[2 * p]; pm.ciny = centres[2 * p + 1];
         pm.fixed_k = fixed_k ? fixed_k[p] : 0;
         pm.pad = 0;
+        pm.wx0 = pm.wy0 = pm.wx1 = pm.wy1 = 0;
         double sx = 0, sy = 0;
         for (int i = 0; i < pm.n; ++i) {
             const double* r = src_host + (size_t)(pm.off + i) * ld;
@@ -432,42 +416,79 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
             sx += ux; sy += uy;
         }
         pm.ubx = sx / pm.n; pm.uby = sy / pm.n;
-        double rho = 0;
+        Foot& f = foot[(size_t)p];
+        f.rho = 0;
         for (int i = 0; i < pm.n; ++i) {
             const double2 u = h_u[(size_t)(pm.off + i)];
-            rho = std::max(rho, std::hypot(u.x - pm.ubx, u.y - pm.uby));
+            f.rho = std::max(f.rho, std::hypot(u.x - pm.ubx, u.y - pm.uby));
         }
         // footprint of the plot centroid over all start poses: centre_h = M_h ubar + cin + d_h
-        double fx0, fx1, fy0, fy1;
-        if (std::hypot(pm.ubx, pm.uby) <= 1e-9 * (rho + 1.0)) {
-            fx0 = pm.cinx + dxmin; fx1 = pm.cinx + dxmax; fy0 = pm.ciny + dymin; fy1 = pm.ciny + dymax;
+        if (std::hypot(pm.ubx, pm.uby) <= 1e-9 * (f.rho + 1.0)) {
+            f.fx0 = pm.cinx + dxmin; f.fx1 = pm.cinx + dxmax; f.fy0 = pm.ciny + dymin; f.fy1 = pm.ciny + dymax;
         } else {
-            fx0 = fy0 = HUGE_VAL; fx1 = fy1 = -HUGE_VAL;
+            f.fx0 = f.fy0 = HUGE_VAL; f.fx1 = f.fy1 = -HUGE_VAL;
             for (int64_t h = 0; h < n_hyp; ++h) {
                 const double* hr = hyp + h * 6;
                 const double cx = hr[0] * pm.ubx + hr[1] * pm.uby + pm.cinx + hr[4];
                 const double cy = hr[2] * pm.ubx + hr[3] * pm.uby + pm.ciny + hr[5];
-                fx0 = std::min(fx0, cx); fx1 = std::max(fx1, cx); fy0 = std::min(fy0, cy); fy1 = std::max(fy1, cy);
+                f.fx0 = std::min(f.fx0, cx); f.fx1 = std::max(f.fx1, cx); f.fy0 = std::min(f.fy0, cy); f.fy1 = std::max(f.fy1, cy);
             }
         }
-        pm.wx0 = pm.wy0 = pm.wx1 = pm.wy1 = 0;
-        if (wcap_pts > 0) {
-            double margin = margin0;
-            for (int attempt = 0; attempt < 12; ++attempt, margin *= 0.7) {
-                const double r = rho + margin;
-                const double bx0 = fx0 - r, bx1 = fx1 + r;
-                const double by0 = fy0 - r, by1 = fy1 + r;
-                if (bx1 < g.x0 || by1 < g.y0 || bx0 > g.x0 + g.gw * g.h || by0 > g.y0 + g.gh * g.h) break;  // off the map
-                const int x0 = clamp_cell((bx0 - g.x0) * g.inv_h, g.gw), x1 = clamp_cell((bx1 - g.x0) * g.inv_h, g.gw) + 1;
-                const int y0 = clamp_cell((by0 - g.y0) * g.inv_h, g.gh), y1 = clamp_cell((by1 - g.y0) * g.inv_h, g.gh) + 1;
-                const long long cells = (long long)(x1 - x0) * (y1 - y0);
-                const double est = cells * mean_cell_pts * 1.15 + 96;
-                if (cells <= wcap_pts && (y1 - y0) <= wcap_rows && est <= wcap_pts) {
-                    pm.wx0 = x0; pm.wx1 = x1; pm.wy0 = y0; pm.wy1 = y1;
-                    need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est));
-                    need_pts = std::max<long long>(need_pts, cells);
-                    break;
-                }
+    }
+    // window of grid cells a plot can reach with `margin` of slack: cell rectangle + estimated point count
+    const double mean_cell_pts = (double)t->m / ((double)g.gw * g.gh);
+    const double margin0 = prm->window_margin >= 0.0 ? prm->window_margin : (3.0 * g.h + 5.0);
+    auto window_of = [&](const Foot& f, double margin, int* rect, long long* cells, double* est) -> bool {
+        const double r = f.rho + margin;
+        const double bx0 = f.fx0 - r, bx1 = f.fx1 + r, by0 = f.fy0 - r, by1 = f.fy1 + r;
+        if (bx1 < g.x0 || by1 < g.y0 || bx0 > g.x0 + g.gw * g.h || by0 > g.y0 + g.gh * g.h) return false;  // off the map
+        rect[0] = clamp_cell((bx0 - g.x0) * g.inv_h, g.gw); rect[1] = clamp_cell((bx1 - g.x0) * g.inv_h, g.gw) + 1;
+        rect[2] = clamp_cell((by0 - g.y0) * g.inv_h, g.gh); rect[3] = clamp_cell((by1 - g.y0) * g.inv_h, g.gh) + 1;
+        *cells = (long long)(rect[1] - rect[0]) * (rect[3] - rect[2]);
+        *est = (double)*cells * mean_cell_pts * 1.15 + 96;
+        return true;
+    };
+
+    // ---- launch shape: warps per CTA, CTAs per SM, shared-memory budget, window capacity
+    int dev = 0, sms = 0, smem_optin = 0;
+    FICP_CUDA(cudaGetDevice(&dev));
+    FICP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FICP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int warps = prm->warps_per_cta > 0 ? prm->warps_per_cta : std::min(icp_max_warps(e), 16);
+    warps = std::max(1, std::min(warps, std::min(icp_max_warps(e), n_hyp_local)));
+    const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
+    const int wcap_rows = 256;
+    const size_t fixed_bytes = icp_smem_bytes(e, z3, warps, 0, 0, wcap_rows);
+    const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
+    auto cap_for = [&](int ctas) -> int {
+        const size_t budget = std::min<size_t>((size_t)smem_optin, sm_total / ctas - 1024);
+        if (prm->disable_window || budget <= fixed_bytes + 4096) return 0;
+        return (int)std::min<size_t>(65535, (budget - fixed_bytes - 256) / per_pt);
+    };
+    // points a window needs with a modest margin (one ring of cells + a few metres of drift), worst plot
+    double need_modest = 0;
+    for (int64_t p = 0; p < n_plots; ++p) {
+        int rect[4]; long long cells; double est;
+        if (window_of(foot[(size_t)p], std::min(margin0, 1.5 * g.h + 3.0), rect, &cells, &est)) need_modest = std::max(need_modest, std::max(est, (double)cells));
+    }
+    int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));
+    if (prm->ctas_per_sm <= 0)  // fewer resident CTAs when that is what it takes for the windows to fit on-chip
+        while (want_ctas_per_sm > 1 && cap_for(want_ctas_per_sm) < need_modest) --want_ctas_per_sm;
+    int wcap_pts = cap_for(want_ctas_per_sm);
+
+    // ---- window rectangles: the largest margin (up to margin0) that fits the capacity
+    int need_pts = 0;
+    for (int64_t p = 0; p < n_plots && wcap_pts > 0; ++p) {
+        PlotMeta& pm = plots[(size_t)p];
+        double margin = margin0;
+        for (int attempt = 0; attempt < 12; ++attempt, margin *= 0.7) {
+            int rect[4]; long long cells; double est;
+            if (!window_of(foot[(size_t)p], margin, rect, &cells, &est)) break;
+            if (cells <= wcap_pts && (rect[3] - rect[2]) <= wcap_rows && est <= wcap_pts) {
+                pm.wx0 = rect[0]; pm.wx1 = rect[1]; pm.wy0 = rect[2]; pm.wy1 = rect[3];
+                need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est));
+                need_pts = std::max<long long>(need_pts, cells);
+                break;
             }
         }
     }
