@@ -262,7 +262,10 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
         Target* t; bool armed = true;
         double* raw = nullptr; unsigned* cellid = nullptr; unsigned* counts = nullptr; unsigned* fill = nullptr;
         unsigned* bsum = nullptr; BBox* part = nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         ~Guard() {
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
             dev_free(cellid); dev_free(counts); dev_free(fill); dev_free(bsum); dev_free(part);
             dev_free(raw);
             if (armed) target_free(t);
@@ -282,9 +285,9 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
         FICP_CUDA(cudaMemcpyAsync(g.raw, pts, sizeof(double) * (size_t)m * ld, cudaMemcpyHostToDevice, stream));
         d_pts = g.raw;
     }
-    cudaEvent_t ev0, ev1;
-    FICP_CUDA(cudaEventCreate(&ev0));
-    FICP_CUDA(cudaEventCreate(&ev1));
+    FICP_CUDA(cudaEventCreate(&g.ev0));
+    FICP_CUDA(cudaEventCreate(&g.ev1));
+    cudaEvent_t ev0 = g.ev0, ev1 = g.ev1;
 
     // ---- bounding box + finiteness
     const int nb_bbox = (int)std::min<long long>((m + kT - 1) / kT, 148 * 8);
@@ -299,7 +302,6 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     float bbox_ms = 0.f;
     cudaEventElapsedTime(&bbox_ms, ev0, ev1);
     if (bb.nonfinite) {
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         set_error("target contains non-finite coordinates ('x' must be finite)");
         return kErrNonFinite;
     }
@@ -361,8 +363,6 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     FICP_CUDA(cudaStreamSynchronize(stream));
     cudaEventElapsedTime(&t->build_ms, ev0, ev1);
     t->build_ms += bbox_ms;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
 
     t->view.g = gg;
     t->view.xy = t->d_xy;

@@ -92,15 +92,17 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ 
 }  // namespace
 
 int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
-    uint4* buf = nullptr;
-    unsigned* sink = nullptr;
+    struct Res {
+        uint4* buf = nullptr; unsigned* sink = nullptr; cudaEvent_t a = nullptr, b = nullptr;
+        ~Res() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); dev_free(buf); dev_free(sink); }
+    } r;
     const size_t n_vec = bytes / sizeof(uint4);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&buf), n_vec * sizeof(uint4)));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&sink), sizeof(unsigned)));
-    FICP_CUDA(cudaMemset(buf, 1, n_vec * sizeof(uint4)));
-    cudaEvent_t a, b;
-    FICP_CUDA(cudaEventCreate(&a));
-    FICP_CUDA(cudaEventCreate(&b));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.buf), n_vec * sizeof(uint4)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.sink), sizeof(unsigned)));
+    FICP_CUDA(cudaMemset(r.buf, 1, n_vec * sizeof(uint4)));
+    FICP_CUDA(cudaEventCreate(&r.a));
+    FICP_CUDA(cudaEventCreate(&r.b));
+    uint4* buf = r.buf; unsigned* sink = r.sink; cudaEvent_t a = r.a, b = r.b;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     l2_read_kernel<<<sms * 8, 256>>>(buf, n_vec, 2, sink);  // warm the L2
@@ -111,10 +113,6 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
     *gbs = (double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    dev_free(buf);
-    dev_free(sink);
     return kOk;
 }
 
