@@ -76,10 +76,29 @@ class FicpError(RuntimeError):
     pass
 
 
+def _try_build():
+    """The shared library is a build artefact (git-ignored).  If it is missing but the CUDA toolchain is present,
+    compile it in-tree once (sm_100a, ~2 min) - this is the same `make` that `__graft_entry__.build()` runs."""
+    import shutil
+    import subprocess
+    import sys
+    nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+    if not nvcc or not shutil.which("make"):
+        return
+    print(f"[coregistrationgame_b200] {LIB_PATH} missing: building it with {nvcc} ...", file=sys.stderr)
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(min(8, os.cpu_count() or 1)), f"NVCC={nvcc}"],
+                              stdout=subprocess.DEVNULL)
+    except Exception as exc:  # the loader reports the missing library right after
+        print(f"[coregistrationgame_b200] build failed: {exc}", file=sys.stderr)
+
+
 def load():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and not os.environ.get("FICP_B200_LIB"):
+            _try_build()
         if not os.path.exists(LIB_PATH):
             raise FicpError(
                 f"{LIB_PATH} not found: the CUDA extension is not built. Run `python __graft_entry__.py` "

@@ -183,31 +183,32 @@ class FractionalICP:
         self.n_passes_ += int(row["passes"])
         return self.source
 
-    def _iterate_stepwise(self):
-        """One stage driven from the host over the stage kernels (plots larger than the persistent
-        kernel's 1024-tree limit).  Same loop as ficp.py:122-147."""
-        corr, d = self.find_correspondences(self.source, self.target)
+    def _pass_stepwise(self):
+        """One NN pass + trimming through the stage kernels: (correspondences, trimmed rows, k, FRMSD at k)."""
+        matched, dist = self.find_correspondences(self.source, self.target)
         self.n_passes_ += 1
-        frac, k = self.find_optimal_fraction(corr, d)
+        frac, k = self.find_optimal_fraction(matched, dist)
+        if k == 0:
+            return matched, None, 0, float("inf")
+        rows = self.get_n_first_elements(k, dist)
+        return matched, rows, k, self.frmsd(frac, k, self.source[rows], matched[rows])
+
+    def _iterate_stepwise(self):
+        """One stage driven from the host over the stage kernels, for plots above the persistent kernel's 1024-tree
+        limit: pass, then (fit, move, pass) until the FRMSD stops improving by more than `threshold` - the loop of
+        ficp.py:122-147, including its habit of keeping the pose of the last (possibly worse) pass."""
+        matched, rows, k, score = self._pass_stepwise()
         if k == 0:
             return self.source
-        sel = self.get_n_first_elements(k, d)
-        best = self.frmsd(frac, k, self.source[sel], corr[sel])
-        done = 0
-        while done < self.max_iterations:
-            T = self.compute_optimal_transform_2d(self.source[sel], corr[sel])
-            self.source = self.apply_transform_2d_xy_only(self.source, T)
-            self.transform_ = T @ self.transform_
-            corr, d = self.find_correspondences(self.source, self.target)
-            self.n_passes_ += 1
-            frac, k = self.find_optimal_fraction(corr, d)
-            sel = self.get_n_first_elements(k, d)
-            now = self.frmsd(frac, k, self.source[sel], corr[sel])
-            self.frmsd_, self.k_ = float(now), int(k)
-            if best - now <= self.threshold:
+        for _ in range(self.max_iterations):
+            step = self.compute_optimal_transform_2d(self.source[rows], matched[rows])
+            self.source = self.apply_transform_2d_xy_only(self.source, step)
+            self.transform_ = step @ self.transform_
+            matched, rows, k, new_score = self._pass_stepwise()
+            self.frmsd_, self.k_ = float(new_score), int(k)
+            if score - new_score <= self.threshold:
                 break
-            best = now
-            done += 1
+            score = new_score
         return self.source
 
     def _iterate(self):
