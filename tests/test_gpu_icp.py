@@ -386,3 +386,29 @@ def test_full_size_c4_properties(gpu):
         np.testing.assert_allclose(out["final_xy"][offs[p]:offs[p + 1]], ref[:, :2], rtol=0, atol=1e-6)
     b.close()
     ti.close()
+
+
+def test_xy_plots_against_xyz_built_index(gpu):
+    """ficp.py:40: matching falls back to XY when only one side has heights.  Here the CHM index is built WITH Z
+    (packed 32-byte records) and reused for 2-column plots: batch kernel, stand-alone query and match-remove must
+    all read X, Y out of the packed layout."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(40000, 90, seed=21, dims=3, n_plots=2, hidden_pose=True, dup_every=13)
+    hyp = orc.hypothesis_table(6, flips=(0, 1))
+    ti = TargetIndex(tgt)                       # has_z = True
+    assert ti.info()["has_z"]
+    plots_xy = [p[:, :2].copy() for p in plots]
+    b = IcpBatch(ti, plots_xy, hyp)
+    assert b.match_dims == 2
+    out = b.run().results()
+    for p, src in enumerate(plots_xy):
+        ref = orc.run_hypotheses(src, tgt[:, :2], hyp, centre=b.centres[p], closed_form=True)
+        np.testing.assert_array_equal(out["hyp"][p]["passes"], np.array(ref["passes"]))
+        np.testing.assert_array_equal(out["hyp"][p]["k"], np.array(ref["k"]))
+        assert out["best_key"][p] == ref["best_key"]
+    b.close()
+    idx, dist = ti.query(plots_xy[0])           # XY query against the XYZ-built index
+    ridx, rd2 = orc.nn_assign_bruteforce(plots_xy[0], tgt[:, :2], 2)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, np.sqrt(rd2))
+    ti.close()
