@@ -62,12 +62,13 @@ def parse():
 
 
 def workload(args, n_plots):
-    from oracle import ficp_oracle as orc      # scene generator only (synthetic data), not the timed path
+    from coregistrationgame_b200 import synthetic as orc   # input generator (the oracle is imported by the CPU legs only)
+    from coregistrationgame_b200.batch import hypothesis_matrix, hypothesis_table, translation_lattice
     if args.workload == "c4":
         tgt, plots, _ = orc.synthetic_scene(args.points, args.trees, seed=4, dims=args.dims, n_plots=n_plots,
                                             hidden_pose=False)
         rng = np.random.default_rng(1)
-        plots = [orc.pre_transform(p, np.r_[orc.hypothesis_matrix(rng.uniform(-5.0, 5.0), 0).ravel(), rng.uniform(-1.5, 1.5, 2)],
+        plots = [orc.apply_pose(p, np.r_[hypothesis_matrix(rng.uniform(-5.0, 5.0), 0).ravel(), rng.uniform(-1.5, 1.5, 2)],
                                    p[:, :2].mean(axis=0)) for p in plots]
         hyp = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
         name = (f"C4 batched breakout: {n_plots} plots x {args.trees} trees vs a shared {args.points}-point CHM, one ICP per plot, "
@@ -75,7 +76,7 @@ def workload(args, n_plots):
         return tgt, plots, hyp, name
     tgt, plots, _ = orc.synthetic_scene(args.points, args.trees, seed=3, dims=args.dims, n_plots=n_plots,
                                         hidden_pose=True)
-    hyp = orc.hypothesis_table(args.rotations, flips=(0, 1), translations=orc.translation_lattice(args.tside, 2.5))
+    hyp = hypothesis_table(args.rotations, flips=(0, 1), translations=translation_lattice(args.tside, 2.5))
     tag = "C3 synthetic stand" if args.workload == "c3" else "C2 synthetic plot"
     name = (f"{tag}: {args.trees} trees vs {args.points} CHM points, {hyp.shape[0]} hypotheses "
             f"({args.rotations} rot x 2 flips x {args.tside}x{args.tside} translations), {'XYZ' if args.dims == 3 else 'XY'} matching")
