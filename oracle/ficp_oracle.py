@@ -246,9 +246,15 @@ class IterRecord:
     inliers: np.ndarray   # sorted source indices of the trimmed subset
 
 
+class TimeBudgetExceeded(Exception):
+    """Raised between passes when a RunTrace carries a wall-clock deadline (bounded CPU baseline samples)."""
+
+
 @dataclass
 class RunTrace:
     records: list = field(default_factory=list)   # one per NN pass (= hypothesis-iteration)
+    deadline: float = None                        # time.perf_counter() value after which no new pass starts
+    light: bool = False                           # keep only counters, not the per-pass arrays
     transform: np.ndarray = field(default_factory=lambda: np.eye(3))  # composed T_total
     stage_passes: list = field(default_factory=list)
 
@@ -258,6 +264,10 @@ class RunTrace:
 
 
 def _pass(src, tgt, md, lam, nn, tree, fixed_k, trace, pairwise):
+    if trace is not None and trace.deadline is not None:
+        import time
+        if time.perf_counter() > trace.deadline:
+            raise TimeBudgetExceeded()
     if nn == "tree":
         idx, d2 = nn_assign_tree(src, tgt, md, tree)
     elif nn == "brute":
@@ -279,7 +289,7 @@ def _pass(src, tgt, md, lam, nn, tree, fixed_k, trace, pairwise):
         k, value, order = select_fraction_cumsum(d2, lam)
     inl = order[:k]
     if trace is not None:
-        trace.records.append(IterRecord(idx.copy(), d2.copy(), k, value, np.sort(inl)))
+        trace.records.append(None if trace.light else IterRecord(idx.copy(), d2.copy(), k, value, np.sort(inl)))
     return idx, inl, k, value
 
 
