@@ -412,3 +412,15 @@ def test_xy_plots_against_xyz_built_index(gpu):
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_array_equal(dist, np.sqrt(rd2))
     ti.close()
+
+
+def test_randomised_parity_soak(gpu):
+    """A short run of tools/fuzz_parity.py (random sizes, modes, duplicates, off-map poses, tiny targets): every
+    hypothesis whose parity is pinned must agree with the oracle.  The long soak (tens of thousands of hypotheses)
+    is run by hand: `python tools/fuzz_parity.py 600 <seed>`."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "15", "11"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "0 mismatching cases" in out.stdout

@@ -1,0 +1,137 @@
+"""Randomised parity soak: random scenes / plot sizes / modes through the batched CUDA kernel vs the CPU oracle.
+
+    python tools/fuzz_parity.py [seconds] [seed]
+
+Every case checks, per hypothesis: identical pass counts and trimmed sizes (above the rounding-noise floor), FRMSD to
+1e-6 relative, final positions to 1e-6 m, and the winner key.  Prints a one-line summary; exits 1 on any mismatch."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from coregistrationgame_b200 import IcpBatch, TargetIndex  # noqa: E402
+from coregistrationgame_b200.batch import compose_world_transform  # noqa: E402
+from oracle import ficp_oracle as orc  # noqa: E402  (the checker)
+
+NOISE_FLOOR = 1e-9
+
+
+def one_case(rng):
+    dims = int(rng.choice([2, 3]))
+    m = int(rng.choice([1, 3, 40, 400, 3000, 20000]))
+    n = int(rng.choice([1, 2, 5, 31, 33, 90, 200, 300]))
+    side = float(rng.choice([5.0, 60.0, 400.0]))
+    off = rng.choice([0.0, 4.2e5]) * np.array([1.0, 15.4])
+    tgt = np.column_stack([rng.uniform(0, side, m), rng.uniform(0, side * rng.choice([1.0, 0.05]), m), rng.uniform(5, 35, m)])
+    if m > 20 and rng.random() < 0.4:
+        tgt[m // 2:] = tgt[: m - m // 2]                      # exact duplicates (higher index = copy)
+    if m > 50 and rng.random() < 0.3:
+        g = np.arange(5.0)
+        gx, gy = np.meshgrid(g, g)
+        tgt[:25, 0], tgt[:25, 1], tgt[:25, 2] = side / 2 + gx.ravel(), gy.ravel(), 20.0   # lattice: equidistant ties
+    pick = rng.integers(0, m, n)
+    src = tgt[pick] + np.column_stack([rng.normal(0, 0.4, (n, 2)), rng.normal(0, 1.0, n)]) * rng.choice([0.0, 1.0, 1.0])
+    if rng.random() < 0.3:
+        k = max(1, n // 3)
+        src[:k, :2] = rng.uniform(0, side, (k, 2))           # outlier trees
+    tgt[:, :2] += off
+    src[:, :2] += off
+    tgt, src = tgt[:, :dims].copy(), src[:, :dims].copy()
+    nh = int(rng.choice([1, 3, 6]))
+    hyp = np.array([np.r_[orc.hypothesis_matrix(rng.uniform(-180, 180), int(rng.random() < 0.3)).ravel(),
+                          rng.normal(0, 2.0, 2) * rng.choice([1.0, 1.0, 500.0])] for _ in range(nh)])
+    kw = {}
+    if rng.random() < 0.25:
+        kw["allow_reflection"] = True
+    if rng.random() < 0.25:
+        kw["fixed_frac"] = float(rng.choice([0.5, 0.7, 0.95]))
+    if rng.random() < 0.2:
+        kw["max_iterations"] = int(rng.choice([0, 1, 4]))
+    if rng.random() < 0.2:
+        kw["lambda_val"] = float(rng.choice([0.5, 1.0, 6.0]))
+    launch = {}
+    if rng.random() < 0.2:
+        launch["disable_window"] = True
+    if rng.random() < 0.2:
+        launch["warps_per_cta"] = int(rng.choice([1, 2, 8]))
+    return src, tgt, hyp, kw, launch
+
+
+def check(src, tgt, hyp, kw, launch):
+    ti = TargetIndex(tgt)
+    b = IcpBatch(ti, [src], hyp, min_k=1, **kw, **launch)
+    out = b.run().results()
+    rows = out["hyp"][0]
+    ref = orc.run_hypotheses(src, tgt, hyp, centre=b.centres[0], min_k=1, closed_form=True, trace_all=True, **kw)
+    # rounding-noise floor: residuals of a few ulps of the coordinates (1 ulp of a UTM northing is 9e-10 m) make the
+    # trimmed size a coin flip for any two implementations - compare such hypotheses by the final pose only
+    floor = max(NOISE_FLOOR, 1e-13 * float(np.abs(tgt[:, :2]).max()) * len(src))
+    real = np.array([not any(r.value < floor for r in t.records) for t in ref["traces"]])
+    # Parity is unpinned where the reference's own answer is rounding noise: every inlier
+    # matched to ONE target point (H = 0 +- ulp), or - with reflections allowed - to <= 2 / collinear target points
+    # (rank-deficient H, det(H) = 0 +- ulp decides rotation vs reflection).
+    for h, t in enumerate(ref["traces"]):
+        for r in t.records:
+            # residuals equal to the last ulp across the trim boundary (e.g. the two mirror-image residuals of a
+            # 2-point fit): which tree is the k-th is decided by rounding - parity is defined modulo such ties
+            ds = np.sort(r.d2)
+            if 0 < r.k < len(ds) and abs(ds[r.k] - ds[r.k - 1]) <= 1e-11 * max(ds[r.k], 1e-300):
+                real[h] = False
+            uniq = np.unique(r.idx[r.inliers])
+            if r.k > 1 and len(uniq) < 2:
+                real[h] = False
+            if kw.get("allow_reflection") and r.k > 1:
+                pts = tgt[uniq, :2] - tgt[uniq, :2].mean(axis=0)
+                sv = np.linalg.svd(pts, compute_uv=False) if len(uniq) > 1 else np.zeros(2)
+                if len(uniq) <= 2 or sv[-1] <= 1e-6 * max(sv[0], 1e-300):
+                    real[h] = False
+    msgs = []
+    if not np.array_equal(rows["passes"][real], np.array(ref["passes"])[real]):
+        msgs.append(f"passes {rows['passes'].tolist()} vs {ref['passes']}")
+    if not np.array_equal(rows["k"][real], np.array(ref["k"])[real]):
+        msgs.append(f"k {rows['k'].tolist()} vs {ref['k']}")
+    for h in np.flatnonzero(real):
+        A = compose_world_transform(rows[h], b.centres[0])
+        got = src[:, :2] @ A[:, :2].T + A[:, 2]
+        err = np.abs(got - ref["aligned"][h][:, :2]).max()
+        if err > 1e-6:
+            msgs.append(f"hyp {h}: positions differ by {err:.3g}")
+        if np.isfinite(ref["score"][h]) and abs(rows["frmsd"][h] - ref["score"][h]) > 1e-6 * max(1.0, ref["score"][h]):
+            msgs.append(f"hyp {h}: frmsd {rows['frmsd'][h]} vs {ref['score'][h]}")
+    if real.all() and out["best_key"][0] != ref["best_key"]:
+        # two hypotheses that converged to the same pose can swap places at the fp32 rounding of the score
+        hg, hr = int(out["best_hyp"][0]), ref["best_hyp"]
+        sg, sr = ref["score"][hg], ref["score"][hr]
+        if not (np.isfinite(sg) and abs(sg - sr) <= 1e-6 * max(abs(sr), 1e-300)):
+            msgs.append(f"best key differs: hyp {hg} (score {sg}) vs {hr} (score {sr})")
+    b.close()
+    ti.close()
+    return msgs, int(real.sum()), len(real)
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = np.random.default_rng(seed)
+    t0, cases, hyps, compared, bad = time.time(), 0, 0, 0, 0
+    while time.time() - t0 < budget:
+        src, tgt, hyp, kw, launch = one_case(rng)
+        msgs, nreal, nh = check(src, tgt, hyp, kw, launch)
+        cases += 1
+        hyps += nh
+        compared += nreal
+        if msgs:
+            bad += 1
+            print(f"MISMATCH case {cases}: n={len(src)} m={len(tgt)} dims={src.shape[1]} kw={kw} launch={launch}: " + "; ".join(msgs[:4]))
+            if bad >= 5:
+                break
+    print(f"fuzz_parity: {cases} cases, {hyps} hypotheses ({compared} above the noise floor compared in full), {bad} mismatching cases, "
+          f"{time.time() - t0:.0f} s, seed {seed}")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
