@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--trees", type=int, default=500)
     ap.add_argument("--dims", type=int, default=3, choices=[2, 3])
     ap.add_argument("--plots-per-gpu", type=int, default=16)
+    ap.add_argument("--team", type=int, default=0, help="warps per ICP at launch (0 = planner's choice)")
+    ap.add_argument("--helpers", choices=["auto", "on", "off"], default="auto",
+                    help="elastic kernel (idle warps help the ICPs in flight): planner's choice, forced on, forced off")
+    ap.add_argument("--no-single-stand", action="store_true", help="skip the one-stand strong-scaling leg")
     ap.add_argument("--rotations", type=int, default=128)
     ap.add_argument("--tside", type=int, default=4, help="translation lattice side (tside^2 translations)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the CPU baseline sample (0 = one per core, <= 32)")
@@ -238,10 +242,10 @@ def run_b200(args):
     if by_plots:
         mine = list(range(rank, n_plots, world))
         batch = IcpBatch(index, [plots[p] for p in mine], hyp, min_k=0, warps_per_cta=args.warps,
-                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)
+                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin, team_warps=args.team, helpers={'auto': None, 'on': True, 'off': False}[args.helpers])
     else:
         batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), warps_per_cta=args.warps,
-                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin)
+                         ctas_per_sm=args.ctas_per_sm, window_margin=args.window_margin, team_warps=args.team, helpers={'auto': None, 'on': True, 'off': False}[args.helpers])
     keys = torch.empty(batch.n_plots, dtype=torch.int64, device=dev)
     gathered = torch.zeros(n_plots, dtype=torch.int64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -331,6 +335,43 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = e2e_passes / float(e2e_s.item()) if e2e_steps else None
     h2d, d2h = r["h2d_bytes"], r["d2h_bytes"]
+
+    # ---- the named config taken literally: ONE stand x all its hypotheses, strong-scaled over the ranks
+    # (time to register a single stand; the headline above is the throughput of a batch of stands)
+    single = None
+    if not by_plots and not args.no_single_stand:
+        sb = IcpBatch(index, [plots[0]], hyp, hyp_shard=shard_of(rank, world), team_warps=args.team, helpers={'auto': None, 'on': True, 'off': False}[args.helpers])
+        skey = torch.empty(1, dtype=torch.int64, device=dev)
+
+        def sstep():
+            sb.run(stream)
+            sb.copy_best_keys_to(skey.data_ptr(), stream)
+            if world > 1:
+                dist.all_reduce(skey, op=dist.ReduceOp.MIN)
+        for _ in range(3):
+            sstep()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sev = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sstep()
+            b.record(stream)
+            sev.append((a, b))
+        torch.cuda.synchronize()
+        sms_ = torch.tensor([sum(a.elapsed_time(b) for a, b in sev) / args.steps], dtype=torch.float64, device=dev)
+        sp_ = torch.tensor([float(sb.results(stream, per_hypothesis=False)["stats"]["passes"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sms_, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sp_, op=dist.ReduceOp.SUM)
+        single = {"workload": "one stand x %d hypotheses (plot 0), hypotheses sharded over %d GPU(s)" % (hyp.shape[0], world),
+                  "scaling": "strong", "ms": float(sms_.item()), "hyp_iterations": float(sp_.item()),
+                  "hyp_iter_per_s": float(sp_.item()) / (float(sms_.item()) * 1e-3), "team_warps": sb.info["team_warps"],
+                  "warps_per_cta": sb.info["warps_per_cta"], "ctas": sb.info["ctas"]}
+        sb.close()
 
     # ---- standalone kernels (reported, not the headline): bulk NN query and grid build
     extra = {}
@@ -428,6 +469,8 @@ def run_b200(args):
                 "path_stats": stats}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if single:
+            line["single_stand"] = single
         line.update(extra)
         print(json.dumps(line))
     batch.close()

@@ -455,10 +455,30 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     FICP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FICP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int warps = prm->warps_per_cta > 0 ? prm->warps_per_cta : std::min(icp_max_warps(e), 16);
-    warps = std::max(1, std::min(warps, std::min(icp_max_warps(e), n_hyp_local)));
+    warps = std::max(1, std::min(warps, icp_max_warps(e)));
+    // Elastic kernel: warps without an ICP of their own help the ICPs in flight in their CTA.  It pays while the
+    // tail (the last ICP of every warp) is a visible share of the launch - measured: 1.7 ICPs per warp slot +8..19 %,
+    // 28 per slot -2 % (its one-warp-per-ICP path compiles slightly worse) - so by default it is used below 10 ICPs per
+    // warp slot.  `team` = warps per ICP at launch: one, unless the batch is smaller than the machine (fewer ICPs
+    // than warp slots) - then each CTA starts with fewer leads than warps and the rest help from the first pass on.
+    // Results are bit-identical in every mode.
+    if (prm->no_helpers < 0 || prm->no_helpers > 2) { set_error("ficp_batch_create: no_helpers must be 0 (auto), 1 (off) or 2 (on)"); return kErrInvalid; }
+    const long long n_icps_all = (long long)n_plots * n_hyp_local;
+    const bool elastic = prm->no_helpers == 2 || (prm->no_helpers == 0 && (prm->team_warps > 1 || n_icps_all < 10LL * sms * 16));
+    int team = prm->team_warps;
+    if (team != 0 && team != 1 && team != 2 && team != 4 && team != 8) { set_error("ficp_batch_create: team_warps must be 0 (auto), 1, 2, 4 or 8"); return kErrInvalid; }
+    if (!elastic && team > 1) { set_error("ficp_batch_create: team_warps > 1 needs the elastic kernel (no_helpers = 0)"); return kErrInvalid; }
+    if (team == 0) {
+        team = 1;
+        const long long n_icps = (long long)n_plots * n_hyp_local, slots16 = (long long)sms * 16;
+        while (elastic && team < 8 && n_icps * team * 2 <= slots16) team *= 2;
+    }
+    while (team > 1 && (team > e || team > warps)) team >>= 1;  // at least one round per warp of the team
+    const int slots_per_cta = std::max(1, std::min(warps / team, n_hyp_local));
+    warps = slots_per_cta * team;
     const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
     const int wcap_rows = 256;
-    const size_t fixed_bytes = icp_smem_bytes(e, z3, warps, 0, 0, wcap_rows);
+    const size_t fixed_bytes = icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows);
     const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
     auto cap_for = [&](int ctas) -> int {
         const size_t budget = std::min<size_t>((size_t)smem_optin, sm_total / ctas - 1024);
@@ -495,17 +515,17 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // do not reserve more on-chip window than any plot can use
     wcap_pts = std::min(wcap_pts, need_pts);
     const int wcap_cells = wcap_pts;
-    const size_t smem = icp_smem_bytes(e, z3, warps, wcap_pts, wcap_cells, wcap_rows);
+    const size_t smem = icp_smem_bytes(e, z3, slots_per_cta, wcap_pts, wcap_cells, wcap_rows);
     if (smem > (size_t)smem_optin) { set_error("ficp_batch_create: shared-memory plan exceeds the device limit"); return kErrTooLarge; }
     int occ = 0;
-    int rc = icp_max_ctas_per_sm(e, z3, warps, smem, &occ);
+    int rc = icp_max_ctas_per_sm(e, z3, warps, elastic, smem, &occ);
     if (rc) return rc;
     if (occ < 1) { set_error("ficp_batch_create: kernel does not fit on an SM with this configuration"); return kErrTooLarge; }
     const int ctas_per_sm = prm->ctas_per_sm > 0 ? std::min(occ, prm->ctas_per_sm) : occ;
     const long long resident = (long long)sms * ctas_per_sm;
     // tickets: each plot can be worked on by up to `slices_per_plot` CTAs at once (all of them when there are
     // few plots); tickets are dealt round-robin over the plots by the kernel
-    const int max_slices_per_plot = (n_hyp_local + warps - 1) / warps;
+    const int max_slices_per_plot = (n_hyp_local + slots_per_cta - 1) / slots_per_cta;
     int slices_per_plot = (int)std::min<long long>(max_slices_per_plot, resident);
     const long long n_slices = (long long)n_plots * slices_per_plot;
     if (n_slices > 2000000000LL) { set_error("ficp_batch_create: too many work slices"); return kErrTooLarge; }
@@ -557,8 +577,10 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     P.slice_counter = b->d_counters; P.hyp_counter = b->d_counters + 1;
     P.slices_per_plot = slices_per_plot; P.n_slices = (int)n_slices;
     P.wcap_pts = wcap_pts; P.wcap_cells = wcap_cells; P.wcap_rows = wcap_rows;
+    P.slots = slots_per_cta;
+    P.dyn_leads = warps / 2;  // rounds are handed out once the helpers are at least as many as the leads (8 vs 12: same)
     P.stats = b->d_stats;
-    b->launch.e = e; b->launch.z3 = z3; b->launch.warps = warps; b->launch.smem = smem;
+    b->launch.e = e; b->launch.z3 = z3; b->launch.warps = warps; b->launch.slots = slots_per_cta; b->launch.elastic = elastic; b->launch.smem = smem;
     b->launch.ctas = (int)std::min<long long>(n_slices, resident);
     b->ctas_per_sm = ctas_per_sm;
     guard.armed = false;
@@ -572,7 +594,7 @@ int ficp_batch_get_info(const ficp_batch* bh, ficp_batch_info* info) {
     info->n_plots = b->n_plots; info->n_hyp = b->n_hyp; info->n_hyp_local = b->n_hyp_local;
     info->elems_per_lane = b->launch.e; info->match_z = b->z3 ? 1 : 0; info->warps_per_cta = b->launch.warps;
     info->ctas = b->launch.ctas; info->ctas_per_sm = b->ctas_per_sm; info->slices_per_plot = b->params.slices_per_plot;
-    info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells;
+    info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells; info->team_warps = b->launch.warps / b->launch.slots; info->helpers = b->launch.elastic ? 1 : 0;
     info->smem_bytes = (int64_t)b->launch.smem; info->rows = b->rows;
     return kOk;
 }

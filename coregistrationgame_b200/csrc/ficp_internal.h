@@ -115,6 +115,8 @@ struct IcpParams {
     int* hyp_counter;               // [n_plots]
     int slices_per_plot, n_slices;
     int wcap_pts, wcap_cells, wcap_rows;
+    int slots;                      // elastic kernel: lead warps (ICPs in flight) per CTA; the rest help
+    int dyn_leads;                  // rounds are handed out to helpers while at most this many leads are active
     unsigned long long* stats;      // [0] passes [1] queries resolved on the global path [2] window disabled
                                     // [3] trim-order fix-up rounds [4] queries
 };
@@ -123,12 +125,14 @@ struct IcpLaunch {
     int e;            // elements per lane (NPAD = 32*e)
     bool z3;
     int warps;        // warps per CTA
+    int slots;        // lead warps per CTA (= warps unless elastic)
+    bool elastic;     // idle warps help the ICPs in flight (icp_kernel<..., true>)
     int ctas;         // grid size
     size_t smem;      // dynamic shared memory per CTA
 };
 int icp_max_warps(int e);
-size_t icp_smem_bytes(int e, bool z3, int warps, int wcap_pts, int wcap_cells, int wcap_rows);
-int icp_max_ctas_per_sm(int e, bool z3, int warps, size_t smem, int* out);
+size_t icp_smem_bytes(int e, bool z3, int slots, int wcap_pts, int wcap_cells, int wcap_rows);
+int icp_max_ctas_per_sm(int e, bool z3, int warps, bool elastic, size_t smem, int* out);
 int launch_icp(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream);
 
 }  // namespace ficp

@@ -11,6 +11,10 @@
 // Mapping (DESIGN.md "persistent kernel"):
 //   * one WARP owns one (plot, hypothesis) ICP from start to convergence - no block barrier inside
 //     the loop, so the 5..70-pass spread between hypotheses costs nothing;
+//   * ELASTIC: warps with no ICP of their own (the batch is smaller than the machine - one stand sharded over 8
+//     GPUs, one start pose per plot - or the plot is running out of hypotheses) HELP the ICPs in flight in
+//     their CTA: a lead hands out the nearest-neighbour rounds of its pass through a shared-memory ticket;
+//     trimming and fit stay with the lead in unchanged arithmetic, so results are bit-identical either way;
 //   * each lane owns E source points (N <= 32*E); the trim order is a register-resident bitonic
 //     sort of packed 32-bit keys (quantised d2 | point index) followed by an exact fix-up on the
 //     fp64 (d2, index) keys, a warp prefix scan of d2 and an arg-min of FRMSD(k);
@@ -38,11 +42,30 @@ struct LaneCfg {
     static constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
 };
 
+struct Pose {  // q = M u + c ; warp-uniform
+    double m00, m01, m10, m11, cx, cy;
+};
+
+// Elastic mode: what a lead warp publishes for the helper warps of its CTA (warps that have no ICP of their own).
+struct __align__(16) SlotCtrl {
+    Pose pose;         // pose of the pass in flight
+    int ticket;        // (epoch << 8) | next work unit to hand out; a unit field >= `count` means "closed"
+    int count;         // work units of the current epoch (rounds of 32 queries, or chunks of 32 deferred queries)
+    int done;          // units of the current epoch completed (by anyone)
+    int mode;          // 0: nearest-neighbour rounds, 1: chunks of the deferred list
+    int have_prev;     // the pass has a previous pass's neighbours to seed from
+    int ndef;          // length of the deferred list (mode 1)
+    int nglob;         // helpers' count of queries that ran on the global grid
+    int pad;
+};
+constexpr int kTicketClosed = 0xFF;
+
 // ---- shared-memory carve-up (host and device use the same function) -------------------------------
 struct SmemLayout {
-    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, sord, w_cell, rowoff, rowdelta, rowg, total;
+    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, sord, ctrl, w_cell, rowoff, rowdelta, rowg, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, int wcap_pts, int wcap_cells,
+// `slots` = ICPs in flight per CTA (= lead warps); the other warps of the CTA, if any, are helpers
+__host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int slots, int wcap_pts, int wcap_cells,
                                                   int wcap_rows) {
     SmemLayout L;
     size_t o = 0;
@@ -52,9 +75,10 @@ __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int warps, 
     L.s_z = take(z3 ? (size_t)npad * 8 : 0);
     L.w_z = take(z3 ? (size_t)wcap_pts * 8 : 0);
     L.s_g = take((size_t)kMaxStages * npad * 8);
-    L.sd2 = take((size_t)warps * npad * 8);
-    L.snn = take((size_t)warps * npad * 4);
-    L.sord = take((size_t)warps * npad * 2);
+    L.sd2 = take((size_t)slots * npad * 8);
+    L.snn = take((size_t)slots * npad * 4);
+    L.sord = take((size_t)slots * npad * 2);
+    L.ctrl = take((size_t)slots * sizeof(SlotCtrl));
     L.w_cell = take((size_t)wcap_cells * 4);
     L.rowoff = take((size_t)(wcap_rows + 1) * 4);
     L.rowdelta = take((size_t)wcap_rows * 4);
@@ -122,10 +146,6 @@ __device__ __forceinline__ bool key_greater(double da, unsigned ka, double db, u
     return (da > db) || (da == db && ka > kb);
 }
 
-struct Pose {  // q = M u + c ; warp-uniform
-    double m00, m01, m10, m11, cx, cy;
-};
-
 struct PassOut {
     int k;          // trimmed subset size (0: none, like ficp.py:125)
     double f;       // FRMSD at k
@@ -165,89 +185,287 @@ FICP_GLOBAL_ATTR int nn_query_global(const GridView& G, double qx, double qy, do
     return pos;
 }
 
-// One NN pass + trimming for the warp's hypothesis.
-template <int E, bool Z3>
-__device__ __forceinline__ PassOut icp_pass(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
-                                            const Pose& P, const double* __restrict__ s_g,
-                                            const double* __restrict__ g_c, double* __restrict__ sd2,
-                                            int* __restrict__ snn, unsigned short* __restrict__ sord, int lane,
-                                            bool have_prev, unsigned& n_global, unsigned& n_fix) {
-    using C = LaneCfg<E>;
-    const int n = pc.n;
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-    // ---- nearest neighbours: one query per lane per round.  Round e takes the 32 queries at positions
-    // 32e..32e+31 of the PREVIOUS pass's trim order (identity on the first pass): neighbours in that order have
-    // similar residuals, hence similar search radii and candidate counts, so the lanes of a warp finish together
-    // and the rare wide searches (ring >= 2) fall into the same rounds. ----
-    // Queries whose 3x3 block does not settle the search (wide search radius, or the block is not inside the
-    // shared-memory window) are NOT finished inline - a handful of lanes would drag the whole warp through the
-    // ring loop in almost every round.  They are appended (ballot-compacted) to a per-warp list that reuses the
-    // already-consumed slots of `sord`, and finished afterwards with all lanes busy.
-    int n_def = 0;
-#pragma unroll 1
-    for (int e = 0; e < E; ++e) {
-        const int p = e * 32 + lane;
-        int defer = -1;  // >= 0: (point index | 0x8000 if it must run on the global grid)
-        if (p < n) {
-            const int i = sord[p];
-            FICP_ASSERT(i >= 0 && i < n);
-            double qx, qy;
-            pose_apply(P, pc.s_u[i], qx, qy);
-            const double qz = Z3 ? pc.s_z[i] : 0.0;
-            // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
-            const int pc_prev = have_prev ? snn[i] : -1;
-            double best = kInf;
-            int pos = -1, cx, cy;
-            bool ok = false;
-            if (win_ok) ok = nn_search_block3<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy);
-            if (ok) {
-                sd2[i] = best;
-                snn[i] = pos;
-                if (!nn_block_settles(G.g, qx, qy, cx, cy, 1, best)) defer = i;
-            } else {
-                if (!have_prev) snn[i] = -1;  // keep the previous pass's code as the seed of the deferred query
-                defer = i | 0x8000;
-            }
+// A warp-uniform view of a shared word that other warps change: ONE lane reads, everybody gets that value.  (Every lane
+// reading for itself can split the warp on a loop or branch condition when the lanes are not converged at the load.)
+__device__ __forceinline__ int ld_volatile_uniform(const int* p, int lane) {
+    __syncwarp();
+    int v = 0;
+    if (lane == 0) v = ld_volatile(p);
+    return __shfl_sync(kFull, v, 0);
+}
+
+// Hand out the next work unit of a slot's epoch in flight: -1 when none is left (or the slot is closed).
+__device__ __forceinline__ int grab_unit(SlotCtrl* c, int lane) {
+    int e = -1;
+    if (lane == 0) {
+        for (;;) {
+            const int t = ld_volatile(&c->ticket);
+            if ((t & 0xFF) >= ld_volatile(&c->count)) break;   // count belongs to t's epoch iff the CAS below succeeds
+            if (atomicCAS(&c->ticket, t, t + 1) == t) { e = t & 0xFF; break; }
         }
-        const unsigned m = __ballot_sync(kFull, defer >= 0);
-        FICP_ASSERT(n_def + __popc(m) <= e * 32 + 32);
-        if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
-        n_def += __popc(m);
+    }
+    return __shfl_sync(kFull, e, 0);
+}
+
+// Lead: open an epoch of `count` units for the helpers.
+__device__ __forceinline__ void open_epoch(SlotCtrl* c, int& epoch, int mode, int count, int lane) {
+    if (lane == 0) {
+        c->mode = mode;
+        c->done = 0;
+        *reinterpret_cast<volatile int*>(&c->ticket) = (epoch << 8) | kTicketClosed;  // nobody grabs while count changes
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&c->count) = count;
+        __threadfence_block();
+        epoch = (epoch + 1) & 0x7FFFFF;
+        *reinterpret_cast<volatile int*>(&c->ticket) = epoch << 8;
     }
     __syncwarp();
-#pragma unroll 1
-    for (int base = 0; base < n_def; base += 32) {
-        if (base + lane < n_def) {
-            const int d = sord[base + lane];
-            const int i = d & 0x7FFF;
-            FICP_ASSERT(i < n);
-            double qx, qy;
-            pose_apply(P, pc.s_u[i], qx, qy);
-            const double qz = Z3 ? pc.s_z[i] : 0.0;
-            double best = kInf;
-            int pos = -1;
-            bool ok = false;
-            if (!(d & 0x8000)) {
-                best = sd2[i];
-                pos = snn[i];
-                const int cx = clamp_cell((qx - G.g.x0) * G.g.inv_h, G.g.gw);
-                const int cy = clamp_cell((qy - G.g.y0) * G.g.inv_h, G.g.gh);
-                ok = nn_ring_loop_impl<Z3>(W, G.g, qx, qy, qz, cx, cy, 2, best, pos);
-            }
-            int code = pos;
-            if (!ok) {
-                // window miss: whole query on the global grid, seeded with the best candidate known so far
-                const int seed = snn[i];
-                const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed) : (seed & 0x7FFFFFFF));
-                pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
-                code = (int)((unsigned)pos | 0x80000000u);
-                ++n_global;
+}
+
+// Lead: wait until every unit of the epoch is done, then close the slot.
+__device__ __forceinline__ void close_epoch(SlotCtrl* c, int epoch, int count, int lane) {
+    if (lane == 0) {
+        while (ld_volatile(&c->done) < count) __nanosleep(40);
+        *reinterpret_cast<volatile int*>(&c->ticket) = (epoch << 8) | kTicketClosed;
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+
+__device__ __forceinline__ void unit_done(SlotCtrl* c, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&c->done, 1);
+}
+
+// 32 entries of the deferred list: rings >= 2 inside the window, or the whole query on the global grid.
+template <bool Z3, bool ELASTIC>
+__device__ __forceinline__ void nn_deferred_chunk(const GridView& G, const WindowAcc& W, const PlotCtx& pc, const Pose& P,
+                                                  double* __restrict__ sd2, int* __restrict__ snn,
+                                                  const unsigned short* __restrict__ sord, int base, int n_def,
+                                                  int lane, unsigned& n_global) {
+    if (base + lane < n_def) {
+        const int d = sord[base + lane];
+        const int i = d & 0x7FFF;
+        FICP_ASSERT(i < pc.n);
+        double qx, qy;
+        pose_apply(P, pc.s_u[i], qx, qy);
+        const double qz = Z3 ? pc.s_z[i] : 0.0;
+        double best = kInf;
+        int pos = -1;
+        bool ok = false;
+        if (!(d & 0x8000)) {
+            best = ELASTIC ? fabs(sd2[i]) : sd2[i];
+            pos = snn[i];
+            const int cx = clamp_cell((qx - G.g.x0) * G.g.inv_h, G.g.gw);
+            const int cy = clamp_cell((qy - G.g.y0) * G.g.inv_h, G.g.gh);
+            ok = nn_ring_loop_impl<Z3>(W, G.g, qx, qy, qz, cx, cy, 2, best, pos);
+        }
+        int code = pos;
+        if (!ok) {
+            // window miss: whole query on the global grid, seeded with the best candidate known so far
+            const int seed = snn[i];
+            const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed) : (seed & 0x7FFFFFFF));
+            pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
+            code = (int)((unsigned)pos | 0x80000000u);
+            ++n_global;
+        }
+        sd2[i] = best;
+        snn[i] = code;
+    }
+}
+
+// One round of nearest-neighbour queries: the 32 queries at positions 32e..32e+31 of the PREVIOUS pass's trim order
+// (identity on the first pass): neighbours in that order have similar residuals, hence similar search radii and
+// candidate counts, so the lanes of a warp finish together and the rare wide searches (ring >= 2) fall into the same
+// rounds.  Queries whose 3x3 block does not settle the search (wide search radius, or the block is not inside the
+// shared-memory window) are NOT finished inline - a handful of lanes would drag the whole warp through the ring loop
+// in almost every round - they are returned as `defer` (point index | 0x8000 if it must run on the global grid) and
+// finished afterwards with all lanes busy.  MARK: also flag them in the sign bit of sd2 (-best: in-window candidate
+// known, -inf: nothing known) for rounds that complete out of order.
+template <bool Z3, bool MARK>
+__device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
+                                        const Pose& P, double* __restrict__ sd2, int* __restrict__ snn,
+                                        const unsigned short* __restrict__ sord, int e, int lane, bool have_prev) {
+    const int p = e * 32 + lane;
+    int defer = -1;
+    if (p < pc.n) {
+        const int i = sord[p];
+        FICP_ASSERT(i >= 0 && i < pc.n);
+        double qx, qy;
+        pose_apply(P, pc.s_u[i], qx, qy);
+        const double qz = Z3 ? pc.s_z[i] : 0.0;
+        // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
+        const int pc_prev = have_prev ? snn[i] : -1;
+        double best = kInf;
+        int pos = -1, cx, cy;
+        bool ok = false;
+        if (win_ok) ok = nn_search_block3<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy);
+        if (ok) {
+            snn[i] = pos;
+            if (!nn_block_settles(G.g, qx, qy, cx, cy, 1, best)) {
+                defer = i;
+                if (MARK) best = -best;
             }
             sd2[i] = best;
-            snn[i] = code;
+        } else {
+            if (!have_prev) snn[i] = -1;  // keep the previous pass's code as the seed of the deferred query
+            if (MARK) sd2[i] = -kInf;
+            defer = i | 0x8000;
+        }
+    }
+    return defer;
+}
+
+// Everything a warp needs to work on the plot staged in this CTA, rebuilt from the kernel parameters and the plot's
+// metadata (so that the out-of-line slot_work below takes three pointers instead of references to the caller's
+// structures, which would otherwise be forced into local memory).
+template <bool Z3>
+struct PlotView {
+    WindowAcc W;
+    PlotCtx pc;
+    __device__ __forceinline__ PlotView(const IcpParams& P, const PlotMeta& pm, unsigned char* smem, const SmemLayout& L)
+        : W{reinterpret_cast<double2*>(smem + L.w_xy), reinterpret_cast<double*>(smem + L.w_z),
+            reinterpret_cast<unsigned*>(smem + L.w_cell), reinterpret_cast<int*>(smem + L.rowoff),
+            reinterpret_cast<int*>(smem + L.rowdelta), P.grid.orig, P.grid.rec,
+            pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0},
+          pc{reinterpret_cast<double2*>(smem + L.s_u), reinterpret_cast<double*>(smem + L.s_z), pm.n, pm.fixed_k,
+             pm.ubx, pm.uby} {}
+};
+
+// Take work units of slot `s` until its epoch has none left (called by helpers and by the slot's own lead).  Out of
+// line on purpose: the one-warp-per-ICP code around the call sites stays exactly what it is without helpers.
+template <bool Z3>
+__device__ __noinline__ void slot_work(const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, int npad,
+                                       int win_ok, int s, int lane) {
+    const IcpParams& P = *Pp;
+    const PlotMeta pm = *pmp;
+    const SmemLayout L = smem_layout(npad, Z3, P.slots, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    const PlotView<Z3> V(P, pm, smem, L);
+    const GridView& G = P.grid;
+    SlotCtrl* c = reinterpret_cast<SlotCtrl*>(smem + L.ctrl) + s;
+    double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)s * npad;
+    int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)s * npad;
+    const unsigned short* sord = reinterpret_cast<const unsigned short*>(smem + L.sord) + (size_t)s * npad;
+#pragma unroll 1
+    for (;;) {
+        const int e = grab_unit(c, lane);
+        if (e < 0) break;
+        __threadfence_block();
+        const Pose pose = c->pose;
+        if (c->mode == 0) {
+            (void)nn_round<Z3, true>(G, V.W, win_ok != 0, V.pc, pose, sd2, snn, sord, e, lane, c->have_prev != 0);
+        } else {
+            unsigned ng = 0;
+            nn_deferred_chunk<Z3, true>(G, V.W, V.pc, pose, sd2, snn, sord, e * 32, c->ndef, lane, ng);
+            ng = __reduce_add_sync(kFull, ng);
+            if (lane == 0 && ng) atomicAdd(&c->nglob, (int)ng);
+        }
+        unit_done(c, lane);
+    }
+}
+
+// Nearest neighbours of one pass (ficp.py:65-71) for the ICP of slot `ctrl`.  ELASTIC: when enough warps of the CTA
+// have no ICP of their own (`*sh_active <= dyn_leads`: the batch is smaller than the machine, or the plot is running
+// out of hypotheses) the rounds are handed out through the slot's ticket so that those warps take some; trimming
+// and fit stay with the lead warp in unchanged arithmetic, so results do not depend on who computed a round.
+template <int E, bool Z3, bool ELASTIC>
+__device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
+                                             const Pose& P, double* __restrict__ sd2, int* __restrict__ snn,
+                                             unsigned short* __restrict__ sord, SlotCtrl* ctrl, const int* sh_active,
+                                             const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, int slot,
+                                             int& epoch, int lane, bool have_prev, unsigned& n_global) {
+    const int n = pc.n;
+    int n_def = 0;
+    if (ELASTIC && ld_volatile_uniform(sh_active, lane) <= Pp->dyn_leads) {
+        const int rounds = (n + 31) >> 5;
+        if (lane == 0) {
+            ctrl->pose = P;
+            ctrl->have_prev = have_prev ? 1 : 0;
+        }
+        open_epoch(ctrl, epoch, 0, rounds, lane);
+        slot_work<Z3>(Pp, pmp, smem, 32 * E, win_ok ? 1 : 0, slot, lane);
+        // wait for the rounds the helpers took, then compact the flagged queries into `sord` (all consumed by now)
+        close_epoch(ctrl, epoch, rounds, lane);
+#pragma unroll 1
+        for (int e = 0; e < rounds; ++e) {
+            const int p = e * 32 + lane;
+            int defer = -1;
+            if (p < n) {
+                const int i = sord[p];
+                const long long b = __double_as_longlong(sd2[i]);
+                if (b < 0) defer = i | ((b == __double_as_longlong(-kInf)) ? 0x8000 : 0);
+            }
+            const unsigned m = __ballot_sync(kFull, defer >= 0);
+            if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
+            n_def += __popc(m);
+        }
+        __syncwarp();
+        if (n_def > 32) {
+            // the deferred list is handed out as well, in chunks of 32
+            const int chunks = (n_def + 31) >> 5;
+            if (lane == 0) ctrl->ndef = n_def;
+            open_epoch(ctrl, epoch, 1, chunks, lane);
+            slot_work<Z3>(Pp, pmp, smem, 32 * E, win_ok ? 1 : 0, slot, lane);
+            close_epoch(ctrl, epoch, chunks, lane);
+            n_def = 0;
+        }
+    } else {
+        // in-order rounds: the deferred list reuses the already-consumed slots of `sord`
+#pragma unroll 1
+        for (int e = 0; e < E; ++e) {
+            const int defer = nn_round<Z3, false>(G, W, win_ok, pc, P, sd2, snn, sord, e, lane, have_prev);
+            const unsigned m = __ballot_sync(kFull, defer >= 0);
+            FICP_ASSERT(n_def + __popc(m) <= e * 32 + 32);
+            if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
+            n_def += __popc(m);
         }
     }
     __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < n_def; base += 32)
+        nn_deferred_chunk<Z3, ELASTIC>(G, W, pc, P, sd2, snn, sord, base, n_def, lane, n_global);
+    __syncwarp();
+}
+
+// A warp without an ICP of its own: take work units from the passes in flight in this CTA until every lead is done.
+template <bool Z3>
+__device__ __forceinline__ void icp_help(const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, SlotCtrl* ctrls,
+                                         int npad, int win_ok, int slots, const int* sh_active, int warp, int lane) {
+    int s = warp % slots;
+    unsigned idle = 0;
+#pragma unroll 1
+    while (ld_volatile_uniform(sh_active, lane) > 0) {
+        bool open = false;
+        if (lane == 0) {
+#pragma unroll 1
+            for (int k = 0; k < slots; ++k) {
+                const int t = ld_volatile(&ctrls[s].ticket);
+                if ((t & 0xFF) < ld_volatile(&ctrls[s].count)) { open = true; break; }
+                s = (s + 1 == slots) ? 0 : s + 1;
+            }
+        }
+        open = __shfl_sync(kFull, (int)open, 0) != 0;
+        s = __shfl_sync(kFull, s, 0);
+        if (open) {
+            slot_work<Z3>(Pp, pmp, smem, npad, win_ok, s, lane);
+            idle = 0;
+        } else {
+            idle = min(idle + 1, 8u);
+            __nanosleep(100u << (idle >> 1));  // back off (up to 1.6 us): spinning warps compete with the leads for issue slots
+        }
+    }
+}
+
+// FRMSD trimming of one pass (ficp.py:62-63,73-86), by the ICP's (lead) warp.
+template <int E>
+__device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const double* __restrict__ s_g,
+                                                  const double* __restrict__ g_c, const double* __restrict__ sd2,
+                                                  unsigned short* __restrict__ sord, int lane, unsigned& n_fix) {
+    using C = LaneCfg<E>;
+    const int n = pc.n;
 
     // ---- trim order: packed keys (monotone 32-IDXBITS-bit code of d2 | index), warp bitonic sort ----
     unsigned key[E];
@@ -465,21 +683,27 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
     P = Q;
 }
 
-template <int E, bool Z3, int NT>
-__global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
+template <int E, bool Z3, int NT, bool ELASTIC>
+__global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpParams P) {
     using C = LaneCfg<E>;
     constexpr int NPAD = C::kNPad;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const SmemLayout L = smem_layout(NPAD, Z3, nwarps, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    // ELASTIC: the first `slots` warps of the CTA lead an ICP each; the others - and every lead that finds no
+    // hypothesis left - help with the nearest-neighbour rounds of the passes in flight
+    const int slots = ELASTIC ? P.slots : nwarps;
+    const bool is_lead = warp < slots;
+    const int slot = is_lead ? warp : 0;
+    const SmemLayout L = smem_layout(NPAD, Z3, slots, P.wcap_pts, P.wcap_cells, P.wcap_rows);
     double2* s_u = reinterpret_cast<double2*>(smem + L.s_u);
     double2* w_xy = reinterpret_cast<double2*>(smem + L.w_xy);
     double* s_z = reinterpret_cast<double*>(smem + L.s_z);
     double* w_z = reinterpret_cast<double*>(smem + L.w_z);
     double* s_g = reinterpret_cast<double*>(smem + L.s_g);
-    double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)warp * NPAD;
-    int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)warp * NPAD;
-    unsigned short* sord = reinterpret_cast<unsigned short*>(smem + L.sord) + (size_t)warp * NPAD;
+    double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)slot * NPAD;
+    int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)slot * NPAD;
+    unsigned short* sord = reinterpret_cast<unsigned short*>(smem + L.sord) + (size_t)slot * NPAD;
+    SlotCtrl* ctrl = reinterpret_cast<SlotCtrl*>(smem + L.ctrl) + slot;
     unsigned* w_cell = reinterpret_cast<unsigned*>(smem + L.w_cell);
     int* rowoff = reinterpret_cast<int*>(smem + L.rowoff);
     int* rowdelta = reinterpret_cast<int*>(smem + L.rowdelta);
@@ -487,8 +711,11 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
     __shared__ int sh_slice;
     __shared__ int sh_exhausted;
     __shared__ int sh_win_ok;
+    __shared__ int sh_active;  // ELASTIC: warps leading an ICP or still entitled to pull one
 
     const GridView& G = P.grid;
+    if (ELASTIC && is_lead && lane == 0) { ctrl->ticket = kTicketClosed; ctrl->count = 0; }
+    int epoch = 0;
     int staged_plot = -1;
     unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0;
 
@@ -498,6 +725,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             const int t = atomicAdd(P.slice_counter, 1);
             sh_slice = t;
             sh_exhausted = (t < P.n_slices) ? (atomicAdd(P.hyp_counter + (t % P.n_plots), 0) >= P.n_hyp_local) : 0;
+            sh_active = slots;
         }
         __syncthreads();
         const int slice = sh_slice;
@@ -570,8 +798,9 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
         const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
         const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NPAD;  // [stage][0]=g [stage][1]=c
 
-        // ---- warps pull hypotheses of this plot until none are left ----
+        // ---- lead warps pull hypotheses of this plot until none are left ----
         for (;;) {
+            if (!is_lead) break;
             int j = 0;
             if (lane == 0) j = atomicAdd(P.hyp_counter + plot, 1);
             j = __shfl_sync(kFull, j, 0);
@@ -581,6 +810,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
             unsigned n_global = 0, n_fix = 0;
             int passes = 0;
+            if (ELASTIC && lane == 0) ctrl->nglob = 0;
             // first pass: identity order; padding slots never change
             for (int i = lane; i < NPAD; i += 32) {
                 sord[i] = (unsigned short)i;
@@ -597,7 +827,9 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
                 int it = 0;
                 bool first = true;
                 for (;;) {
-                    po = icp_pass<E, Z3>(G, W, win_ok, pc, pose, sg, gc, sd2, snn, sord, lane, passes > 0, n_global, n_fix);
+                    icp_nn_phase<E, Z3, ELASTIC>(G, W, win_ok, pc, pose, sd2, snn, sord, ctrl, &sh_active, &P, P.plots + plot,
+                                                 smem, slot, epoch, lane, passes > 0, n_global);
+                    po = icp_trim_phase<E>(pc, sg, gc, sd2, sord, lane, n_fix);
                     ++passes;
                     if (first) {
                         if (po.k == 0) break;  // ficp.py:125-126
@@ -616,6 +848,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             }
             // ---- results ----
             n_global = __reduce_add_sync(kFull, n_global);  // counted per lane
+            if (ELASTIC) n_global += (unsigned)ld_volatile_uniform(&ctrl->nglob, lane);
             const size_t ridx = (size_t)plot * P.n_hyp_local + j;
             if (lane == 0) {
                 HypResult r;
@@ -641,6 +874,14 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const IcpParams P) {
             acc_queries += (unsigned long long)passes * pm.n;
             __syncwarp();
         }
+        if (ELASTIC) {
+            // no hypothesis left for this warp: help the passes still in flight in this CTA
+            if (is_lead && lane == 0) atomicSub(&sh_active, 1);
+            __syncwarp();
+            if (P.dyn_leads >= 0)
+                icp_help<Z3>(&P, P.plots + plot, smem, reinterpret_cast<SlotCtrl*>(smem + L.ctrl), NPAD, win_ok ? 1 : 0, slots,
+                             &sh_active, warp, lane);
+        }
     }
     if (lane == 0 && acc_passes) {
         atomicAdd(P.stats + 0, acc_passes);
@@ -662,11 +903,11 @@ struct KernelFor {
 template <int E, bool Z3>
 int launch_one(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream) {
     constexpr int NT = KernelFor<E, Z3>::kNT;
-    if (l.warps * 32 > NT) {
-        set_error("launch_icp: too many warps per CTA for this instantiation");
+    if (l.warps * 32 > NT || l.slots < 1 || l.slots > l.warps || (!l.elastic && l.slots != l.warps)) {
+        set_error("launch_icp: bad warps per CTA / lead warps for this instantiation");
         return kErrInvalid;
     }
-    auto kern = icp_kernel<E, Z3, NT>;
+    auto kern = l.elastic ? icp_kernel<E, Z3, NT, true> : icp_kernel<E, Z3, NT, false>;
     FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
     kern<<<l.ctas, l.warps * 32, l.smem, stream>>>(p);
     FICP_CUDA(cudaGetLastError());
@@ -674,9 +915,9 @@ int launch_one(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream) {
 }
 
 template <int E, bool Z3>
-int occupancy_one(int warps, size_t smem, int* out) {
+int occupancy_one(int warps, bool elastic, size_t smem, int* out) {
     constexpr int NT = KernelFor<E, Z3>::kNT;
-    auto kern = icp_kernel<E, Z3, NT>;
+    auto kern = elastic ? icp_kernel<E, Z3, NT, true> : icp_kernel<E, Z3, NT, false>;
     FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, warps * 32, smem));
     return kOk;
@@ -684,8 +925,8 @@ int occupancy_one(int warps, size_t smem, int* out) {
 
 }  // namespace
 
-size_t icp_smem_bytes(int e, bool z3, int warps, int wcap_pts, int wcap_cells, int wcap_rows) {
-    return smem_layout(32 * e, z3, warps, wcap_pts, wcap_cells, wcap_rows).total;
+size_t icp_smem_bytes(int e, bool z3, int slots, int wcap_pts, int wcap_cells, int wcap_rows) {
+    return smem_layout(32 * e, z3, slots, wcap_pts, wcap_cells, wcap_rows).total;
 }
 
 int icp_max_warps(int e) { return (e >= 32) ? 12 : (e >= 16) ? FICP_NT16 / 32 : 16; }  // = KernelFor<E>::kNT / 32
@@ -701,8 +942,8 @@ int icp_max_warps(int e) { return (e >= 32) ? 12 : (e >= 16) ? FICP_NT16 / 32 : 
         default: set_error("launch_icp: unsupported elements-per-lane"); return kErrInvalid;      \
     }
 
-int icp_max_ctas_per_sm(int e, bool z3, int warps, size_t smem, int* out) {
-    FICP_DISPATCH(occupancy_one, warps, smem, out)
+int icp_max_ctas_per_sm(int e, bool z3, int warps, bool elastic, size_t smem, int* out) {
+    FICP_DISPATCH(occupancy_one, warps, elastic, smem, out)
 }
 
 int launch_icp(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream) {

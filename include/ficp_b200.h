@@ -56,6 +56,11 @@ typedef struct {
     int32_t warps_per_cta;     /* 0 = auto */
     int32_t ctas_per_sm;       /* 0 = auto */
     int32_t disable_window;    /* 1 = never stage a window (every query walks the global grid); for tests */
+    int32_t team_warps;        /* warps per ICP at launch: 0 = auto (1 unless the batch has fewer ICPs than the GPU
+                                  has warp slots), 1, 2, 4 or 8; results do not depend on it */
+    int32_t no_helpers;        /* warps that run out of hypotheses help the ICPs still in flight in their CTA (elastic
+                                  kernel): 0 = auto (on for batches below ~10 ICPs per warp slot), 1 = off, 2 = on;
+                                  results are identical */
     int32_t reserved;
 } ficp_batch_params;
 
@@ -73,6 +78,9 @@ typedef struct {
     int32_t n_plots, n_hyp, n_hyp_local;
     int32_t elems_per_lane, match_z, warps_per_cta, ctas, ctas_per_sm, slices_per_plot;
     int32_t window_pts_cap, window_cells_cap;
+    int32_t team_warps;        /* warps per ICP at launch chosen by the planner */
+    int32_t helpers;           /* 1 = elastic kernel (idle warps help) */
+    int32_t reserved;
     int64_t smem_bytes;
     int64_t rows;
 } ficp_batch_info;

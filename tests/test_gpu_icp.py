@@ -230,6 +230,47 @@ def test_determinism_bitwise(gpu):
     np.testing.assert_array_equal(a["best_key"], b["best_key"])
 
 
+@pytest.mark.parametrize("n,dims", [(40, 2), (150, 3), (200, 2), (500, 3), (1000, 3)])
+def test_helper_warps_are_bit_identical(gpu, n, dims):
+    """Elastic kernel: warps without an ICP of their own (small batches: one stand over 8 GPUs, one start pose per
+    plot; or a plot running out of hypotheses) take nearest-neighbour rounds of the ICPs in flight; trimming and fit
+    keep their arithmetic, so the plain kernel and every team size return the same bits."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(40000, n, seed=21 + n, dims=dims, n_plots=3, hidden_pose=True, out_frac=0.15,
+                                        dup_every=7)
+    hyp = orc.hypothesis_table(6, flips=(0, 1), translations=[(0.0, 0.0), (60.0, -45.0)])   # second half: off the window
+    ti = TargetIndex(tgt)
+    base = None
+    for kw in (dict(team_warps=1, helpers=False), dict(team_warps=1), dict(team_warps=2), dict(team_warps=4),
+               dict(team_warps=8), dict(team_warps=0), dict(team_warps=4, disable_window=True),
+               dict(team_warps=2, warps_per_cta=6), dict(team_warps=1, warps_per_cta=3, ctas_per_sm=1)):
+        b = IcpBatch(ti, plots, hyp, **kw)
+        out = b.run().results()
+        assert b.info["helpers"] == int(kw.get("helpers", True))          # auto: 36 ICPs -> elastic
+        want = kw["team_warps"]
+        if want in (1, 2, 4, 8):
+            assert b.info["team_warps"] == min(want, b.info["elems_per_lane"], max(1, b.info["warps_per_cta"]))
+        else:
+            assert b.info["team_warps"] >= 2          # 36 ICPs on a 148-SM GPU: the planner teams up by itself
+        b.close()
+        if base is None:
+            base = out
+            ref = orc.run_hypotheses(plots[0], tgt, hyp[:3], centre=b.centres[0], min_k=3, closed_form=True)
+            np.testing.assert_array_equal(out["hyp"]["passes"][0, :3], ref["passes"])
+            continue
+        assert _rows_equal_except_flags(out["hyp"], base["hyp"]), kw
+        np.testing.assert_array_equal(out["best_key"], base["best_key"])
+        assert out["stats"]["passes"] == base["stats"]["passes"]
+    # one start pose per plot (C4 shape), with final positions
+    one = [IcpBatch(ti, plots, None, want_final_xy=True, team_warps=t, helpers=(t > 1)) for t in (1, 4)]
+    res = [b.run().results() for b in one]
+    assert _rows_equal_except_flags(res[0]["hyp"], res[1]["hyp"])
+    np.testing.assert_array_equal(res[0]["final_xy"], res[1]["final_xy"])
+    for b in one:
+        b.close()
+    ti.close()
+
+
 @pytest.mark.parametrize("dims", [2, 3])
 def test_full_size_c3_properties(gpu, dims):
     """Config 3 at full size (500 trees vs 1e6 CHM points, 4096 hypotheses): size-independent properties
@@ -295,7 +336,7 @@ def test_many_plots_one_pose_each_c4_shape(gpu):
         starts.append(orc.pre_transform(p, row, p[:, :2].mean(axis=0)))
     ti = TargetIndex(tgt)
     b = IcpBatch(ti, starts, None, centres=np.zeros((len(starts), 2)), min_k=0, want_final_xy=True)
-    assert b.info["n_hyp_local"] == 1 and b.info["warps_per_cta"] == 1
+    assert b.info["n_hyp_local"] == 1 and b.info["warps_per_cta"] == b.info["team_warps"]
     out = b.run().results()
     rows = out["hyp"][:, 0]
     offs = b.offsets

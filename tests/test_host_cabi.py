@@ -35,7 +35,8 @@ def test_abi_struct_sizes():
     import ctypes as C
     from coregistrationgame_b200 import _lib
     assert _lib.HYP_RESULT_DTYPE.itemsize == 80
-    assert C.sizeof(_lib.BatchParams) == 48
+    assert C.sizeof(_lib.BatchParams) == 56
+    assert C.sizeof(_lib.BatchInfo) == 72
     assert C.sizeof(_lib.TargetInfo) == 88
 
 

@@ -57,6 +57,10 @@ def one_case(rng):
         launch["disable_window"] = True
     if rng.random() < 0.2:
         launch["warps_per_cta"] = int(rng.choice([1, 2, 8]))
+    if rng.random() < 0.5:
+        launch["team_warps"] = int(rng.choice([1, 2, 4, 8]))    # default 0 = auto: these tiny batches team up anyway
+    elif rng.random() < 0.3:
+        launch["helpers"] = False                                # the plain kernel
     return src, tgt, hyp, kw, launch
 
 
