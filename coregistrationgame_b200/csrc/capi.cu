@@ -474,10 +474,12 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         while (elastic && team < 8 && n_icps * team * 2 <= slots16) team *= 2;
     }
     while (team > 1 && (team > e || team > warps)) team >>= 1;  // at least one round per warp of the team
-    const int slots_per_cta = std::max(1, std::min(warps / team, n_hyp_local));
-    warps = slots_per_cta * team;
+    int slots_per_cta = std::max(1, std::min(warps / team, n_hyp_local));
     const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
     const int wcap_rows = 256;
+    // per-ICP state (distances, neighbours, search list, slack: 16 B per tree) must leave room for a window
+    while (slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
+    warps = slots_per_cta * team;
     const size_t fixed_bytes = icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows);
     const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
     auto cap_for = [&](int ctas) -> int {

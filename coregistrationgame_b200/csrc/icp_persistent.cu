@@ -15,6 +15,12 @@
 //     GPUs, one start pose per plot - or the plot is running out of hypotheses) HELP the ICPs in flight in
 //     their CTA: a lead hands out the nearest-neighbour rounds of its pass through a shared-memory ticket;
 //     trimming and fit stay with the lead in unchanged arithmetic, so results are bit-identical either way;
+//   * SKIP TEST: a full search also yields a lower bound on the distance to every OTHER target point; the
+//     difference to the winner's distance is the query's SLACK.  On later passes the slack shrinks by the distance
+//     the pose update moves the query (triangle inequality, directed rounding); while the winner's new distance is
+//     still below it, the winner provably is the unique nearest neighbour again and the query costs ONE distance
+//     evaluation instead of a search (measured: ~80 % of all queries).  Only the others are compacted into a list
+//     and searched; the result is bit-identical to searching every query on every pass;
 //   * each lane owns E source points (N <= 32*E); the trim order is a register-resident bitonic
 //     sort of packed 32-bit keys (quantised d2 | point index) followed by an exact fix-up on the
 //     fp64 (d2, index) keys, a warp prefix scan of d2 and an arg-min of FRMSD(k);
@@ -26,6 +32,7 @@
 //     from a per-plot counter (dynamic load balance across the whole GPU).
 #include <algorithm>
 #include <climits>
+#include <cuda_fp16.h>
 #include "ficp_internal.h"
 #include "nn_search.cuh"
 
@@ -56,13 +63,13 @@ struct __align__(16) SlotCtrl {
     int have_prev;     // the pass has a previous pass's neighbours to seed from
     int ndef;          // length of the deferred list (mode 1)
     int nglob;         // helpers' count of queries that ran on the global grid
-    int pad;
+    int nlist;         // mode 0: entries of the search list (queries that failed the skip test)
 };
 constexpr int kTicketClosed = 0xFF;
 
 // ---- shared-memory carve-up (host and device use the same function) -------------------------------
 struct SmemLayout {
-    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, sord, ctrl, w_cell, rowoff, rowdelta, rowg, total;
+    size_t s_u, w_xy, s_z, w_z, s_g, sd2, snn, sord, ssl, ctrl, w_cell, rowoff, rowdelta, rowg, total;
 };
 // `slots` = ICPs in flight per CTA (= lead warps); the other warps of the CTA, if any, are helpers
 __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int slots, int wcap_pts, int wcap_cells,
@@ -78,6 +85,7 @@ __host__ __device__ inline SmemLayout smem_layout(int npad, bool z3, int slots, 
     L.sd2 = take((size_t)slots * npad * 8);
     L.snn = take((size_t)slots * npad * 4);
     L.sord = take((size_t)slots * npad * 2);
+    L.ssl = take((size_t)slots * npad * 2);
     L.ctrl = take((size_t)slots * sizeof(SlotCtrl));
     L.w_cell = take((size_t)wcap_cells * 4);
     L.rowoff = take((size_t)(wcap_rows + 1) * 4);
@@ -288,10 +296,11 @@ __device__ __forceinline__ void nn_deferred_chunk(const GridView& G, const Windo
 template <bool Z3, bool MARK>
 __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
                                         const Pose& P, double* __restrict__ sd2, int* __restrict__ snn,
-                                        const unsigned short* __restrict__ sord, int e, int lane, bool have_prev) {
+                                        __half* __restrict__ ssl, const unsigned short* __restrict__ sord, int e,
+                                        int count, int lane, bool have_prev) {
     const int p = e * 32 + lane;
     int defer = -1;
-    if (p < pc.n) {
+    if (p < count) {
         const int i = sord[p];
         FICP_ASSERT(i >= 0 && i < pc.n);
         double qx, qy;
@@ -302,10 +311,19 @@ __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, b
         double best = kInf;
         int pos = -1, cx, cy;
         bool ok = false;
-        if (win_ok) ok = nn_search_block3<Z3>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy);
+        int lb_hi = kHiInf;
+        if (win_ok)
+            ok = nn_search_block3_impl<Z3, true>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy, lb_hi);
+        float slack = 0.f;  // deferred / global-grid queries carry no bound: they are searched again next pass
         if (ok) {
             snn[i] = pos;
-            if (!nn_block_settles(G.g, qx, qy, cx, cy, 1, best)) {
+            const double border2 = nn_block_border2(G.g, qx, qy, cx, cy, 1);
+            if ((border2 == kInf) || best < border2) {   // == nn_block_settles
+                // every target point other than the winner is at least sqrt(lb2) away (second-best streamed, pruned
+                // cells of the block, the block's border): rounded DOWN at every step
+                const double lb2 = fmin(hi_to_double(lb_hi), border2);
+                slack = fminf(__fsqrt_rd(__double2float_rd(lb2)), 60000.f);
+            } else {
                 defer = i;
                 if (MARK) best = -best;
             }
@@ -315,8 +333,49 @@ __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, b
             if (MARK) sd2[i] = -kInf;
             defer = i | 0x8000;
         }
+        ssl[i] = __float2half_rd(slack);
     }
     return defer;
+}
+
+// Skip test of one round of 32 queries (i = 32e + lane), passes after the first.  `D` = pose of this pass minus the
+// pose of the previous pass.  The query moved by |D.M u + D.c| (+ rounding of the two positions, `1e-14 |q|` is
+// 50x what they can differ by); every point other than last pass's winner is therefore still at least
+// slack - move away (triangle inequality; in 3-D too, Z does not move).  If the winner's distance - evaluated in
+// the canonical arithmetic, it is the value the full search would return - is below that, it is the unique nearest
+// neighbour again: no tie, nothing to search.  All roundings are directed against passing.  Returns the point
+// index if the query must be searched, -1 if it is settled.
+template <bool Z3>
+__device__ __forceinline__ int nn_test_round(const WindowAcc& W, const PlotCtx& pc, const Pose& P, const Pose& D,
+                                             double* __restrict__ sd2, const int* __restrict__ snn,
+                                             __half* __restrict__ ssl, int e, int lane) {
+    const int i = e * 32 + lane;
+    int need = -1;
+    if (i < pc.n) {
+        need = i;
+        const int code = snn[i];
+        const float s0 = __half2float(ssl[i]);
+        if (code >= 0 && s0 > 0.f) {
+            const double2 u = pc.s_u[i];
+            const double ex = D.m00 * u.x + D.m01 * u.y + D.cx;
+            const double ey = D.m10 * u.x + D.m11 * u.y + D.cy;
+            const double pad = 1e-14 * ((fabs(P.cx) + fabs(P.cy)) + (fabs(u.x) + fabs(u.y)));
+            const float move = __fadd_ru(__fsqrt_ru(__double2float_ru(ex * ex + ey * ey)), __double2float_ru(pad));
+            const float s1 = __fmul_rd(__fsub_rd(s0, move), 0.99999904632568359375f);  // (1 - 2^-20): rounding of d2
+            const __half sh = __float2half_rd(fmaxf(s1, 0.f));
+            ssl[i] = sh;
+            const float s = __half2float(sh);
+            double qx, qy;
+            pose_apply(P, u, qx, qy);
+            const double qz = Z3 ? pc.s_z[i] : 0.0;
+            const double d2 = nn_dist2<Z3>(W, code, qx, qy, qz);
+            if (d2 < (double)s * (double)s) {
+                sd2[i] = d2;
+                need = -1;
+            }
+        }
+    }
+    return need;
 }
 
 // Everything a warp needs to work on the plot staged in this CTA, rebuilt from the kernel parameters and the plot's
@@ -348,6 +407,7 @@ __device__ __noinline__ void slot_work(const IcpParams* Pp, const PlotMeta* pmp,
     SlotCtrl* c = reinterpret_cast<SlotCtrl*>(smem + L.ctrl) + s;
     double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)s * npad;
     int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)s * npad;
+    __half* ssl = reinterpret_cast<__half*>(smem + L.ssl) + (size_t)s * npad;
     const unsigned short* sord = reinterpret_cast<const unsigned short*>(smem + L.sord) + (size_t)s * npad;
 #pragma unroll 1
     for (;;) {
@@ -356,7 +416,8 @@ __device__ __noinline__ void slot_work(const IcpParams* Pp, const PlotMeta* pmp,
         __threadfence_block();
         const Pose pose = c->pose;
         if (c->mode == 0) {
-            (void)nn_round<Z3, true>(G, V.W, win_ok != 0, V.pc, pose, sd2, snn, sord, e, lane, c->have_prev != 0);
+            (void)nn_round<Z3, true>(G, V.W, win_ok != 0, V.pc, pose, sd2, snn, ssl, sord, e, c->nlist, lane,
+                                     c->have_prev != 0);
         } else {
             unsigned ng = 0;
             nn_deferred_chunk<Z3, true>(G, V.W, V.pc, pose, sd2, snn, sord, e * 32, c->ndef, lane, ng);
@@ -367,23 +428,44 @@ __device__ __noinline__ void slot_work(const IcpParams* Pp, const PlotMeta* pmp,
     }
 }
 
-// Nearest neighbours of one pass (ficp.py:65-71) for the ICP of slot `ctrl`.  ELASTIC: when enough warps of the CTA
-// have no ICP of their own (`*sh_active <= dyn_leads`: the batch is smaller than the machine, or the plot is running
-// out of hypotheses) the rounds are handed out through the slot's ticket so that those warps take some; trimming
-// and fit stay with the lead warp in unchanged arithmetic, so results do not depend on who computed a round.
+// Nearest neighbours of one pass (ficp.py:65-71) for the ICP of slot `ctrl`: skip test for every query (passes after
+// the first), then the search of the queries that failed it, in rounds of 32 list entries.  ELASTIC: when enough warps
+// of the CTA have no ICP of their own (`*sh_active <= dyn_leads`: the batch is smaller than the machine, or the plot is
+// running out of hypotheses) the search rounds are handed out through the slot's ticket so that those warps take some;
+// skip test, trimming and fit stay with the lead warp in unchanged arithmetic, so results do not depend on who
+// computed a round.
 template <int E, bool Z3, bool ELASTIC>
 __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
-                                             const Pose& P, double* __restrict__ sd2, int* __restrict__ snn,
+                                             const Pose& P, const Pose& D, double* __restrict__ sd2,
+                                             int* __restrict__ snn, __half* __restrict__ ssl,
                                              unsigned short* __restrict__ sord, SlotCtrl* ctrl, const int* sh_active,
                                              const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, int slot,
-                                             int& epoch, int lane, bool have_prev, unsigned& n_global) {
+                                             int& epoch, int lane, bool have_prev, unsigned& n_global,
+                                             unsigned& n_searched) {
     const int n = pc.n;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // ---- search list: every query on the first pass (identity list, written when the ICP starts), afterwards the
+    // queries whose slack does not cover the pose update
+    int n_list = n;
+    if (have_prev) {
+        n_list = 0;
+#pragma unroll 1
+        for (int e = 0; e * 32 < n; ++e) {
+            const int need = nn_test_round<Z3>(W, pc, P, D, sd2, snn, ssl, e, lane);
+            const unsigned m = __ballot_sync(kFull, need >= 0);
+            if (need >= 0) sord[n_list + __popc(m & lt_mask)] = (unsigned short)need;
+            n_list += __popc(m);
+        }
+        __syncwarp();
+    }
+    n_searched += (unsigned)n_list;
+    const int rounds = (n_list + 31) >> 5;
     int n_def = 0;
-    if (ELASTIC && ld_volatile_uniform(sh_active, lane) <= Pp->dyn_leads) {
-        const int rounds = (n + 31) >> 5;
+    if (ELASTIC && rounds > 1 && ld_volatile_uniform(sh_active, lane) <= Pp->dyn_leads) {
         if (lane == 0) {
             ctrl->pose = P;
             ctrl->have_prev = have_prev ? 1 : 0;
+            ctrl->nlist = n_list;
         }
         open_epoch(ctrl, epoch, 0, rounds, lane);
         slot_work<Z3>(Pp, pmp, smem, 32 * E, win_ok ? 1 : 0, slot, lane);
@@ -393,13 +475,13 @@ __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc&
         for (int e = 0; e < rounds; ++e) {
             const int p = e * 32 + lane;
             int defer = -1;
-            if (p < n) {
+            if (p < n_list) {
                 const int i = sord[p];
                 const long long b = __double_as_longlong(sd2[i]);
                 if (b < 0) defer = i | ((b == __double_as_longlong(-kInf)) ? 0x8000 : 0);
             }
             const unsigned m = __ballot_sync(kFull, defer >= 0);
-            if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
+            if (defer >= 0) sord[n_def + __popc(m & lt_mask)] = (unsigned short)defer;
             n_def += __popc(m);
         }
         __syncwarp();
@@ -413,13 +495,13 @@ __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc&
             n_def = 0;
         }
     } else {
-        // in-order rounds: the deferred list reuses the already-consumed slots of `sord`
+        // in-order rounds: the deferred list reuses the already-consumed entries of `sord`
 #pragma unroll 1
-        for (int e = 0; e < E; ++e) {
-            const int defer = nn_round<Z3, false>(G, W, win_ok, pc, P, sd2, snn, sord, e, lane, have_prev);
+        for (int e = 0; e < rounds; ++e) {
+            const int defer = nn_round<Z3, false>(G, W, win_ok, pc, P, sd2, snn, ssl, sord, e, n_list, lane, have_prev);
             const unsigned m = __ballot_sync(kFull, defer >= 0);
             FICP_ASSERT(n_def + __popc(m) <= e * 32 + 32);
-            if (defer >= 0) sord[n_def + __popc(m & ((1u << lane) - 1u))] = (unsigned short)defer;
+            if (defer >= 0) sord[n_def + __popc(m & lt_mask)] = (unsigned short)defer;
             n_def += __popc(m);
         }
     }
@@ -463,7 +545,7 @@ __device__ __forceinline__ void icp_help(const IcpParams* Pp, const PlotMeta* pm
 template <int E>
 __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const double* __restrict__ s_g,
                                                   const double* __restrict__ g_c, const double* __restrict__ sd2,
-                                                  unsigned short* __restrict__ sord, int lane, unsigned& n_fix) {
+                                                  int lane, unsigned& n_fix) {
     using C = LaneCfg<E>;
     const int n = pc.n;
 
@@ -522,10 +604,6 @@ __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const doubl
         if (!__any_sync(kFull, sw)) break;
         ++n_fix;
     }
-
-    // publish the trim order (positions 0..n-1 hold exactly the n real points) for the next pass's rounds
-#pragma unroll
-    for (int r = 0; r < E; ++r) sord[lane * E + r] = (unsigned short)(key[r] & C::kIdxMask);
 
     // ---- inclusive prefix sums S_k of d2 in trim order (in place: dd[r] becomes S at position lane*E + r) ----
     double run = 0.0;
@@ -620,7 +698,7 @@ __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const doubl
 
 // Closed-form rigid fit on the trimmed subset and composition into the pose.
 template <int E, bool Z3>
-__device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, const PlotCtx& pc, Pose& P,
+__device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, const PlotCtx& pc, Pose& P, Pose& D,
                                         const PassOut& po, const double* __restrict__ sd2,
                                         const int* __restrict__ snn, int lane, int allow_reflection) {
     const int n = pc.n;
@@ -680,6 +758,9 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
     Q.m10 = r10 * P.m00 + r11 * P.m10; Q.m11 = r10 * P.m01 + r11 * P.m11;
     Q.cx = (r00 * ex + r01 * ey) + (ax + mv0);
     Q.cy = (r10 * ex + r11 * ey) + (ay + mv1);
+    // pose update of this fit, for the next pass's skip test
+    D.m00 = Q.m00 - P.m00; D.m01 = Q.m01 - P.m01; D.m10 = Q.m10 - P.m10; D.m11 = Q.m11 - P.m11;
+    D.cx = Q.cx - P.cx; D.cy = Q.cy - P.cy;
     P = Q;
 }
 
@@ -703,6 +784,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
     double* sd2 = reinterpret_cast<double*>(smem + L.sd2) + (size_t)slot * NPAD;
     int* snn = reinterpret_cast<int*>(smem + L.snn) + (size_t)slot * NPAD;
     unsigned short* sord = reinterpret_cast<unsigned short*>(smem + L.sord) + (size_t)slot * NPAD;
+    __half* ssl = reinterpret_cast<__half*>(smem + L.ssl) + (size_t)slot * NPAD;
     SlotCtrl* ctrl = reinterpret_cast<SlotCtrl*>(smem + L.ctrl) + slot;
     unsigned* w_cell = reinterpret_cast<unsigned*>(smem + L.w_cell);
     int* rowoff = reinterpret_cast<int*>(smem + L.rowoff);
@@ -717,7 +799,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
     if (ELASTIC && is_lead && lane == 0) { ctrl->ticket = kTicketClosed; ctrl->count = 0; }
     int epoch = 0;
     int staged_plot = -1;
-    unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0;
+    unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0;
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous slice (and with sh_slice)
@@ -808,8 +890,9 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
             const int h = P.hyp_begin + j * P.hyp_stride;
             const double* hr = P.hyp + (size_t)h * 6;
             Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
-            unsigned n_global = 0, n_fix = 0;
+            unsigned n_global = 0, n_fix = 0, n_searched = 0;
             int passes = 0;
+            Pose dpose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pose of the coming pass minus pose of the previous pass
             if (ELASTIC && lane == 0) ctrl->nglob = 0;
             // first pass: identity order; padding slots never change
             for (int i = lane; i < NPAD; i += 32) {
@@ -827,9 +910,10 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                 int it = 0;
                 bool first = true;
                 for (;;) {
-                    icp_nn_phase<E, Z3, ELASTIC>(G, W, win_ok, pc, pose, sd2, snn, sord, ctrl, &sh_active, &P, P.plots + plot,
-                                                 smem, slot, epoch, lane, passes > 0, n_global);
-                    po = icp_trim_phase<E>(pc, sg, gc, sd2, sord, lane, n_fix);
+                    icp_nn_phase<E, Z3, ELASTIC>(G, W, win_ok, pc, pose, dpose, sd2, snn, ssl, sord, ctrl, &sh_active, &P,
+                                                 P.plots + plot, smem, slot, epoch, lane, passes > 0, n_global, n_searched);
+                    dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
+                    po = icp_trim_phase<E>(pc, sg, gc, sd2, lane, n_fix);
                     ++passes;
                     if (first) {
                         if (po.k == 0) break;  // ficp.py:125-126
@@ -841,7 +925,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                         ++it;
                     }
                     if (it >= P.max_iter) break;
-                    icp_fit<E, Z3>(G, W, pc, pose, po, sd2, snn, lane, P.allow_reflection);
+                    icp_fit<E, Z3>(G, W, pc, pose, dpose, po, sd2, snn, lane, P.allow_reflection);
                     __syncwarp();
                 }
                 __syncwarp();
@@ -870,7 +954,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                     P.final_xy[(pm.off + i) * 2 + 1] = qy;
                 }
             }
-            acc_passes += passes; acc_global += n_global; acc_fix += n_fix;
+            acc_passes += passes; acc_global += n_global; acc_fix += n_fix; acc_searched += n_searched;
             acc_queries += (unsigned long long)passes * pm.n;
             __syncwarp();
         }
@@ -888,6 +972,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
         atomicAdd(P.stats + 1, acc_global);
         atomicAdd(P.stats + 3, acc_fix);
         atomicAdd(P.stats + 4, acc_queries);
+        atomicAdd(P.stats + 5, acc_searched);
     }
 }
 

@@ -22,6 +22,29 @@ namespace ficp {
 #define FICP_LDG(p) (*(p))
 #endif
 
+// Upper 32 bits of a non-negative double: a monotone integer code of the value, truncated TOWARDS ZERO (20 mantissa
+// bits survive).  Free on the device (it is one register of the pair); used for the running lower bounds below.
+constexpr int kHiInf = 0x7FF00000;  // code of +inf
+FICP_HD int d_hi(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(d);
+#else
+    long long v;
+    __builtin_memcpy(&v, &d, sizeof v);
+    return (int)(v >> 32);
+#endif
+}
+FICP_HD double hi_to_double(int hi) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, 0);
+#else
+    const long long v = (long long)(unsigned)hi << 32;
+    double d;
+    __builtin_memcpy(&d, &v, sizeof d);
+    return d;
+#endif
+}
+
 // One 32 B record = one L2 sector = ONE load request: sm_100 has 256-bit global loads (SASS LDG.E.ENL2.256).
 FICP_HD void grid_load_rec(const double4* rec, int j, double& x, double& y, double& z, double& w) {
 #if defined(__CUDA_ARCH__)
@@ -176,6 +199,18 @@ FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpo
         best = d2;
         bestpos = j;
     }
+}
+
+// Same fold, additionally keeping `sec` = code (d_hi, rounded down) of the smallest squared distance among the
+// candidates OTHER than the running winner - a lower bound on the distance to the second-nearest candidate seen.
+// Re-meeting the winner (the seed comes by again in the stream) does not count; an exact tie with a different
+// point does (sec == best: no slack).
+template <class Acc>
+FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& bestpos, int& sec) {
+    const bool lt = d2 < best;
+    const int c = lt ? d_hi(best) : ((j == bestpos) ? kHiInf : d_hi(d2));
+    sec = (c < sec) ? c : sec;
+    nn_fold(acc, j, d2, best, bestpos);
 }
 
 // ---- one candidate ---------------------------------------------------------------------------------
@@ -334,9 +369,14 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
 //   3. one loop over the concatenation of the three ranges;
 //   4. if the border of the block is not provably farther than the best distance, the ring loop goes on
 //      from radius 2 (rare).
-template <bool Z3, class Acc>
-FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
-                              double& best, int& bestpos, int& cx, int& cy) {
+// TRACK: also return `lb_hi` = code (d_hi, rounded down) of a lower bound on the squared distance from the query to
+// every target point of the 3x3 block OTHER than the winner: the second-best candidate streamed, and the (inflated)
+// boxes of the block's cells that were pruned.  Together with the distance to the block's border (see
+// nn_block_border2) it bounds every other point of the target - what the ICP kernel needs to prove, on later passes,
+// that a query that moved by less than the slack still has the same nearest neighbour.
+template <bool Z3, bool TRACK, class Acc>
+FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
+                                   double& best, int& bestpos, int& cx, int& cy, int& lb_hi) {
     cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
     cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
     const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
@@ -344,6 +384,7 @@ FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, doub
     if (!acc.covers(xl, xh, yl, yh)) return false;
     best = kInf;
     bestpos = -1;
+    int lb = kHiInf;
     if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
     // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
     // query from the lower-left corner of its (clamped) cell; it lies in [0, h] unless the query is off the grid.
@@ -370,9 +411,15 @@ FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, doub
 #pragma unroll
         for (int rx = 0; rx < 3; ++rx) {
             const int x = cx - 1 + rx;
-            if (x >= xl && x <= xh && gx[rx] + gy[ry] <= best) {
-                if (x < xa) xa = x;
-                xb = x;
+            if (x >= xl && x <= xh) {
+                const double gap2 = gx[rx] + gy[ry];
+                if (gap2 <= best) {
+                    if (x < xa) xa = x;
+                    xb = x;
+                } else if (TRACK) {
+                    const int c = d_hi(gap2);
+                    lb = (c < lb) ? c : lb;
+                }
             }
         }
         if (xa <= xb) {
@@ -391,10 +438,22 @@ FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, doub
         const int j1 = t1 + ((t1 < n[0]) ? s[0] : (t1 < n01) ? o1 : o2);
         const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
         const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
-        nn_fold(acc, j0, da, best, bestpos);
-        nn_fold(acc, j1, db, best, bestpos);
+        if (TRACK) {
+            nn_fold_track(acc, j0, da, best, bestpos, lb);
+            nn_fold_track(acc, j1, db, best, bestpos, lb);
+        } else {
+            nn_fold(acc, j0, da, best, bestpos);
+            nn_fold(acc, j1, db, best, bestpos);
+        }
     }
+    lb_hi = lb;
     return true;
+}
+template <bool Z3, class Acc>
+FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
+                              double& best, int& bestpos, int& cx, int& cy) {
+    int lb_hi;
+    return nn_search_block3_impl<Z3, false>(acc, g, qx, qy, qz, prev, best, bestpos, cx, cy, lb_hi);
 }
 
 // True when the visited block of Chebyshev radius `rad` around (cx, cy) provably bounds the search (cheap form of
@@ -409,6 +468,20 @@ FICP_HD bool nn_block_settles(const GridGeom& g, double qx, double qy, int cx, i
     if (b == kInf) return true;
     b -= g.eps;
     return b > 0.0 && best < b * b;
+}
+
+// The same bound as a number: squared distance below which the visited block provably holds the nearest neighbour
+// (+inf: the block spans the whole grid; 0: nothing can be said).  nn_block_settles(best) == (best < border2).
+FICP_HD double nn_block_border2(const GridGeom& g, double qx, double qy, int cx, int cy, int rad) {
+    const int xl = cx - rad, xh = cx + rad, yl = cy - rad, yh = cy + rad;
+    double b = kInf;
+    if (xl > 0) b = fmin(b, qx - (g.x0 + xl * g.h));
+    if (xh < g.gw - 1) b = fmin(b, (g.x0 + (xh + 1) * g.h) - qx);
+    if (yl > 0) b = fmin(b, qy - (g.y0 + yl * g.h));
+    if (yh < g.gh - 1) b = fmin(b, (g.y0 + (yh + 1) * g.h) - qy);
+    if (b == kInf) return kInf;
+    b -= g.eps;
+    return (b > 0.0) ? b * b : 0.0;
 }
 
 template <bool Z3, class Acc>

@@ -158,7 +158,8 @@ FICP_API int ficp_batch_run(ficp_batch* b, void* stream);  /* enqueue only */
 /* waits for `stream`, then copies out whatever is non-NULL: results [n_plots*n_hyp_local], best_keys
  * [n_plots] ((fp32 score bits << 32) | hypothesis id, min = best), final_xy [rows*2] (only when created
  * with want_final_xy and n_hyp_local == 1), stats [8]: passes, global-path queries, windows disabled,
- * fix-up rounds, queries. */
+ * fix-up rounds, queries, queries that needed a search (the others passed the skip test: their previous
+ * neighbour was proved to still be the nearest). */
 FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_t* best_keys, double* final_xy,
                        uint64_t* stats, void* stream);
 /* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then
