@@ -390,6 +390,8 @@ def run_b200(args):
         lib = _lib.load()
         import ctypes as C
         sp = C.c_void_p(stream.cuda_stream)
+        icp_index = index
+        index = TargetIndex(tgt, pts_per_cell=(args.pts_per_cell or None), purpose="query")   # bulk-query grid density
         for _ in range(2):
             _lib.check(lib.ficp_nn_query_device(index.handle, C.c_void_p(dq.data_ptr()), nq, args.dims, int(args.dims == 3),
                                                 C.c_void_p(didx.data_ptr()), C.c_void_p(ddist.data_ptr()), sp))
@@ -407,7 +409,10 @@ def run_b200(args):
         extra["nn_query_kernel"] = {"queries": nq, "ms": ms, "queries_per_s": nq / (ms * 1e-3),
                                     "alg_GBps_L2_level": alg, "l2_read_peak_GBps_measured": l2.value,
                                     "frac_of_l2_peak": alg / l2.value if l2.value else None,
-                                    "hbm_compulsory_GBps": nq * 24.0 / (ms * 1e-3) / 1e9}
+                                    "hbm_compulsory_GBps": nq * 24.0 / (ms * 1e-3) / 1e9,
+                                    "cell_m": index.info()["cell"]}
+        index.close()
+        index = icp_index
         extra["grid_build"] = {"points": int(tinfo["m"]), "ms": tinfo["build_ms"],
                                "alg_GBps": tinfo["m"] * GRID_BYTES_PER_POINT / (tinfo["build_ms"] * 1e-3) / 1e9,
                                "grid": [tinfo["grid_w"], tinfo["grid_h"]], "cell_m": tinfo["cell"]}

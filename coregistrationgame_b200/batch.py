@@ -71,7 +71,12 @@ class TargetIndex:
     """Device-resident uniform-grid index over the Layer-2 (CHM) points; built once, reused by
     every pass of every hypothesis (the reference rebuilds its kd-tree on every pass, ficp.py:69)."""
 
-    def __init__(self, target, use_z=None, pts_per_cell=None, stream=None):
+    # points per grid cell, measured on B200 (profiles/r01_summary.md).  The ICP kernel wants cells wide enough that the
+    # 3x3 block around a query settles its search even for poor start poses (3-D residuals of 6-8 m) and gives its
+    # skip test a long leash; bulk one-shot queries (no previous neighbour to bound the search) want small cells.
+    PTS_PER_CELL = {("icp", True): 6.0, ("icp", False): 4.0, ("query", True): 3.0, ("query", False): 2.0}
+
+    def __init__(self, target, use_z=None, pts_per_cell=None, stream=None, purpose="icp"):
         lib = _lib.load()
         arr = np.ascontiguousarray(np.asarray(target, dtype=np.float64))
         if arr.ndim != 2 or arr.shape[1] < 2:
@@ -79,9 +84,7 @@ class TargetIndex:
         self.m, self.ld = int(arr.shape[0]), int(arr.shape[1])
         self.has_z = bool(arr.shape[1] >= 3) if use_z is None else bool(use_z)
         if pts_per_cell is None:
-            # measured on B200 (profiles/): ~3 points per cell when matching in XYZ (larger search radii),
-            # ~2 when matching in XY
-            pts_per_cell = 3.0 if self.has_z else 2.0
+            pts_per_cell = self.PTS_PER_CELL[(purpose, self.has_z)]
         self._h = C.c_void_p()
         _lib.require_device()
         _lib.check(lib.ficp_target_create(_lib.ptr(arr), self.m, self.ld, int(self.has_z), float(pts_per_cell),
@@ -217,7 +220,7 @@ class IcpBatch:
                "hyp_ids": self.hyp_begin + self.hyp_stride * np.arange(self.n_hyp_local),
                "stats": {"passes": int(stats[0]), "global_path_queries": int(stats[1]),
                          "windows_disabled": int(stats[2]), "fixup_rounds": int(stats[3]), "queries": int(stats[4]),
-                         "searched_queries": int(stats[5])}}
+                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6])}}
         out.update(decode_best_keys(keys))
         self.d2h_bytes = int(keys.nbytes + stats.nbytes + (res.nbytes if res is not None else 0)
                              + (final.nbytes if final is not None else 0))

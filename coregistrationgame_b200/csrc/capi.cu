@@ -437,7 +437,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     }
     // window of grid cells a plot can reach with `margin` of slack: cell rectangle + estimated point count
     const double mean_cell_pts = (double)t->m / ((double)g.gw * g.gh);
-    const double margin0 = prm->window_margin >= 0.0 ? prm->window_margin : (3.0 * g.h + 5.0);
+    const double margin0 = prm->window_margin >= 0.0 ? prm->window_margin : std::min(3.0 * g.h + 5.0, g.h + 20.0);
     auto window_of = [&](const Foot& f, double margin, int* rect, long long* cells, double* est) -> bool {
         const double r = f.rho + margin;
         const double bx0 = f.fx0 - r, bx1 = f.fx1 + r, by0 = f.fy0 - r, by1 = f.fy1 + r;
@@ -477,46 +477,56 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     int slots_per_cta = std::max(1, std::min(warps / team, n_hyp_local));
     const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
     const int wcap_rows = 256;
-    // per-ICP state (distances, neighbours, search list, slack: 16 B per tree) must leave room for a window
+    // per-ICP state (distances, neighbours, search list, trim order, slack: 18 B per tree) must leave room for a window
     while (slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
     warps = slots_per_cta * team;
     const size_t fixed_bytes = icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows);
-    const size_t per_pt = 16 + (z3 ? 8 : 0) + 4;
-    auto cap_for = [&](int ctas) -> int {
+    const size_t per_pt = 16 + (z3 ? 8 : 0), per_cell = 4;
+    // bytes left for the window (point records + cell table) with `ctas` CTAs resident per SM
+    auto window_bytes = [&](int ctas) -> size_t {
         const size_t budget = std::min<size_t>((size_t)smem_optin, sm_total / ctas - 1024);
         if (prm->disable_window || budget <= fixed_bytes + 4096) return 0;
-        return (int)std::min<size_t>(65535, (budget - fixed_bytes - 256) / per_pt);
+        return budget - fixed_bytes - 256;
     };
-    // points a window needs with a modest margin (one ring of cells + a few metres of drift), worst plot
-    double need_modest = 0;
-    for (int64_t p = 0; p < n_plots; ++p) {
-        int rect[4]; long long cells; double est;
-        if (window_of(foot[(size_t)p], std::min(margin0, 1.5 * g.h + 3.0), rect, &cells, &est)) need_modest = std::max(need_modest, std::max(est, (double)cells));
-    }
+    auto fits = [&](double est, long long cells, size_t bytes) -> bool {
+        return est <= 65535.0 && (size_t)std::ceil(est) * per_pt + (size_t)cells * per_cell + 64 <= bytes;
+    };
+    // a window with a modest margin (one ring of cells + a few metres of drift) must fit for the worst plot
     int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));
-    if (prm->ctas_per_sm <= 0)  // fewer resident CTAs when that is what it takes for the windows to fit on-chip
-        while (want_ctas_per_sm > 1 && cap_for(want_ctas_per_sm) < need_modest) --want_ctas_per_sm;
-    int wcap_pts = cap_for(want_ctas_per_sm);
+    if (prm->ctas_per_sm <= 0) {  // fewer resident CTAs when that is what it takes for the windows to fit on-chip
+        auto modest_fits = [&](int ctas) -> bool {
+            const size_t bytes = window_bytes(ctas);
+            for (int64_t p = 0; p < n_plots; ++p) {
+                int rect[4]; long long cells; double est;
+                if (window_of(foot[(size_t)p], std::min(margin0, 1.5 * g.h + 3.0), rect, &cells, &est) && !fits(est, cells, bytes)) return false;
+            }
+            return true;
+        };
+        while (want_ctas_per_sm > 1 && !modest_fits(want_ctas_per_sm)) --want_ctas_per_sm;
+    }
+    const size_t wbytes = window_bytes(want_ctas_per_sm);
 
     // ---- window rectangles: the largest margin (up to margin0) that fits the capacity
-    int need_pts = 0;
-    for (int64_t p = 0; p < n_plots && wcap_pts > 0; ++p) {
+    int wcap_pts = 0;
+    long long need_cells = 0;
+    for (int64_t p = 0; p < n_plots && wbytes > 0; ++p) {
         PlotMeta& pm = plots[(size_t)p];
         double margin = margin0;
         for (int attempt = 0; attempt < 12; ++attempt, margin *= 0.7) {
             int rect[4]; long long cells; double est;
             if (!window_of(foot[(size_t)p], margin, rect, &cells, &est)) break;
-            if (cells <= wcap_pts && (rect[3] - rect[2]) <= wcap_rows && est <= wcap_pts) {
+            // the largest window of any plot sets the reservation: a plot must fit next to the others' maxima
+            const double est_all = std::max(est, (double)wcap_pts);
+            const long long cells_all = std::max(cells, need_cells);
+            if ((rect[3] - rect[2]) <= wcap_rows && fits(est_all, cells_all, wbytes)) {
                 pm.wx0 = rect[0]; pm.wx1 = rect[1]; pm.wy0 = rect[2]; pm.wy1 = rect[3];
-                need_pts = std::max(need_pts, (int)std::min<double>(65535.0, est));
-                need_pts = std::max<long long>(need_pts, cells);
+                wcap_pts = (int)std::ceil(est_all);
+                need_cells = cells_all;
                 break;
             }
         }
     }
-    // do not reserve more on-chip window than any plot can use
-    wcap_pts = std::min(wcap_pts, need_pts);
-    const int wcap_cells = wcap_pts;
+    const int wcap_cells = (int)need_cells;
     const size_t smem = icp_smem_bytes(e, z3, slots_per_cta, wcap_pts, wcap_cells, wcap_rows);
     if (smem > (size_t)smem_optin) { set_error("ficp_batch_create: shared-memory plan exceeds the device limit"); return kErrTooLarge; }
     int occ = 0;

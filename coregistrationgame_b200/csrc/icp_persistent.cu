@@ -441,7 +441,7 @@ __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc&
                                              unsigned short* __restrict__ sord, SlotCtrl* ctrl, const int* sh_active,
                                              const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, int slot,
                                              int& epoch, int lane, bool have_prev, unsigned& n_global,
-                                             unsigned& n_searched) {
+                                             unsigned& n_searched, unsigned& n_deferred) {
     const int n = pc.n;
     const unsigned lt_mask = (1u << lane) - 1u;
     // ---- search list: every query on the first pass (identity list, written when the ICP starts), afterwards the
@@ -489,6 +489,7 @@ __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc&
             // the deferred list is handed out as well, in chunks of 32
             const int chunks = (n_def + 31) >> 5;
             if (lane == 0) ctrl->ndef = n_def;
+            n_deferred += (unsigned)n_def;
             open_epoch(ctrl, epoch, 1, chunks, lane);
             slot_work<Z3>(Pp, pmp, smem, 32 * E, win_ok ? 1 : 0, slot, lane);
             close_epoch(ctrl, epoch, chunks, lane);
@@ -506,6 +507,7 @@ __device__ __forceinline__ void icp_nn_phase(const GridView& G, const WindowAcc&
         }
     }
     __syncwarp();
+    n_deferred += (unsigned)n_def;
 #pragma unroll 1
     for (int base = 0; base < n_def; base += 32)
         nn_deferred_chunk<Z3, ELASTIC>(G, W, pc, P, sd2, snn, sord, base, n_def, lane, n_global);
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
     if (ELASTIC && is_lead && lane == 0) { ctrl->ticket = kTicketClosed; ctrl->count = 0; }
     int epoch = 0;
     int staged_plot = -1;
-    unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0;
+    unsigned long long acc_passes = 0, acc_global = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0, acc_deferred = 0;
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous slice (and with sh_slice)
@@ -890,7 +892,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
             const int h = P.hyp_begin + j * P.hyp_stride;
             const double* hr = P.hyp + (size_t)h * 6;
             Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
-            unsigned n_global = 0, n_fix = 0, n_searched = 0;
+            unsigned n_global = 0, n_fix = 0, n_searched = 0, n_deferred = 0;
             int passes = 0;
             Pose dpose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pose of the coming pass minus pose of the previous pass
             if (ELASTIC && lane == 0) ctrl->nglob = 0;
@@ -911,7 +913,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                 bool first = true;
                 for (;;) {
                     icp_nn_phase<E, Z3, ELASTIC>(G, W, win_ok, pc, pose, dpose, sd2, snn, ssl, sord, ctrl, &sh_active, &P,
-                                                 P.plots + plot, smem, slot, epoch, lane, passes > 0, n_global, n_searched);
+                                                 P.plots + plot, smem, slot, epoch, lane, passes > 0, n_global, n_searched, n_deferred);
                     dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
                     po = icp_trim_phase<E>(pc, sg, gc, sd2, lane, n_fix);
                     ++passes;
@@ -954,7 +956,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                     P.final_xy[(pm.off + i) * 2 + 1] = qy;
                 }
             }
-            acc_passes += passes; acc_global += n_global; acc_fix += n_fix; acc_searched += n_searched;
+            acc_passes += passes; acc_global += n_global; acc_fix += n_fix; acc_searched += n_searched; acc_deferred += n_deferred;
             acc_queries += (unsigned long long)passes * pm.n;
             __syncwarp();
         }
@@ -973,6 +975,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
         atomicAdd(P.stats + 3, acc_fix);
         atomicAdd(P.stats + 4, acc_queries);
         atomicAdd(P.stats + 5, acc_searched);
+        atomicAdd(P.stats + 6, acc_deferred);
     }
 }
 

@@ -399,6 +399,12 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
     gy[2] = fmax(h - uy - eps, 0.0);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+    // TRACK: cells a little beyond the seed's distance are streamed as well - every cell pruned caps the lower bound
+    // (and with it how long the query can skip its searches) at the cell's gap, which would be barely above `best`
+#ifndef FICP_PRUNE_PAD
+#define FICP_PRUNE_PAD 1.5
+#endif
+    const double bound = TRACK ? best * FICP_PRUNE_PAD : best;
     int s[3], n[3];
 #pragma unroll
     for (int ry = 0; ry < 3; ++ry) {
@@ -413,7 +419,7 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
             const int x = cx - 1 + rx;
             if (x >= xl && x <= xh) {
                 const double gap2 = gx[rx] + gy[ry];
-                if (gap2 <= best) {
+                if (gap2 <= bound) {
                     if (x < xa) xa = x;
                     xb = x;
                 } else if (TRACK) {

@@ -62,7 +62,7 @@ def remove_matches_batch(plots, chm, min_dist_percent=15, index=None, stream=Non
             trees = np.ascontiguousarray(trees[:, :2])
         own = index is None
         if own:
-            index = TargetIndex(chm[:, :3] if use_3d else chm[:, :2], use_z=use_3d)
+            index = TargetIndex(chm[:, :3] if use_3d else chm[:, :2], use_z=use_3d, purpose="query")
         try:
             _lib.check(_lib.load().ficp_match_remove(index.handle, _lib.ptr(trees), _lib.ptr(offsets), len(plots),
                                                      trees.shape[1], int(use_3d), _lib.ptr(thr), _lib.ptr(matched),
@@ -94,7 +94,7 @@ def radial_crop(index_or_points, x, y, dist, stream=None):
     ``CHMPlot`` / ``SavedPlot`` (chm_plot.py:144-148, :306-311: ``cdist(coordinates, [[x, y]]) <= dist``).
     Accepts a built ``TargetIndex`` (cell-range query, O(points near the disc)) or an (M, >=2) array."""
     own = not isinstance(index_or_points, TargetIndex)
-    index = TargetIndex(np.asarray(index_or_points, dtype=np.float64)[:, :2], use_z=False) if own else index_or_points
+    index = TargetIndex(np.asarray(index_or_points, dtype=np.float64)[:, :2], use_z=False, purpose="query") if own else index_or_points
     try:
         mask = np.zeros(index.m, dtype=np.uint8)
         if index.m:
