@@ -489,7 +489,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         return budget - fixed_bytes - 256;
     };
     auto fits = [&](double est, long long cells, size_t bytes) -> bool {
-        return est <= 65535.0 && (size_t)std::ceil(est) * per_pt + (size_t)cells * per_cell + 64 <= bytes;
+        return est <= 32767.0 && (size_t)std::ceil(est) * per_pt + (size_t)cells * per_cell + 64 <= bytes;
     };
     // a window with a modest margin (one ring of cells + a few metres of drift) must fit for the worst plot
     int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));

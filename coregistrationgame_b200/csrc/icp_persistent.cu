@@ -193,6 +193,14 @@ FICP_GLOBAL_ATTR int nn_query_global(const GridView& G, double qx, double qy, do
     return pos;
 }
 
+// Neighbour code of a query (`snn`): -1 = none; bit 31 set = position in the GLOBAL cell-sorted target (the query ran
+// on the global grid); otherwise two window-local positions (< 32768): bits 0-15 the nearest neighbour, bits 16-30 the
+// runner-up of its last search (== the neighbour: none).
+__device__ __forceinline__ int code_pack(int pos, int pos2) {
+    return (pos < 0) ? -1 : (pos | (((pos2 < 0) ? pos : pos2) << 16));
+}
+__device__ __forceinline__ int code_win(int code) { return (code < 0) ? -1 : (code & 0xFFFF); }
+
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // A warp-uniform view of a shared word that other warps change: ONE lane reads, everybody gets that value.  (Every lane
@@ -266,16 +274,16 @@ __device__ __forceinline__ void nn_deferred_chunk(const GridView& G, const Windo
         bool ok = false;
         if (!(d & 0x8000)) {
             best = ELASTIC ? fabs(sd2[i]) : sd2[i];
-            pos = snn[i];
+            pos = code_win(snn[i]);
             const int cx = clamp_cell((qx - G.g.x0) * G.g.inv_h, G.g.gw);
             const int cy = clamp_cell((qy - G.g.y0) * G.g.inv_h, G.g.gh);
             ok = nn_ring_loop_impl<Z3>(W, G.g, qx, qy, qz, cx, cy, 2, best, pos);
         }
-        int code = pos;
+        int code = code_pack(pos, -1);
         if (!ok) {
             // window miss: whole query on the global grid, seeded with the best candidate known so far
             const int seed = snn[i];
-            const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed) : (seed & 0x7FFFFFFF));
+            const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed & 0xFFFF) : (seed & 0x7FFFFFFF));
             pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
             code = (int)((unsigned)pos | 0x80000000u);
             ++n_global;
@@ -307,20 +315,19 @@ __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, b
         pose_apply(P, pc.s_u[i], qx, qy);
         const double qz = Z3 ? pc.s_z[i] : 0.0;
         // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
-        const int pc_prev = have_prev ? snn[i] : -1;
+        const int pc_prev = have_prev ? code_win(snn[i]) : -1;
         double best = kInf;
         int pos = -1, cx, cy;
         bool ok = false;
-        int lb_hi = kHiInf;
-        if (win_ok)
-            ok = nn_search_block3_impl<Z3, true>(W, G.g, qx, qy, qz, (pc_prev >= 0) ? pc_prev : -1, best, pos, cx, cy, lb_hi);
+        int lb_hi = kHiInf, pos2 = -1;
+        if (win_ok) ok = nn_search_block3_impl<Z3, true>(W, G.g, qx, qy, qz, pc_prev, best, pos, cx, cy, lb_hi, pos2);
         float slack = 0.f;  // deferred / global-grid queries carry no bound: they are searched again next pass
         if (ok) {
-            snn[i] = pos;
+            snn[i] = code_pack(pos, pos2);
             const double border2 = nn_block_border2(G.g, qx, qy, cx, cy, 1);
             if ((border2 == kInf) || best < border2) {   // == nn_block_settles
-                // every target point other than the winner is at least sqrt(lb2) away (second-best streamed, pruned
-                // cells of the block, the block's border): rounded DOWN at every step
+                // every target point other than the winner and the runner-up is at least sqrt(lb2) away (third-best
+                // streamed, pruned cells of the block, the block's border): rounded DOWN at every step
                 const double lb2 = fmin(hi_to_double(lb_hi), border2);
                 slack = fminf(__fsqrt_rd(__double2float_rd(lb2)), 60000.f);
             } else {
@@ -340,14 +347,14 @@ __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, b
 
 // Skip test of one round of 32 queries (i = 32e + lane), passes after the first.  `D` = pose of this pass minus the
 // pose of the previous pass.  The query moved by |D.M u + D.c| (+ rounding of the two positions, `1e-14 |q|` is
-// 50x what they can differ by); every point other than last pass's winner is therefore still at least
-// slack - move away (triangle inequality; in 3-D too, Z does not move).  If the winner's distance - evaluated in
-// the canonical arithmetic, it is the value the full search would return - is below that, it is the unique nearest
-// neighbour again: no tie, nothing to search.  All roundings are directed against passing.  Returns the point
+// 50x what they can differ by); every point other than the winner and the runner-up of the query's last search is
+// therefore still at least slack - move away (triangle inequality; in 3-D too, Z does not move).  If the smaller of
+// their two distances - evaluated in the canonical arithmetic, it is the value the full search would return - is
+// below that, that point is the unique nearest neighbour: no tie, nothing to search.  All roundings are directed against passing.  Returns the point
 // index if the query must be searched, -1 if it is settled.
 template <bool Z3>
 __device__ __forceinline__ int nn_test_round(const WindowAcc& W, const PlotCtx& pc, const Pose& P, const Pose& D,
-                                             double* __restrict__ sd2, const int* __restrict__ snn,
+                                             double* __restrict__ sd2, int* __restrict__ snn,
                                              __half* __restrict__ ssl, int e, int lane) {
     const int i = e * 32 + lane;
     int need = -1;
@@ -368,9 +375,15 @@ __device__ __forceinline__ int nn_test_round(const WindowAcc& W, const PlotCtx& 
             double qx, qy;
             pose_apply(P, u, qx, qy);
             const double qz = Z3 ? pc.s_z[i] : 0.0;
-            const double d2 = nn_dist2<Z3>(W, code, qx, qy, qz);
-            if (d2 < (double)s * (double)s) {
-                sd2[i] = d2;
+            const int p1 = code & 0xFFFF, p2 = code >> 16;
+            const double d1 = nn_dist2<Z3>(W, p1, qx, qy, qz);
+            const double dr = nn_dist2<Z3>(W, p2, qx, qy, qz);   // p2 == p1 when there is no runner-up
+            const bool swap = dr < d1;
+            const double dmin = swap ? dr : d1;
+            // an exact tie between the two is left to the search (lowest original index wins there)
+            if (dmin < (double)s * (double)s && (p2 == p1 || d1 != dr)) {
+                sd2[i] = dmin;
+                if (swap) snn[i] = p2 | (p1 << 16);
                 need = -1;
             }
         }
@@ -717,8 +730,8 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
                 double qx, qy;
                 pose_apply(P, pc.s_u[i], qx, qy);
                 const int code = snn[i];
-                FICP_ASSERT(code != -1 && ((code < 0) ? ((code & 0x7FFFFFFF) < G.m) : (code < W.rowoff[W.wh])));
-                const double2 t = (code < 0) ? grid_xy(G, code & 0x7FFFFFFF) : W.xy[code];
+                FICP_ASSERT(code != -1 && ((code < 0) ? ((code & 0x7FFFFFFF) < G.m) : ((code & 0xFFFF) < W.rowoff[W.wh])));
+                const double2 t = (code < 0) ? grid_xy(G, code & 0x7FFFFFFF) : W.xy[code & 0xFFFF];
                 const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
                 su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
                 h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
@@ -850,7 +863,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                         o += cnt;
                     }
                     rowoff[wh] = o;
-                    if (o > P.wcap_pts || o > 65535) ok = false;
+                    if (o > P.wcap_pts || o > 32767) ok = false;  // window positions are packed in 15 bits
                 }
                 sh_win_ok = ok ? 1 : 0;
                 if (!ok) atomicAdd(P.stats + 2, 1ull);
@@ -862,7 +875,7 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                     const int r = c / ww, col = c - r * ww;
                     const size_t g = (size_t)(pm.wy0 + r) * G.g.gw + pm.wx0 + col;
                     const unsigned a = G.cell_start[g], b = G.cell_start[g + 1];
-                    FICP_ASSERT(b - a < 65536u && rowoff[r] + (int)(a - (unsigned)rowg[r]) < 65536);
+                    FICP_ASSERT(b - a < 65536u && rowoff[r] + (int)(a - (unsigned)rowg[r]) < 32768);
                     w_cell[c] = (unsigned)(rowoff[r] + (int)(a - (unsigned)rowg[r])) | ((b - a) << 16);
                 }
                 for (int r = warp; r < wh; r += nwarps) {

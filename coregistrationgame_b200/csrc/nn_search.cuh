@@ -201,15 +201,26 @@ FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpo
     }
 }
 
-// Same fold, additionally keeping `sec` = code (d_hi, rounded down) of the smallest squared distance among the
-// candidates OTHER than the running winner - a lower bound on the distance to the second-nearest candidate seen.
-// Re-meeting the winner (the seed comes by again in the stream) does not count; an exact tie with a different
-// point does (sec == best: no slack).
+// Same fold, additionally keeping the RUNNER-UP: `pos2` = the candidate with the smallest squared distance among the
+// candidates other than the running winner (`sec` = its code: d_hi, rounded down), and `third` = code of a lower bound
+// on the squared distance of every candidate streamed that is neither the winner nor the runner-up.  Re-meeting the
+// winner or the runner-up (a seed comes by again in the stream) does not count.  The choice of the runner-up is made
+// on the truncated codes - any choice is valid, `third` bounds whoever was not chosen.
 template <class Acc>
-FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& bestpos, int& sec) {
+FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& bestpos, int& sec, int& pos2, int& third) {
     const bool lt = d2 < best;
-    const int c = lt ? d_hi(best) : ((j == bestpos) ? kHiInf : d_hi(d2));
-    sec = (c < sec) ? c : sec;
+    // an exact tie with a different point is settled by original index inside nn_fold (either may win): no runner-up
+    // bookkeeping for it, the bound simply drops to the tied distance (no slack - such queries are always searched)
+    const bool tie = (d2 == best) && (j != bestpos);
+    const bool skip = (j == bestpos) || (j == pos2) || tie;
+    const int cd = lt ? d_hi(best) : (skip ? kHiInf : d_hi(d2));   // what joins the "others": the old winner, or j
+    const int cp = lt ? bestpos : j;
+    const bool lt2 = cd < sec;
+    int t3 = lt2 ? sec : cd;
+    t3 = tie ? d_hi(d2) : t3;
+    third = (t3 < third) ? t3 : third;
+    pos2 = lt2 ? cp : pos2;
+    sec = lt2 ? cd : sec;
     nn_fold(acc, j, d2, best, bestpos);
 }
 
@@ -369,14 +380,15 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
 //   3. one loop over the concatenation of the three ranges;
 //   4. if the border of the block is not provably farther than the best distance, the ring loop goes on
 //      from radius 2 (rare).
-// TRACK: also return `lb_hi` = code (d_hi, rounded down) of a lower bound on the squared distance from the query to
-// every target point of the 3x3 block OTHER than the winner: the second-best candidate streamed, and the (inflated)
-// boxes of the block's cells that were pruned.  Together with the distance to the block's border (see
-// nn_block_border2) it bounds every other point of the target - what the ICP kernel needs to prove, on later passes,
-// that a query that moved by less than the slack still has the same nearest neighbour.
+// TRACK: also return the runner-up `pos2` (accessor-local position, -1: none) and `lb_hi` = code (d_hi, rounded down)
+// of a lower bound on the squared distance from the query to every target point of the 3x3 block OTHER than the winner
+// and the runner-up: the third-best candidate streamed, and the (inflated) boxes of the block's cells that were
+// pruned.  Together with the distance to the block's border (see nn_block_border2) it bounds every other point of the
+// target - what the ICP kernel needs to prove, on later passes, that a query that moved by less than the slack still
+// has one of these two as its nearest neighbour.
 template <bool Z3, bool TRACK, class Acc>
 FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
-                                   double& best, int& bestpos, int& cx, int& cy, int& lb_hi) {
+                                   double& best, int& bestpos, int& cx, int& cy, int& lb_hi, int& pos2) {
     cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
     cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
     const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
@@ -384,7 +396,8 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
     if (!acc.covers(xl, xh, yl, yh)) return false;
     best = kInf;
     bestpos = -1;
-    int lb = kHiInf;
+    int lb = kHiInf, sec = kHiInf;
+    pos2 = -1;
     if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
     // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
     // query from the lower-left corner of its (clamped) cell; it lies in [0, h] unless the query is off the grid.
@@ -445,21 +458,22 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
         const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
         const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
         if (TRACK) {
-            nn_fold_track(acc, j0, da, best, bestpos, lb);
-            nn_fold_track(acc, j1, db, best, bestpos, lb);
+            nn_fold_track(acc, j0, da, best, bestpos, sec, pos2, lb);
+            nn_fold_track(acc, j1, db, best, bestpos, sec, pos2, lb);
         } else {
             nn_fold(acc, j0, da, best, bestpos);
             nn_fold(acc, j1, db, best, bestpos);
         }
     }
+    if (TRACK && pos2 == bestpos) pos2 = -1;   // a re-met runner-up won an exact tie: the bound is already down at `best`
     lb_hi = lb;
     return true;
 }
 template <bool Z3, class Acc>
 FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
                               double& best, int& bestpos, int& cx, int& cy) {
-    int lb_hi;
-    return nn_search_block3_impl<Z3, false>(acc, g, qx, qy, qz, prev, best, bestpos, cx, cy, lb_hi);
+    int lb_hi, pos2;
+    return nn_search_block3_impl<Z3, false>(acc, g, qx, qy, qz, prev, best, bestpos, cx, cy, lb_hi, pos2);
 }
 
 // True when the visited block of Chebyshev radius `rad` around (cx, cy) provably bounds the search (cheap form of

@@ -62,7 +62,7 @@ template <bool Z3>
 static int check(const HostGrid& G, const std::vector<double>& px, const std::vector<double>& py,
                  const std::vector<double>& pz, const std::vector<double>& qx, const std::vector<double>& qy,
                  const std::vector<double>& qz, int wx0, int wy0, int wx1, int wy1, long* n_window_hits,
-                 long* n_lb_checked, long* n_lb_tight) {
+                 long* n_lb_checked, long* n_lb_tight, long* n_lb_runner) {
     // XYZ instantiation reads the packed 32 B records, XY the split arrays (exactly like the device layouts)
     std::vector<double4> rec(G.xy.size());
     for (size_t i = 0; i < rec.size(); ++i) rec[i] = make_double4(G.xy[i].x, G.xy[i].y, G.z[i], index_to_bits(G.org[i]));
@@ -127,8 +127,8 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
             if (variant == 1) prev = pos;
             if (variant == 2) prev = (int)((i * 7919u + 13u) % px.size());
             if (variant == 3) prev = std::min<int>((int)px.size() - 1, pos + 1);
-            double b3; int p3, cx, cy, lbh;
-            if (!nn_search_block3_impl<Z3, true>(ga, G.g, qx[i], qy[i], qz[i], prev, b3, p3, cx, cy, lbh)) continue;
+            double b3; int p3, cx, cy, lbh, p2nd;
+            if (!nn_search_block3_impl<Z3, true>(ga, G.g, qx[i], qy[i], qz[i], prev, b3, p3, cx, cy, lbh, p2nd)) continue;
             const double border2 = nn_block_border2(G.g, qx[i], qy[i], cx, cy, 1);
             if (nn_block_settles(G.g, qx[i], qy[i], cx, cy, 1, b3) != (b3 < border2)) {
                 if (bad < 5) printf("BORDER2 disagrees with nn_block_settles q%zu\n", i);
@@ -137,6 +137,19 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
             if (!(b3 < border2)) continue;
             ++*n_lb_checked;
             const double lb2 = std::min(hi_to_double(lbh), border2);
+            // the bound covers every point other than the winner and the runner-up
+            double b_others = kInf;
+            const int o2 = (p2nd >= 0) ? G.org[p2nd] : -1;
+            if (p2nd == p3) { if (bad < 5) printf("runner-up equals winner q%zu\n", i); ++bad; }
+            for (size_t j = 0; j < px.size(); ++j) {
+                if ((int)j == bi || (int)j == o2) continue;
+                double dx = qx[i] - px[j], dy = qy[i] - py[j];
+                double d2 = dx * dx + dy * dy;
+                if (Z3) { double dz = qz[i] - pz[j]; d2 = d2 + dz * dz; }
+                if (d2 < b_others) b_others = d2;
+            }
+            if (o2 >= 0 && b2nd < b_others) ++*n_lb_runner;   // the runner-up is the true second-nearest
+            b2nd = b_others;
             if (G.org[p3] != bi || b3 != bb || lb2 > b2nd) {
                 if (bad < 5) printf("LOWER-BOUND(v%d) q%zu: winner %d (%.17g) want %d (%.17g); lb2 %.17g > second %.17g\n", variant, i, G.org[p3], b3, bi, bb, lb2, b2nd);
                 ++bad;
@@ -176,7 +189,7 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
 int main() {
     std::mt19937_64 rng(12345);
     std::uniform_real_distribution<double> U(0.0, 1.0);
-    int bad = 0; long hits = 0; long total = 0; long lbc = 0, lbt = 0;
+    int bad = 0; long hits = 0; long total = 0; long lbc = 0, lbt = 0, lbr = 0;
     for (int trial = 0; trial < 24; ++trial) {
         const size_t m = (trial % 4 == 0) ? 37 : 3000 + 500 * trial;
         const double side = 300.0 * (1 + trial % 3);
@@ -208,10 +221,10 @@ int main() {
         size_t wpts = 0;
         for (int r = wy0; r < wy1; ++r) wpts += G.cs[(size_t)r * G.g.gw + wx1] - G.cs[(size_t)r * G.g.gw + wx0];
         if (wpts > 65535) { wx1 = wx0; }
-        bad += check<false>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits, &lbc, &lbt);
-        bad += check<true>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits, &lbc, &lbt);
+        bad += check<false>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits, &lbc, &lbt, &lbr);
+        bad += check<true>(G, px, py, pz, qx, qy, qz, wx0, wy0, wx1, wy1, &hits, &lbc, &lbt, &lbr);
         total += 2 * nq;
     }
-    printf("queries=%ld window_resolved=%ld lower_bounds_checked=%ld (tight: %ld) mismatches=%d\n", total, hits, lbc, lbt, bad);
+    printf("queries=%ld window_resolved=%ld lower_bounds_checked=%ld (tight: %ld, runner-up is the 2nd nearest: %ld) mismatches=%d\n", total, hits, lbc, lbt, lbr, bad);
     return bad ? 1 : 0;
 }
