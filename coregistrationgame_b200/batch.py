@@ -74,7 +74,7 @@ class TargetIndex:
     # points per grid cell, measured on B200 (profiles/r01_summary.md).  The ICP kernel wants cells wide enough that the
     # 3x3 block around a query settles its search even for poor start poses (3-D residuals of 6-8 m) and gives its
     # skip test a long leash; bulk one-shot queries (no previous neighbour to bound the search) want small cells.
-    PTS_PER_CELL = {("icp", True): 6.0, ("icp", False): 4.0, ("query", True): 3.0, ("query", False): 2.0}
+    PTS_PER_CELL = {("icp", True): 6.0, ("icp", False): 3.0, ("query", True): 3.0, ("query", False): 2.0}
 
     def __init__(self, target, use_z=None, pts_per_cell=None, stream=None, purpose="icp"):
         lib = _lib.load()

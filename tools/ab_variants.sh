@@ -1,4 +1,4 @@
-# A/B helper: bench lines of the other workloads / matching modes (no CPU baseline)
+# Bench lines of the other workloads / matching modes (no CPU baseline); writes gpurun_out/bench_*.json
 B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
 $B --dims 2 > gpurun_out/bench_xy.json 2>gpurun_out/bench_xy.err
 $B --workload c2 > gpurun_out/bench_c2_d3.json 2>gpurun_out/bench_c2_d3.err
