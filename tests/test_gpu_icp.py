@@ -144,6 +144,40 @@ def test_batch_window_and_global_paths_agree(gpu):
     ti.close()
 
 
+@pytest.mark.parametrize("dims,dup", [(3, 0), (2, 0), (3, 5)])
+def test_skip_test_is_bit_identical_to_searching_every_query(gpu, dims, dup):
+    """The skip test (a searched query keeps its runner-up and a lower bound on every other target point; later passes
+    re-evaluate the two and skip the search while the nearer one stays inside the bound) must not change one bit.
+    Reference: the same batch on the global-grid path, where no query carries a bound and every query is searched on
+    every pass.  With exact duplicates among the targets (ties in every neighbourhood) the test must keep deferring to
+    the search (lowest original index wins there) and still agree."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(60000, 180, seed=31 + dims, dims=dims, n_plots=2, hidden_pose=True, out_frac=0.1,
+                                        dup_every=dup)
+    hyp = orc.hypothesis_table(16, flips=(0, 1), translations=orc.translation_lattice(2, 2.5))
+    ti = TargetIndex(tgt)
+    fast = IcpBatch(ti, plots, hyp)
+    a = fast.run().results()
+    centre0 = fast.centres[0].copy()
+    fast.close()
+    slow = IcpBatch(ti, plots, hyp, disable_window=True)
+    b = slow.run().results()
+    slow.close()
+    ti.close()
+    assert _rows_equal_except_flags(a["hyp"], b["hyp"])
+    np.testing.assert_array_equal(a["best_key"], b["best_key"])
+    sa, sb = a["stats"], b["stats"]
+    assert sa["passes"] == sb["passes"] and sa["queries"] == sb["queries"]
+    assert sb["searched_queries"] == sb["queries"]                 # no bound without the window: everything searched
+    # most queries skip the search (with duplicated targets every query whose neighbour has a twin keeps searching) ...
+    assert sa["searched_queries"] < (0.5 if dup == 0 else 1.0) * sa["queries"]
+    assert sa["searched_queries"] >= plots[0].shape[0] * 2 * hyp.shape[0]   # ... but never on the first pass
+    # and the oracle agrees with both (per-hypothesis pass counts and trimmed sizes of plot 0)
+    ref = orc.run_hypotheses(plots[0], tgt, hyp[:6], centre=centre0, min_k=3, closed_form=True)
+    np.testing.assert_array_equal(a["hyp"]["passes"][0, :6], ref["passes"])
+    np.testing.assert_array_equal(a["hyp"]["k"][0, :6], ref["k"])
+
+
 def _rows_equal_except_flags(a, b):
     for f in a.dtype.names:
         if f in ("flags", "pad"):
