@@ -439,6 +439,21 @@ def run_b200(args):
                          "record came from memory); the kernel serves them from a shared-memory window / L1 / L2, so "
                          "frac is NOT an HBM utilisation and can exceed 1 - see DESIGN.md for the on-chip bound")}
 
+    # on-chip view of the same kernel: share of the SM issue slots it uses, from the warp-instructions per
+    # hypothesis-iteration ncu counted on this workload (profiles/traffic.json) and the live kernel time
+    on_chip = None
+    try:
+        ipp = json.load(open(tpath)).get("icp_kernel_warp_instructions_per_hyp_iteration")
+        if ipp and args.workload == "c3" and args.dims == 3 and args.trees == 500:
+            issue_peak = float(props["sms"]) * 4.0 * float(props["clock_khz"]) * 1e3   # 4 schedulers/SM, 1 warp-instr/cycle
+            issued = float(ipp) * float(passes_per_step) / (kern_ms * 1e-3)
+            on_chip = {"bound": "issue slots", "achieved": issued, "peak": issue_peak, "unit": "warp-instr/s",
+                       "frac": issued / issue_peak,
+                       "source": "warp-instructions per hypothesis-iteration from ncu (profiles/r01_icp_kernel_ncu.txt) x live rate"}
+    except Exception:
+        on_chip = None
+    roofline["on_chip"] = on_chip
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = max(1, min(host_threads(), 32))
