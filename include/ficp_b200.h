@@ -94,7 +94,10 @@ FICP_API int ficp_device_props(int32_t* sms, int64_t* l2_bytes, int64_t* smem_op
 /* measurement aid for bench.py: read bandwidth of a buffer of `bytes` that stays in L2, GB/s */
 FICP_API int ficp_measure_l2_read_gbs(int64_t bytes, int32_t iters, double* gbs);
 
-/* ---- kernel 1a: grid build.  Replaces cKDTree(target) (ficp.py:69), hoisted out of the loop. */
+/* ---- kernel 1a: grid build.  Replaces cKDTree(target) (ficp.py:69), hoisted out of the loop.
+ * pts_per_cell: mean target points per grid cell (<= 0: 2).  Measured optima on B200: 6 (XYZ) / 3 (XY) when the index
+ * feeds ficp_batch_* (cells wide enough that a query's 3x3 block settles its search), 3 / 2 for bulk ficp_nn_query;
+ * the Python host (TargetIndex(purpose=...)) passes these.  Results never depend on it. */
 FICP_API int ficp_target_create(const double* pts_host, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
                        void* stream, ficp_target** out);
 FICP_API int ficp_target_create_device(const double* pts_dev, int64_t m, int32_t ld, int32_t use_z, double pts_per_cell,
