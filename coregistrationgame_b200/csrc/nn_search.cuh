@@ -201,27 +201,35 @@ FICP_HD void nn_fold(const Acc& acc, int j, double d2, double& best, int& bestpo
     }
 }
 
-// Same fold, additionally keeping the RUNNER-UP: `pos2` = the candidate with the smallest squared distance among the
-// candidates other than the running winner (`sec` = its code: d_hi, rounded down), and `third` = code of a lower bound
-// on the squared distance of every candidate streamed that is neither the winner nor the runner-up.  Re-meeting the
-// winner or the runner-up (a seed comes by again in the stream) does not count.  The choice of the runner-up is made
-// on the truncated codes - any choice is valid, `third` bounds whoever was not chosen.
+// Running top-3 of the streamed candidates by CODE (d_hi: squared distance truncated towards zero, a monotone integer):
+// the two smallest with their positions, the third as a code only.  Branch-free insertion; a candidate that is met
+// again (the seed comes by in the stream, the odd tail of the stream repeats its last candidate) is not inserted twice
+// while it sits in one of the two position slots - and if it has dropped to the third slot, inserting its code again
+// changes nothing.  The EXACT winner (fp64 compare, ties by original index) is kept by nn_fold as before; because the
+// code is monotone, the winner's code is the smallest, so after the stream it sits in slot 1 - or in slot 2 / beyond
+// when other candidates share its code, in which case c3 (or c1) has already come down to that code.
+struct Top3 {
+    int c1, c2, c3, p1, p2;
+};
+FICP_HD Top3 top3_empty() { return Top3{kHiInf, kHiInf, kHiInf, -1, -1}; }
 template <class Acc>
-FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& bestpos, int& sec, int& pos2, int& third) {
-    const bool lt = d2 < best;
-    // an exact tie with a different point is settled by original index inside nn_fold (either may win): no runner-up
-    // bookkeeping for it, the bound simply drops to the tied distance (no slack - such queries are always searched)
-    const bool tie = (d2 == best) && (j != bestpos);
-    const bool skip = (j == bestpos) || (j == pos2) || tie;
-    const int cd = lt ? d_hi(best) : (skip ? kHiInf : d_hi(d2));   // what joins the "others": the old winner, or j
-    const int cp = lt ? bestpos : j;
-    const bool lt2 = cd < sec;
-    int t3 = lt2 ? sec : cd;
-    t3 = tie ? d_hi(d2) : t3;
-    third = (t3 < third) ? t3 : third;
-    pos2 = lt2 ? cp : pos2;
-    sec = lt2 ? cd : sec;
+FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& bestpos, Top3& t) {
+    const bool again = (j == t.p1) || (j == t.p2);
+    const int c = again ? kHiInf : d_hi(d2);
+    const bool m1 = c < t.c1, m2 = c < t.c2, m3 = c < t.c3;
+    t.c3 = m2 ? t.c2 : (m3 ? c : t.c3);
+    t.c2 = m1 ? t.c1 : (m2 ? c : t.c2);
+    t.p2 = m1 ? t.p1 : (m2 ? j : t.p2);
+    t.c1 = m1 ? c : t.c1;
+    t.p1 = m1 ? j : t.p1;
     nn_fold(acc, j, d2, best, bestpos);
+}
+// Runner-up and the code of a lower bound on every streamed candidate other than winner and runner-up.
+FICP_HD int top3_finish(const Top3& t, int bestpos, int& pos2) {
+    if (t.p1 == bestpos) { pos2 = t.p2; return t.c3; }
+    if (t.p2 == bestpos) { pos2 = t.p1; return t.c3; }   // shares its code with p1
+    pos2 = -1;                                            // >= 3 candidates share the winner's code, or it was not streamed
+    return t.c1;
 }
 
 // ---- one candidate ---------------------------------------------------------------------------------
@@ -396,7 +404,8 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
     if (!acc.covers(xl, xh, yl, yh)) return false;
     best = kInf;
     bestpos = -1;
-    int lb = kHiInf, sec = kHiInf;
+    int lb = kHiInf;
+    Top3 top = top3_empty();
     pos2 = -1;
     if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
     // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
@@ -458,14 +467,17 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
         const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
         const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
         if (TRACK) {
-            nn_fold_track(acc, j0, da, best, bestpos, sec, pos2, lb);
-            nn_fold_track(acc, j1, db, best, bestpos, sec, pos2, lb);
+            nn_fold_track(acc, j0, da, best, bestpos, top);
+            nn_fold_track(acc, j1, db, best, bestpos, top);
         } else {
             nn_fold(acc, j0, da, best, bestpos);
             nn_fold(acc, j1, db, best, bestpos);
         }
     }
-    if (TRACK && pos2 == bestpos) pos2 = -1;   // a re-met runner-up won an exact tie: the bound is already down at `best`
+    if (TRACK) {
+        const int c = top3_finish(top, bestpos, pos2);
+        lb = (c < lb) ? c : lb;
+    }
     lb_hi = lb;
     return true;
 }
