@@ -224,6 +224,26 @@ FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& 
     t.p1 = m1 ? j : t.p1;
     nn_fold(acc, j, d2, best, bestpos);
 }
+#if defined(FICP_TIEFREE_STREAM)
+// EXPERIMENT, off by default (not measured on the GPU yet): the same insertion, but the winner is
+// kept with a plain `<` (first met wins) - no tie test, no branch in the candidate loop.  An exact tie with a different
+// point shows up afterwards as a second candidate carrying the winner's CODE; only then (rare: codes agree to 2^-20) the
+// stream is looked at again with the index rule (see nn_search_block3_impl).  Accessors whose admit() can refuse a
+// candidate must not use it (TRACK is instantiated for WindowAcc / GlobalAcc only).
+FICP_HD void nn_fold_track_notie(int j, double d2, double& best, int& bestpos, Top3& t) {
+    const bool again = (j == t.p1) || (j == t.p2);
+    const int c = again ? kHiInf : d_hi(d2);
+    const bool m1 = c < t.c1, m2 = c < t.c2, m3 = c < t.c3;
+    t.c3 = m2 ? t.c2 : (m3 ? c : t.c3);
+    t.c2 = m1 ? t.c1 : (m2 ? c : t.c2);
+    t.p2 = m1 ? t.p1 : (m2 ? j : t.p2);
+    t.c1 = m1 ? c : t.c1;
+    t.p1 = m1 ? j : t.p1;
+    const bool lt = d2 < best;
+    best = lt ? d2 : best;
+    bestpos = lt ? j : bestpos;
+}
+#endif
 // Runner-up and the code of a lower bound on every streamed candidate other than winner and runner-up.
 FICP_HD int top3_finish(const Top3& t, int bestpos, int& pos2) {
     if (t.p1 == bestpos) { pos2 = t.p2; return t.c3; }
@@ -467,13 +487,31 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
         const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
         const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
         if (TRACK) {
+#if defined(FICP_TIEFREE_STREAM)
+            nn_fold_track_notie(j0, da, best, bestpos, top);
+            nn_fold_track_notie(j1, db, best, bestpos, top);
+#else
             nn_fold_track(acc, j0, da, best, bestpos, top);
             nn_fold_track(acc, j1, db, best, bestpos, top);
+#endif
         } else {
             nn_fold(acc, j0, da, best, bestpos);
             nn_fold(acc, j1, db, best, bestpos);
         }
     }
+#if defined(FICP_TIEFREE_STREAM)
+    if (TRACK) {
+        // a candidate other than the winner carries the winner's code: possibly an exact tie - settle it by original
+        // index in a second look at the stream (the winner's distance is already the minimum, only its index can change)
+        const int cb = d_hi(best);
+        if (top.c1 == cb && (top.p1 != bestpos || top.c2 == cb)) {
+            for (int t = 0; t < total; ++t) {
+                const int j = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+                nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
+            }
+        }
+    }
+#endif
     if (TRACK) {
         const int c = top3_finish(top, bestpos, pos2);
         lb = (c < lb) ? c : lb;

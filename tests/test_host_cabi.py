@@ -98,11 +98,13 @@ def test_product_path_never_imports_the_oracle():
     assert "oracle" not in open(os.path.join(ROOT, "ficp.py")).read()
 
 
-def test_nn_search_host_check(tmp_path):
+@pytest.mark.parametrize("flags", [[], ["-DFICP_TIEFREE_STREAM"]], ids=["product", "tiefree-experiment"])
+def test_nn_search_host_check(tmp_path, flags):
     """The grid NN search (ring/termination/tie logic, window + global accessors, streamed form with arbitrary
-    seeds) is host-compilable: build it with g++ and compare 19 200 queries against brute force."""
+    seeds, runner-up and lower bound of the tracked form) is host-compilable: build it with g++ and compare 19 200
+    queries / 54 332 tracked searches against brute force.  Also for the experimental build flags kept in the source."""
     exe = tmp_path / "nn_check"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "coregistrationgame_b200", "csrc"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", *flags, "-I", os.path.join(ROOT, "coregistrationgame_b200", "csrc"),
                            "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "hostcheck", "nn_search_check.cpp"),
                            "-o", str(exe)])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
