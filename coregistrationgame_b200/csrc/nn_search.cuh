@@ -428,6 +428,12 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
     Top3 top = top3_empty();
     pos2 = -1;
     if (prev >= 0) nn_eval<Z3>(acc, prev, qx, qy, qz, best, bestpos);
+#if defined(FICP_PRESCAN_OWN_CELL)
+    // EXPERIMENT, off by default (not measured on the GPU yet): a search without a seed (first pass
+    // of a hypothesis) looks at the query's own cell first, so that the pruning below has a bound to work with instead
+    // of streaming all nine cells; the own cell is streamed again with the others (same candidates, same result).
+    else if (TRACK) nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
+#endif
     // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
     // query from the lower-left corner of its (clamped) cell; it lies in [0, h] unless the query is off the grid.
     const double h = g.h, eps = g.eps;

@@ -98,7 +98,8 @@ def test_product_path_never_imports_the_oracle():
     assert "oracle" not in open(os.path.join(ROOT, "ficp.py")).read()
 
 
-@pytest.mark.parametrize("flags", [[], ["-DFICP_TIEFREE_STREAM"]], ids=["product", "tiefree-experiment"])
+@pytest.mark.parametrize("flags", [[], ["-DFICP_TIEFREE_STREAM"], ["-DFICP_PRESCAN_OWN_CELL"]],
+                         ids=["product", "tiefree-experiment", "prescan-experiment"])
 def test_nn_search_host_check(tmp_path, flags):
     """The grid NN search (ring/termination/tie logic, window + global accessors, streamed form with arbitrary
     seeds, runner-up and lower bound of the tracked form) is host-compilable: build it with g++ and compare 19 200
