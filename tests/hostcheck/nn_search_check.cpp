@@ -171,6 +171,31 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
                 const int wtot = rowoff[wh];
                 if (variant == 1 && wtot > 0) prev = (int)((i * 104729u + 7u) % (unsigned)wtot);
                 if (variant == 2 && wtot > 0) prev = wtot - 1;
+                // tracked form over the WINDOW accessor - the instantiation the ICP kernel uses
+                {
+                    double b5; int p5, cx5, cy5, lbh5, r5;
+                    if (nn_search_block3_impl<Z3, true>(wa, G.g, qx[i], qy[i], qz[i], prev, b5, p5, cx5, cy5, lbh5, r5)) {
+                        const double border2 = nn_block_border2(G.g, qx[i], qy[i], cx5, cy5, 1);
+                        if (b5 < border2) {
+                            ++*n_lb_checked;
+                            const int won = G.org[wa.global_pos(p5)];
+                            const int o2 = (r5 >= 0) ? G.org[wa.global_pos(r5)] : -1;
+                            double b_others = kInf;
+                            for (size_t j = 0; j < px.size(); ++j) {
+                                if ((int)j == bi || (int)j == o2) continue;
+                                double dx = qx[i] - px[j], dy = qy[i] - py[j];
+                                double d2 = dx * dx + dy * dy;
+                                if (Z3) { double dz = qz[i] - pz[j]; d2 = d2 + dz * dz; }
+                                if (d2 < b_others) b_others = d2;
+                            }
+                            const double lb2 = std::min(hi_to_double(lbh5), border2);
+                            if (won != bi || b5 != bb || r5 == p5 || lb2 > b_others) {
+                                if (bad < 5) printf("LOWER-BOUND(window,v%d) q%zu: winner %d (%.17g) want %d (%.17g); lb2 %.17g vs others %.17g\n", variant, i, won, b5, bi, bb, lb2, b_others);
+                                ++bad;
+                            }
+                        }
+                    }
+                }
                 double b4; int p4;
                 if (nn_search_stream<Z3>(wa, G.g, qx[i], qy[i], qz[i], prev, b4, p4)) {
                     ++*n_window_hits;
