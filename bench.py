@@ -101,14 +101,57 @@ def apply_workload_defaults(args):
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
+_REF_CLS = None
+
+
+def reference_class():
+    """The UNMODIFIED reference class, loaded from oracle/_ref/ficp.py (a byte copy of /root/reference/ficp.py staged by
+    tools/vendor_ref.sh; the reference tree itself does not exist on the GPU box).  None when it has not been staged."""
+    global _REF_CLS
+    if _REF_CLS is None:
+        path = os.path.join(ROOT, "oracle", "_ref", "ficp.py")
+        if not os.path.exists(path):
+            _REF_CLS = False
+        else:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ficp_reference_unmodified", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _REF_CLS = mod.FractionalICP
+    return _REF_CLS or None
+
+
+class _Budget(Exception):
+    pass
+
+
 def _cpu_one(job):
-    """One hypothesis through the reference algorithm as shipped: kd-tree rebuilt on every pass, O(N^2)
-    FRMSD loop (oracle port of ficp.py:122-154).  Stops between passes once the step's time budget is spent; the
-    passes completed so far are the units of work done."""
+    """One hypothesis on the CPU.  hoist=False: `FractionalICP(pre_transform(src, h), tgt).run()` of the unmodified
+    reference (kd-tree rebuilt on every pass, O(N^2) FRMSD loop - ficp.py:122-154) under a subclass that only counts
+    `find_correspondences` calls (= hypothesis-iterations) and stops between passes once the step's time budget is
+    spent; the passes completed so far are the units of work done.  hoist=True: the oracle port with the kd-tree built
+    once and a cumsum FRMSD (the "fair" CPU baseline)."""
     from oracle import ficp_oracle as orc
     src, tgt, row, centre, hoist, deadline = job
-    tr = orc.RunTrace(deadline=deadline, light=True)
     s0 = orc.pre_transform(src, row, centre)
+    ref = reference_class()
+    if not hoist and ref is not None:
+        class Counting(ref):
+            n_passes = 0
+
+            def find_correspondences(self, source, target):
+                if time.perf_counter() > deadline:
+                    raise _Budget()
+                out = super().find_correspondences(source, target)
+                self.n_passes += 1
+                return out
+        icp = Counting(s0, tgt)
+        try:
+            icp.run()
+        except _Budget:
+            pass
+        return icp.n_passes
+    tr = orc.RunTrace(deadline=deadline, light=True)
     try:
         if hoist:
             orc.ficp_run(s0, tgt, nn="tree", hoist_tree=True, trace=tr, closed_form=True)
@@ -161,14 +204,16 @@ def run_reference(args):
         tot_p += p
         tot_t += t
     val = tot_p / tot_t
-    sample = (f"{n_sample} strided hypotheses of one plot per step on {procs} processes, ~8 s time budget per step "
-              f"(kd-tree rebuilt every pass, as shipped)")
+    kind = "reference" if reference_class() is not None else "port"
+    sample = (f"{n_sample} strided hypotheses of one plot per step on {procs} processes, ~8 s time budget per step; "
+              + ("unmodified reference ficp.py (oracle/_ref, staged by tools/vendor_ref.sh): FractionalICP(pre_transform(src, h), tgt).run()"
+                 if kind == "reference" else "oracle port of the reference as shipped (oracle/_ref not staged)"))
     line = {"impl": "reference", "metric": "FICP hypothesis-iterations/sec", "value": val, "unit": "hyp-iter/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "sample": sample},
             "nn_queries_per_s": val * args.trees,
-            "cpu_baseline": {"value": val, "unit": "hyp-iter/s", "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "hyp-iter/s", "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "hyp-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -464,11 +509,13 @@ def run_b200(args):
         # single core (SURVEY 8d asks for both): one hypothesis on one process, ~6 s budget each
         p1, t1 = cpu_step(plots[0], tgt, hyp, 1, 1, hoist=False, budget_s=6.0)
         p1h, t1h = cpu_step(plots[0], tgt, hyp, 1, 1, hoist=True, budget_s=6.0)
-        cpu_baseline = {"value": p_asis / t_asis, "unit": "hyp-iter/s", "cores": procs, "kind": "port",
-                        "sample": sample + " (reference algorithm as shipped: kd-tree rebuilt every pass, O(N^2) FRMSD loop)",
+        kind = "reference" if reference_class() is not None else "port"
+        cpu_baseline = {"value": p_asis / t_asis, "unit": "hyp-iter/s", "cores": procs, "kind": kind,
+                        "sample": sample + (" (unmodified reference ficp.py from oracle/_ref: kd-tree rebuilt every pass, O(N^2) FRMSD loop)"
+                                            if kind == "reference" else " (oracle port of the reference as shipped)"),
                         "seconds": t_asis,
-                        "index_hoisted": {"value": p_h / t_h, "unit": "hyp-iter/s", "seconds": t_h,
-                                          "sample": sample + " (kd-tree built once, cumsum FRMSD)"},
+                        "index_hoisted": {"value": p_h / t_h, "unit": "hyp-iter/s", "seconds": t_h, "kind": "port",
+                                          "sample": sample + " (oracle port: kd-tree built once, cumsum FRMSD)"},
                         "single_core": {"as_shipped": p1 / t1, "index_hoisted": p1h / t1h, "unit": "hyp-iter/s",
                                         "sample": "hypothesis 0 of plot 0 on 1 process, ~6 s budget each"}}
 

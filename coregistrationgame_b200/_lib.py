@@ -26,14 +26,15 @@ class TargetInfo(C.Structure):
 class BatchParams(C.Structure):
     _fields_ = [("n_stages", c_i32), ("max_iterations", c_i32), ("allow_reflection", c_i32), ("min_k", c_i32),
                 ("threshold", c_f64), ("window_margin", c_f64), ("warps_per_cta", c_i32), ("ctas_per_sm", c_i32),
-                ("disable_window", c_i32), ("team_warps", c_i32), ("no_helpers", c_i32), ("reserved", c_i32)]
+                ("disable_window", c_i32), ("team_warps", c_i32), ("no_helpers", c_i32), ("trace_passes", c_i32)]
 
 
 class BatchInfo(C.Structure):
     _fields_ = [("n_plots", c_i32), ("n_hyp", c_i32), ("n_hyp_local", c_i32), ("elems_per_lane", c_i32),
                 ("match_z", c_i32), ("warps_per_cta", c_i32), ("ctas", c_i32), ("ctas_per_sm", c_i32),
                 ("slices_per_plot", c_i32), ("window_pts_cap", c_i32), ("window_cells_cap", c_i32),
-                ("team_warps", c_i32), ("helpers", c_i32), ("reserved", c_i32), ("smem_bytes", c_i64), ("rows", c_i64)]
+                ("team_warps", c_i32), ("helpers", c_i32), ("trace_passes", c_i32), ("smem_bytes", c_i64), ("rows", c_i64),
+                ("trace_stride", c_i32), ("reserved", c_i32)]
 
 
 # numpy view of ficp_hyp_result
@@ -66,6 +67,7 @@ SIGNATURES = {
     "ficp_batch_run": (c_i32, [c_vp, c_vp]),
     "ficp_batch_results": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_copy_best_keys_device": (c_i32, [c_vp, c_vp, c_vp]),
+    "ficp_batch_trace": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_destroy": (None, [c_vp]),
 }
 

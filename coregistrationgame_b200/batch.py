@@ -138,7 +138,7 @@ class IcpBatch:
     def __init__(self, index, sources, hyp_table=None, centres=None, lambda_val=3.0, stage2_lambda=None, n_stages=2,
                  threshold=1e-6, max_iterations=1000, allow_reflection=False, min_k=3, fixed_frac=None,
                  hyp_shard=(0, 1), want_final_xy=False, window_margin=-1.0, warps_per_cta=0, ctas_per_sm=0,
-                 disable_window=False, team_warps=0, helpers=None, stream=None):
+                 disable_window=False, team_warps=0, helpers=None, trace_passes=0, stream=None):
         lib = _lib.load()
         if isinstance(sources, np.ndarray) and sources.ndim == 2:
             sources = [sources]
@@ -179,7 +179,8 @@ class IcpBatch:
         self.hyp_begin, self.hyp_stride = int(hyp_shard[0]), int(hyp_shard[1])
         prm = _lib.BatchParams(self.n_stages, int(max_iterations), int(bool(allow_reflection)), int(min_k),
                                float(threshold), float(window_margin), int(warps_per_cta), int(ctas_per_sm),
-                               int(bool(disable_window)), int(team_warps), (0 if helpers is None else (2 if helpers else 1)), 0)
+                               int(bool(disable_window)), int(team_warps), (0 if helpers is None else (2 if helpers else 1)),
+                               int(trace_passes))
         self._h = C.c_void_p()
         _lib.check(lib.ficp_batch_create(index.handle, _lib.ptr(self.src), ld, int(self.match_dims == 3),
                                          _lib.ptr(self.offsets), self.n_plots, _lib.ptr(self.centres),
@@ -225,6 +226,25 @@ class IcpBatch:
         self.d2h_bytes = int(keys.nbytes + stats.nbytes + (res.nbytes if res is not None else 0)
                              + (final.nbytes if final is not None else 0))
         return out
+
+    def trace(self, stream=None):
+        """Per-pass trace of a batch created with ``trace_passes > 0`` (test instrument).  Returns arrays indexed
+        ``[plot, local hypothesis, pass, tree]``: ``idx`` original target row of every tree's nearest neighbour
+        (ficp.py:70), ``d2`` its squared distance, ``inlier`` membership in the trimmed subset (ficp.py:62-63,133), and
+        ``k`` / ``frmsd`` ``[plot, local hypothesis, pass]``.  Only the first ``min(passes, trace_passes)`` passes of an
+        ICP and the first ``n`` trees of a plot are meaningful."""
+        cap, stride = int(self.info["trace_passes"]), int(self.info["trace_stride"])
+        if cap <= 0:
+            raise ValueError("batch was created without trace_passes")
+        shape = (self.n_plots, self.n_hyp_local, cap)
+        idx = np.empty(shape + (stride,), dtype=np.int32)
+        d2 = np.empty(shape + (stride,), dtype=np.float64)
+        inl = np.empty(shape + (stride,), dtype=np.uint8)
+        k = np.empty(shape, dtype=np.int32)
+        f = np.empty(shape, dtype=np.float64)
+        _lib.check(_lib.load().ficp_batch_trace(self._h, _lib.ptr(idx), _lib.ptr(d2), _lib.ptr(inl), _lib.ptr(k),
+                                                _lib.ptr(f), _stream_ptr(stream)), "ficp_batch_trace")
+        return {"idx": idx, "d2": d2, "inlier": inl.astype(bool), "k": k, "frmsd": f}
 
     def transform_of(self, plot, hyp_row):
         """2x3 world-coordinate transform [A | b] of one result row: final = A p + b."""

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/ficp_b200.h"
@@ -21,34 +22,57 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return kErrCuda;
 }
 
-cudaError_t dev_alloc(void** p, size_t bytes) {
-    static thread_local int pool_ready_for = -1;
+namespace {
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
+bool g_pool_tried[64] = {};
+// private pool of the current device (nullptr: creation failed, fall back to the device's default pool untouched)
+cudaMemPool_t private_pool() {
     int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (pool_ready_for != dev) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool_tried[dev]) {
+        g_pool_tried[dev] = true;
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
             unsigned long long keep = ~0ull;  // never trim: freed blocks stay in the pool for the next index / batch
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            g_pools[dev] = pool;
+        } else {
+            cudaGetLastError();
         }
-        pool_ready_for = dev;
     }
-    return cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0);
+    return g_pools[dev];
 }
-void dev_free(void* p) {
-    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}  // namespace
+
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    cudaMemPool_t pool = private_pool();
+    if (pool) return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, stream);
+    return cudaMallocAsync(p, bytes ? bytes : 1, stream);
+}
+void dev_free(void* p, cudaStream_t stream) {
+    if (p) cudaFreeAsync(p, stream);
 }
 
 static_assert(sizeof(ficp_hyp_result) == sizeof(HypResult), "ABI struct mismatch");
 
 // RAII device buffer for the host-buffer convenience calls
+// (allocated and released on the stream the call works on: stream-ordered, so an early error return never frees
+// memory a kernel enqueued before it still uses)
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    ~DevBuf() { dev_free(p); }
+    cudaStream_t s;
+    explicit DevBuf(cudaStream_t stream = nullptr) : s(stream) {}
+    ~DevBuf() { dev_free(p, s); }
     int alloc(size_t n) {
-        FICP_CUDA(dev_alloc_t(&p, n));
+        FICP_CUDA(dev_alloc_t(&p, n, s));
         return kOk;
     }
 };
@@ -72,9 +96,19 @@ struct Batch {
     double* d_final = nullptr;
     int* d_counters = nullptr;  // [0] slice counter, [1..n_plots] hypothesis counters
     unsigned long long* d_stats = nullptr;
+    int trace_cap = 0, trace_stride = 0;
+    int* d_tr_idx = nullptr;
+    double* d_tr_d2 = nullptr;
+    unsigned char* d_tr_in = nullptr;
+    int* d_tr_k = nullptr;
+    double* d_tr_f = nullptr;
+    UseEvent used;  // last enqueued run / copy that touches the buffers below
     ~Batch() {
-        dev_free(d_src_u); dev_free(d_src_z); dev_free(d_plots); dev_free(d_hyp); dev_free(d_tabs);
-        dev_free(d_results); dev_free(d_best); dev_free(d_final); dev_free(d_counters); dev_free(d_stats);
+        used.wait();  // nothing in flight any more: the release below may be ordered on any stream
+        cudaStream_t s = cudaStreamPerThread;
+        dev_free(d_tr_idx, s); dev_free(d_tr_d2, s); dev_free(d_tr_in, s); dev_free(d_tr_k, s); dev_free(d_tr_f, s);
+        dev_free(d_src_u, s); dev_free(d_src_z, s); dev_free(d_plots, s); dev_free(d_hyp, s); dev_free(d_tabs, s);
+        dev_free(d_results, s); dev_free(d_best, s); dev_free(d_final, s); dev_free(d_counters, s); dev_free(d_stats, s);
     }
 };
 
@@ -170,16 +204,26 @@ int ficp_nn_query_device(const ficp_target* th, const double* q_dev, int64_t n, 
     const Target* t = reinterpret_cast<const Target*>(th);
     if (ld < 2 || (use_z && ld < 3)) { set_error("ficp_nn_query: not enough columns"); return kErrInvalid; }
     if (use_z && !t->has_z) { set_error("ficp_nn_query: target was built without Z"); return kErrInvalid; }
-    return launch_nn_query(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, (cudaStream_t)stream);
+    const int rc = launch_nn_query(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, (cudaStream_t)stream);
+    t->used.record((cudaStream_t)stream);
+    return rc;
 }
 
 int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
                   int64_t* idx_out, double* dist_out, void* stream) {
     if (n <= 0) return kOk;
     if (!th || !q_host || !idx_out) { set_error("ficp_nn_query: null pointer"); return kErrInvalid; }
+    if (ld < 2 || (use_z && ld < 3)) { set_error("ficp_nn_query: not enough columns"); return kErrInvalid; }
+    for (int64_t i = 0; i < n; ++i) {
+        const double* r = q_host + (size_t)i * ld;
+        if (!std::isfinite(r[0]) || !std::isfinite(r[1]) || (use_z && !std::isfinite(r[2]))) {
+            set_error("query contains non-finite coordinates ('x' must be finite)");
+            return kErrNonFinite;
+        }
+    }
     cudaStream_t s = (cudaStream_t)stream;
-    DevBuf<double> dq, dd;
-    DevBuf<int> di;
+    DevBuf<double> dq(s), dd(s);
+    DevBuf<int> di(s);
     int rc;
     if ((rc = dq.alloc((size_t)n * ld)) || (rc = dd.alloc(n)) || (rc = di.alloc(n))) return rc;
     FICP_CUDA(cudaMemcpyAsync(dq.p, q_host, sizeof(double) * (size_t)n * ld, cudaMemcpyHostToDevice, s));
@@ -206,9 +250,9 @@ int ficp_match_remove(const ficp_target* th, const double* trees_host, const int
     if (rows <= 0) return kOk;
     if (t->m <= 0) { for (long long i = 0; i < rows; ++i) matched_out[i] = -1; return kOk; }
     cudaStream_t s = (cudaStream_t)stream;
-    DevBuf<double> dt, dthr;
-    DevBuf<long long> doff, dout;
-    DevBuf<int> dscr;
+    DevBuf<double> dt(s), dthr(s);
+    DevBuf<long long> doff(s), dout(s);
+    DevBuf<int> dscr(s);
     int rc;
     if ((rc = dt.alloc((size_t)rows * ld)) || (rc = dthr.alloc(rows)) || (rc = doff.alloc(n_plots + 1)) || (rc = dout.alloc(rows)) ||
         (rc = dscr.alloc(rows)))
@@ -230,7 +274,7 @@ int ficp_radial_crop(const ficp_target* th, double cx, double cy, double dist, u
     if (t->m <= 0) return kOk;
     if (!std::isfinite(cx) || !std::isfinite(cy) || std::isnan(dist)) { set_error("ficp_radial_crop: non-finite centre or radius"); return kErrNonFinite; }
     cudaStream_t s = (cudaStream_t)stream;
-    DevBuf<unsigned char> dm;
+    DevBuf<unsigned char> dm(s);
     int rc;
     if ((rc = dm.alloc((size_t)t->m))) return rc;
     FICP_CUDA(cudaMemsetAsync(dm.p, 0, (size_t)t->m, s));
@@ -562,16 +606,27 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     }
 
     // ---- device buffers
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows));
-    if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_plots), sizeof(PlotMeta) * (size_t)n_plots));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_hyp), sizeof(double) * 6 * (size_t)n_hyp));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tabs), sizeof(double) * h_tabs.size()));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_results), sizeof(HypResult) * (size_t)n_plots * n_hyp_local));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_best), sizeof(unsigned long long) * (size_t)n_plots));
-    if (b->want_final) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_final), sizeof(double) * 2 * (size_t)rows));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_counters), sizeof(int) * (size_t)(n_plots + 1)));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_stats), sizeof(unsigned long long) * 8));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows, s));
+    if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows, s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_plots), sizeof(PlotMeta) * (size_t)n_plots, s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_hyp), sizeof(double) * 6 * (size_t)n_hyp, s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tabs), sizeof(double) * h_tabs.size(), s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_results), sizeof(HypResult) * (size_t)n_plots * n_hyp_local, s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_best), sizeof(unsigned long long) * (size_t)n_plots, s));
+    if (b->want_final) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_final), sizeof(double) * 2 * (size_t)rows, s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_counters), sizeof(int) * (size_t)(n_plots + 1), s));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_stats), sizeof(unsigned long long) * 8, s));
+    if (prm->trace_passes < 0) { set_error("ficp_batch_create: trace_passes must be >= 0"); return kErrInvalid; }
+    if (prm->trace_passes > 0) {
+        const size_t recs = (size_t)n_plots * n_hyp_local * (size_t)prm->trace_passes;
+        if (recs * (size_t)npad * 13 > ((size_t)4 << 30)) { set_error("ficp_batch_create: trace buffers above 4 GB (trace fewer ICPs / passes)"); return kErrTooLarge; }
+        b->trace_cap = prm->trace_passes; b->trace_stride = npad;
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_idx), sizeof(int) * recs * npad, s));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_d2), sizeof(double) * recs * npad, s));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_in), recs * npad, s));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_k), sizeof(int) * recs, s));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_f), sizeof(double) * recs, s));
+    }
     FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.data(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
     if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.data(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
@@ -592,6 +647,8 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     P.slots = slots_per_cta;
     P.dyn_leads = warps / 2;  // rounds are handed out once the helpers are at least as many as the leads (8 vs 12: same)
     P.stats = b->d_stats;
+    P.trace_cap = b->trace_cap; P.trace_stride = b->trace_stride;
+    P.tr_idx = b->d_tr_idx; P.tr_d2 = b->d_tr_d2; P.tr_in = b->d_tr_in; P.tr_k = b->d_tr_k; P.tr_f = b->d_tr_f;
     b->launch.e = e; b->launch.z3 = z3; b->launch.warps = warps; b->launch.slots = slots_per_cta; b->launch.elastic = elastic; b->launch.smem = smem;
     b->launch.ctas = (int)std::min<long long>(n_slices, resident);
     b->ctas_per_sm = ctas_per_sm;
@@ -608,6 +665,7 @@ int ficp_batch_get_info(const ficp_batch* bh, ficp_batch_info* info) {
     info->ctas = b->launch.ctas; info->ctas_per_sm = b->ctas_per_sm; info->slices_per_plot = b->params.slices_per_plot;
     info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells; info->team_warps = b->launch.warps / b->launch.slots; info->helpers = b->launch.elastic ? 1 : 0;
     info->smem_bytes = (int64_t)b->launch.smem; info->rows = b->rows;
+    info->trace_passes = b->trace_cap; info->trace_stride = b->trace_stride;
     return kOk;
 }
 
@@ -618,7 +676,10 @@ int ficp_batch_run(ficp_batch* bh, void* stream) {
     FICP_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * (size_t)(b->n_plots + 1), s));
     FICP_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(unsigned long long) * 8, s));
     FICP_CUDA(cudaMemsetAsync(b->d_best, 0xFF, sizeof(unsigned long long) * (size_t)b->n_plots, s));
-    return launch_icp(b->params, b->launch, s);
+    const int rc = launch_icp(b->params, b->launch, s);
+    b->used.record(s);
+    b->tgt->used.record(s);
+    return rc;
 }
 
 int ficp_batch_results(ficp_batch* bh, ficp_hyp_result* results, uint64_t* best_keys, double* final_xy, uint64_t* stats,
@@ -645,6 +706,23 @@ int ficp_batch_copy_best_keys_device(ficp_batch* bh, void* dst_dev, void* stream
     Batch* b = reinterpret_cast<Batch*>(bh);
     FICP_CUDA(cudaMemcpyAsync(dst_dev, b->d_best, sizeof(uint64_t) * (size_t)b->n_plots, cudaMemcpyDeviceToDevice,
                               (cudaStream_t)stream));
+    b->used.record((cudaStream_t)stream);
+    return kOk;
+}
+
+int ficp_batch_trace(ficp_batch* bh, int32_t* idx_out, double* d2_out, uint8_t* inlier_out, int32_t* k_out,
+                     double* frmsd_out, void* stream) {
+    if (!bh) { set_error("ficp_batch_trace: null batch"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    if (b->trace_cap <= 0) { set_error("ficp_batch_trace: batch was created with trace_passes = 0"); return kErrInvalid; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t recs = (size_t)b->n_plots * b->n_hyp_local * (size_t)b->trace_cap, ent = recs * (size_t)b->trace_stride;
+    if (idx_out) FICP_CUDA(cudaMemcpyAsync(idx_out, b->d_tr_idx, sizeof(int) * ent, cudaMemcpyDeviceToHost, s));
+    if (d2_out) FICP_CUDA(cudaMemcpyAsync(d2_out, b->d_tr_d2, sizeof(double) * ent, cudaMemcpyDeviceToHost, s));
+    if (inlier_out) FICP_CUDA(cudaMemcpyAsync(inlier_out, b->d_tr_in, ent, cudaMemcpyDeviceToHost, s));
+    if (k_out) FICP_CUDA(cudaMemcpyAsync(k_out, b->d_tr_k, sizeof(int) * recs, cudaMemcpyDeviceToHost, s));
+    if (frmsd_out) FICP_CUDA(cudaMemcpyAsync(frmsd_out, b->d_tr_f, sizeof(double) * recs, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
     return kOk;
 }
 

@@ -26,11 +26,28 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // ---- device memory: stream-ordered allocator with a retaining pool -----------------------------------------
 // cudaMalloc/cudaFree of the tens-of-MB index buffers cost 30-150 ms per call pair on B200 (measured, driver
-// 580); the default mempool with a raised release threshold makes repeated index / batch creation reuse memory.
-cudaError_t dev_alloc(void** p, size_t bytes);
-void dev_free(void* p);
+// 580); a PRIVATE cudaMemPool per device (release threshold = never trim; the process-wide default pool is left
+// alone) makes repeated index / batch creation reuse memory.  Allocation and release are ordered on the stream the
+// caller works on: `stream` is the stream whose subsequent work uses the memory (alloc) / whose prior work was the
+// last to use it (free).  Handles that outlive a call (Target, Batch) record an event after every enqueue and wait
+// for it before releasing their buffers (see UseEvent), so destroy-after-enqueue on a non-blocking stream is safe.
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream);
+void dev_free(void* p, cudaStream_t stream);
 template <class T>
-inline cudaError_t dev_alloc_t(T** p, size_t count) { return dev_alloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1)); }
+inline cudaError_t dev_alloc_t(T** p, size_t count, cudaStream_t stream) {
+    return dev_alloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1), stream);
+}
+// "last use" marker of a handle: record(stream) after enqueuing work that touches the handle's buffers, wait()
+// before they are released.  After wait() nothing is in flight, so the release may be ordered on any stream.
+struct UseEvent {
+    cudaEvent_t ev = nullptr;
+    void record(cudaStream_t s) {
+        if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; cudaStreamSynchronize(s); return; }
+        if (cudaEventRecord(ev, s) != cudaSuccess) cudaStreamSynchronize(s);
+    }
+    void wait() { if (ev) cudaEventSynchronize(ev); }
+    ~UseEvent() { if (ev) cudaEventDestroy(ev); }
+};
 
 // ---- target index -----------------------------------------------------------------------------
 struct Target {
@@ -46,6 +63,7 @@ struct Target {
     int* d_orig = nullptr;     // XY layout
     unsigned* d_cell_start = nullptr;
     float build_ms = 0.f;  // device time of the build kernels (CUDA events)
+    mutable UseEvent used;  // last enqueued work that reads the index (queries, ICP batches)
 };
 
 // Builds the grid from row-major points (ld doubles per row; columns 0,1[,2]).  `pts` is a host
@@ -119,6 +137,14 @@ struct IcpParams {
     int dyn_leads;                  // rounds are handed out to helpers while at most this many leads are active
     unsigned long long* stats;      // [0] passes [1] queries resolved on the global path [2] window disabled
                                     // [3] trim-order fix-up rounds [4] queries
+    // optional per-pass trace (tests: direct parity of NN indices / inlier sets, ficp.py:69-71,62-63,133); off: cap 0
+    int trace_cap;                  // passes recorded per ICP
+    int trace_stride;               // entries per pass record (= NPAD of the launch)
+    int* tr_idx;                    // [icp][cap][stride] original target row of every tree's nearest neighbour
+    double* tr_d2;                  // [icp][cap][stride] its squared distance
+    unsigned char* tr_in;           // [icp][cap][stride] 1 = tree is in the trimmed subset of the pass
+    int* tr_k;                      // [icp][cap]
+    double* tr_f;                   // [icp][cap] FRMSD of the pass
 };
 
 struct IcpLaunch {

@@ -234,10 +234,11 @@ __global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsig
 
 void target_free(Target* t) {
     if (!t) return;
-    dev_free(t->d_xy);
-    dev_free(t->d_rec);
-    dev_free(t->d_orig);
-    dev_free(t->d_cell_start);
+    t->used.wait();  // queries / batches enqueued on any stream have finished reading the index
+    dev_free(t->d_xy, cudaStreamPerThread);
+    dev_free(t->d_rec, cudaStreamPerThread);
+    dev_free(t->d_orig, cudaStreamPerThread);
+    dev_free(t->d_cell_start, cudaStreamPerThread);
     delete t;
 }
 
@@ -263,14 +264,17 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
         double* raw = nullptr; unsigned* cellid = nullptr; unsigned* counts = nullptr; unsigned* fill = nullptr;
         unsigned* bsum = nullptr; BBox* part = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        cudaStream_t s = nullptr;
         ~Guard() {
             if (ev0) cudaEventDestroy(ev0);
             if (ev1) cudaEventDestroy(ev1);
-            dev_free(cellid); dev_free(counts); dev_free(fill); dev_free(bsum); dev_free(part);
-            dev_free(raw);
-            if (armed) target_free(t);
+            // scratch is released in stream order: kernels enqueued before an early return may still use it
+            dev_free(cellid, s); dev_free(counts, s); dev_free(fill, s); dev_free(bsum, s); dev_free(part, s);
+            dev_free(raw, s);
+            if (armed) { t->used.record(s); target_free(t); }
         }
     } g{t};
+    g.s = stream;
 
     if (m == 0) {  // empty target: valid handle, no grid (callers short-circuit like ficp.py:66-68)
         t->view.m = 0;
@@ -281,7 +285,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
 
     const double* d_pts = pts;
     if (!on_device) {
-        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.raw), sizeof(double) * (size_t)m * ld));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.raw), sizeof(double) * (size_t)m * ld, stream));
         FICP_CUDA(cudaMemcpyAsync(g.raw, pts, sizeof(double) * (size_t)m * ld, cudaMemcpyHostToDevice, stream));
         d_pts = g.raw;
     }
@@ -291,7 +295,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
 
     // ---- bounding box + finiteness
     const int nb_bbox = (int)std::min<long long>((m + kT - 1) / kT, 148 * 8);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.part), sizeof(BBox) * (nb_bbox + 1)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.part), sizeof(BBox) * (nb_bbox + 1), stream));
     FICP_CUDA(cudaEventRecord(ev0, stream));
     bbox_kernel<<<nb_bbox, kT, 0, stream>>>(d_pts, m, ld, use_z, g.part);
     bbox_final_kernel<<<1, 32, 0, stream>>>(g.part, nb_bbox, g.part + nb_bbox);
@@ -334,18 +338,18 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     const long long nc = (long long)gg.gw * gg.gh;
 
     // ---- counting sort
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.cellid), sizeof(unsigned) * (size_t)m));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.fill), sizeof(unsigned) * (size_t)nc));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc + 1)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.cellid), sizeof(unsigned) * (size_t)m, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.fill), sizeof(unsigned) * (size_t)nc, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc + 1), stream));
     if (use_z) {
-        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_rec), sizeof(double4) * (size_t)m));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_rec), sizeof(double4) * (size_t)m, stream));
     } else {
-        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m));
-        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m, stream));
+        FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m, stream));
     }
     const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.bsum), sizeof(unsigned) * (size_t)nb_scan));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.bsum), sizeof(unsigned) * (size_t)nb_scan, stream));
     FICP_CUDA(cudaEventRecord(ev0, stream));   // device time of the build = bbox kernels + everything from here
     FICP_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(unsigned) * (size_t)nc, stream));
     FICP_CUDA(cudaMemsetAsync(g.fill, 0, sizeof(unsigned) * (size_t)nc, stream));

@@ -441,6 +441,37 @@ __device__ __noinline__ void slot_work(const IcpParams* Pp, const PlotMeta* pmp,
     }
 }
 
+// Optional per-pass trace (IcpParams::trace_cap > 0; tests only): for every tree the ORIGINAL target row of its nearest
+// neighbour (what `tree.query` returns at ficp.py:70), the squared distance, whether the tree is in the trimmed subset
+// (`argsort(d)[:k]`, ficp.py:62-63,133), plus k and FRMSD of the pass.  Out of line and behind one warp-uniform branch
+// per pass, so the kernel is unchanged when the trace is off.
+template <bool Z3>
+__device__ __noinline__ void trace_pass(const IcpParams* Pp, const PlotMeta* pmp, unsigned char* smem, int npad, int slot,
+                                        int lane, int pass_no, long long icp, int k, double f, double thr, int thr_idx) {
+    const IcpParams& P = *Pp;
+    if (pass_no >= P.trace_cap) return;
+    const PlotMeta pm = *pmp;
+    const SmemLayout L = smem_layout(npad, Z3, P.slots, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    const PlotView<Z3> V(P, pm, smem, L);
+    const double* sd2 = reinterpret_cast<const double*>(smem + L.sd2) + (size_t)slot * npad;
+    const int* snn = reinterpret_cast<const int*>(smem + L.snn) + (size_t)slot * npad;
+    const size_t rec = ((size_t)icp * P.trace_cap + pass_no);
+    const size_t base = rec * P.trace_stride;
+    for (int i = lane; i < pm.n; i += 32) {
+        const int code = snn[i];
+        int orig = -1;
+        if (code != -1) {
+            const int gpos = (code < 0) ? (code & 0x7FFFFFFF) : V.W.global_pos(code & 0xFFFF);
+            orig = grid_orig(P.grid, gpos);
+        }
+        const double d2 = sd2[i];
+        P.tr_idx[base + i] = orig;
+        P.tr_d2[base + i] = d2;
+        P.tr_in[base + i] = (k > 0 && (d2 < thr || (d2 == thr && i <= thr_idx))) ? 1 : 0;
+    }
+    if (lane == 0) { P.tr_k[rec] = k; P.tr_f[rec] = f; }
+}
+
 // Nearest neighbours of one pass (ficp.py:65-71) for the ICP of slot `ctrl`: skip test for every query (passes after
 // the first), then the search of the queries that failed it, in rounds of 32 list entries.  ELASTIC: when enough warps
 // of the CTA have no ICP of their own (`*sh_active <= dyn_leads`: the batch is smaller than the machine, or the plot is
@@ -929,6 +960,9 @@ __global__ void __launch_bounds__(NT, 1) icp_kernel(const __grid_constant__ IcpP
                                                  P.plots + plot, smem, slot, epoch, lane, passes > 0, n_global, n_searched, n_deferred);
                     dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
                     po = icp_trim_phase<E>(pc, sg, gc, sd2, lane, n_fix);
+                    if (P.trace_cap > 0)
+                        trace_pass<Z3>(&P, P.plots + plot, smem, NPAD, slot, lane, passes, (long long)plot * P.n_hyp_local + j,
+                                       po.k, po.f, po.thr, po.thr_idx);
                     ++passes;
                     if (first) {
                         if (po.k == 0) break;  // ficp.py:125-126

@@ -26,9 +26,11 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     double best;
     int pos;
     nn_search_stream<Z3>(acc, v.g, qx, qy, qz, -1, best, pos);
-    idx[i] = grid_orig(v, pos);
-    if (dist) dist[i] = sqrt(best);
-    if (d2out) d2out[i] = best;
+    // a non-finite query has no nearest neighbour (every comparison fails): index -1, distance NaN - never an
+    // out-of-range read.  (The reference raises in scipy, ficp.py:70; the host entry point checks and returns -2.)
+    idx[i] = (pos >= 0) ? grid_orig(v, pos) : -1;
+    if (dist) dist[i] = (pos >= 0) ? sqrt(best) : __longlong_as_double(0x7FF8000000000000LL);
+    if (d2out) d2out[i] = (pos >= 0) ? best : __longlong_as_double(0x7FF8000000000000LL);
 }
 
 // Greedy match-and-remove (replaces CHMPlot.remove_matches, chm_plot.py:223-285): the plot's
@@ -94,11 +96,11 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ 
 int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     struct Res {
         uint4* buf = nullptr; unsigned* sink = nullptr; cudaEvent_t a = nullptr, b = nullptr;
-        ~Res() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); dev_free(buf); dev_free(sink); }
+        ~Res() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); dev_free(buf, nullptr); dev_free(sink, nullptr); }
     } r;
     const size_t n_vec = bytes / sizeof(uint4);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.buf), n_vec * sizeof(uint4)));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.sink), sizeof(unsigned)));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.buf), n_vec * sizeof(uint4), nullptr));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&r.sink), sizeof(unsigned), nullptr));
     FICP_CUDA(cudaMemset(r.buf, 1, n_vec * sizeof(uint4)));
     FICP_CUDA(cudaEventCreate(&r.a));
     FICP_CUDA(cudaEventCreate(&r.b));

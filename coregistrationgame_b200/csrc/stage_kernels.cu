@@ -217,12 +217,9 @@ int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, 
     int npad = 2;
     while (npad < n) npad <<= 1;
     const size_t smem = (size_t)npad * (2 * sizeof(double) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
-        FICP_CUDA(cudaFuncSetAttribute(select_fraction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSelectMaxN * (2 * sizeof(double) + sizeof(int))));
-        attr_set = true;
-    }
+    // per launch, not once per process: the attribute is per device (ficp_set_device may have moved us)
+    FICP_CUDA(cudaFuncSetAttribute(select_fraction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSelectMaxN * (2 * sizeof(double) + sizeof(int))));
     int nt = npad / 2;
     if (nt < 32) nt = 32;
     if (nt > 1024) nt = 1024;

@@ -61,7 +61,9 @@ typedef struct {
     int32_t no_helpers;        /* warps that run out of hypotheses help the ICPs still in flight in their CTA (elastic
                                   kernel): 0 = auto (on for batches below ~10 ICPs per warp slot), 1 = off, 2 = on;
                                   results are identical */
-    int32_t reserved;
+    int32_t trace_passes;      /* > 0: record the first `trace_passes` passes of EVERY ICP of the batch (nearest-neighbour
+                                  rows, squared distances, trimmed-subset flags, k, FRMSD) for ficp_batch_trace; 0 = off.
+                                  Test instrument: direct parity with ficp.py:69-71 (indices) and :62-63,:133 (inlier set) */
 } ficp_batch_params;
 
 typedef struct {
@@ -80,9 +82,11 @@ typedef struct {
     int32_t window_pts_cap, window_cells_cap;
     int32_t team_warps;        /* warps per ICP at launch chosen by the planner */
     int32_t helpers;           /* 1 = elastic kernel (idle warps help) */
-    int32_t reserved;
+    int32_t trace_passes;      /* passes recorded per ICP (0: trace off) */
     int64_t smem_bytes;
     int64_t rows;
+    int32_t trace_stride;      /* entries per pass record of ficp_batch_trace */
+    int32_t reserved;
 } ficp_batch_info;
 
 FICP_API const char* ficp_last_error(void);
@@ -169,6 +173,14 @@ FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_
 /* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then
  * all-reduced with MIN over NCCL). */
 FICP_API int ficp_batch_copy_best_keys_device(ficp_batch* b, void* dst_dev, void* stream);
+/* per-pass trace of a batch created with trace_passes > 0 (waits for `stream`).  For ICP c = plot * n_hyp_local + j and
+ * pass p < min(passes of that ICP, trace_passes), entry t = (c * trace_passes + p) * trace_stride + tree:
+ *   idx_out[t]    original target row of the tree's nearest neighbour (`tree.query`, ficp.py:70; lowest row among ties)
+ *   d2_out[t]     its squared distance (sqrt = the distance ficp.py:70 returns, bit for bit)
+ *   inlier_out[t] 1 iff the tree is in the trimmed subset `argsort(d)[:k]` of that pass (ficp.py:62-63, :133)
+ * and k_out / frmsd_out [c * trace_passes + p] = subset size and FRMSD of the pass (ficp.py:73-86).  NULL = skip. */
+FICP_API int ficp_batch_trace(ficp_batch* b, int32_t* idx_out, double* d2_out, uint8_t* inlier_out, int32_t* k_out,
+                     double* frmsd_out, void* stream);
 FICP_API void ficp_batch_destroy(ficp_batch* b);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ def test_abi_struct_sizes():
     from coregistrationgame_b200 import _lib
     assert _lib.HYP_RESULT_DTYPE.itemsize == 80
     assert C.sizeof(_lib.BatchParams) == 56
-    assert C.sizeof(_lib.BatchInfo) == 72
+    assert C.sizeof(_lib.BatchInfo) == 80
     assert C.sizeof(_lib.TargetInfo) == 88
 
 
