@@ -26,7 +26,8 @@ class TargetInfo(C.Structure):
 class BatchParams(C.Structure):
     _fields_ = [("n_stages", c_i32), ("max_iterations", c_i32), ("allow_reflection", c_i32), ("min_k", c_i32),
                 ("threshold", c_f64), ("window_margin", c_f64), ("warps_per_cta", c_i32), ("ctas_per_sm", c_i32),
-                ("disable_window", c_i32), ("team_warps", c_i32), ("no_helpers", c_i32), ("trace_passes", c_i32)]
+                ("disable_window", c_i32), ("team_warps", c_i32), ("no_helpers", c_i32), ("trace_passes", c_i32),
+                ("cta_per_icp", c_i32), ("reserved", c_i32)]
 
 
 class BatchInfo(C.Structure):
@@ -34,7 +35,7 @@ class BatchInfo(C.Structure):
                 ("match_z", c_i32), ("warps_per_cta", c_i32), ("ctas", c_i32), ("ctas_per_sm", c_i32),
                 ("slices_per_plot", c_i32), ("window_pts_cap", c_i32), ("window_cells_cap", c_i32),
                 ("team_warps", c_i32), ("helpers", c_i32), ("trace_passes", c_i32), ("smem_bytes", c_i64), ("rows", c_i64),
-                ("trace_stride", c_i32), ("reserved", c_i32)]
+                ("trace_stride", c_i32), ("cta_per_icp", c_i32)]
 
 
 # numpy view of ficp_hyp_result

@@ -138,7 +138,7 @@ class IcpBatch:
     def __init__(self, index, sources, hyp_table=None, centres=None, lambda_val=3.0, stage2_lambda=None, n_stages=2,
                  threshold=1e-6, max_iterations=1000, allow_reflection=False, min_k=3, fixed_frac=None,
                  hyp_shard=(0, 1), want_final_xy=False, window_margin=-1.0, warps_per_cta=0, ctas_per_sm=0,
-                 disable_window=False, team_warps=0, helpers=None, trace_passes=0, stream=None):
+                 disable_window=False, team_warps=0, helpers=None, trace_passes=0, cta_per_icp=None, stream=None):
         lib = _lib.load()
         if isinstance(sources, np.ndarray) and sources.ndim == 2:
             sources = [sources]
@@ -180,7 +180,7 @@ class IcpBatch:
         prm = _lib.BatchParams(self.n_stages, int(max_iterations), int(bool(allow_reflection)), int(min_k),
                                float(threshold), float(window_margin), int(warps_per_cta), int(ctas_per_sm),
                                int(bool(disable_window)), int(team_warps), (0 if helpers is None else (2 if helpers else 1)),
-                               int(trace_passes))
+                               int(trace_passes), (0 if cta_per_icp is None else (2 if cta_per_icp else 1)), 0)
         self._h = C.c_void_p()
         _lib.check(lib.ficp_batch_create(index.handle, _lib.ptr(self.src), ld, int(self.match_dims == 3),
                                          _lib.ptr(self.offsets), self.n_plots, _lib.ptr(self.centres),

@@ -500,18 +500,26 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     FICP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int warps = prm->warps_per_cta > 0 ? prm->warps_per_cta : std::min(icp_max_warps(e), 16);
     warps = std::max(1, std::min(warps, icp_max_warps(e)));
+    if (prm->no_helpers < 0 || prm->no_helpers > 2) { set_error("ficp_batch_create: no_helpers must be 0 (auto), 1 (off) or 2 (on)"); return kErrInvalid; }
+    if (prm->cta_per_icp < 0 || prm->cta_per_icp > 2) { set_error("ficp_batch_create: cta_per_icp must be 0 (auto), 1 (off) or 2 (on)"); return kErrInvalid; }
+    const long long n_icps_all = (long long)n_plots * n_hyp_local;
+    // Kernel shape.  One WARP per ICP (icp_persistent.cu) has the higher throughput when the batch fills the machine; a
+    // batch smaller than that is bounded by the serial chain of its longest ICP, and the CTA-per-ICP kernel (icp_team.cu:
+    // every phase of a pass cooperative across 32 e threads) runs that chain several times faster.  Plots of <= 32
+    // trees (e == 1) are one warp either way.  Auto: below kCtaAutoIcpsPerSm ICPs per SM (measured, profiles/r02_summary.md).
+    constexpr long long kCtaAutoIcpsPerSm = 12;
+    const bool cta_mode = (e >= 2) && (prm->cta_per_icp == 2 || (prm->cta_per_icp == 0 && prm->team_warps == 0 && prm->no_helpers == 0 &&
+                                                                 prm->warps_per_cta == 0 && n_icps_all <= kCtaAutoIcpsPerSm * sms));
     // Elastic kernel: warps without an ICP of their own help the ICPs in flight in their CTA.  It pays while the
     // tail (the last ICP of every warp) is a visible share of the launch - measured: 1.7 ICPs per warp slot +8..19 %,
     // 28 per slot -2 % (its one-warp-per-ICP path compiles slightly worse) - so by default it is used below 10 ICPs per
     // warp slot.  `team` = warps per ICP at launch: one, unless the batch is smaller than the machine (fewer ICPs
     // than warp slots) - then each CTA starts with fewer leads than warps and the rest help from the first pass on.
     // Results are bit-identical in every mode.
-    if (prm->no_helpers < 0 || prm->no_helpers > 2) { set_error("ficp_batch_create: no_helpers must be 0 (auto), 1 (off) or 2 (on)"); return kErrInvalid; }
-    const long long n_icps_all = (long long)n_plots * n_hyp_local;
-    const bool elastic = prm->no_helpers == 2 || (prm->no_helpers == 0 && (prm->team_warps > 1 || n_icps_all < 10LL * sms * 16));
+    const bool elastic = !cta_mode && (prm->no_helpers == 2 || (prm->no_helpers == 0 && (prm->team_warps > 1 || n_icps_all < 10LL * sms * 16)));
     int team = prm->team_warps;
     if (team != 0 && team != 1 && team != 2 && team != 4 && team != 8) { set_error("ficp_batch_create: team_warps must be 0 (auto), 1, 2, 4 or 8"); return kErrInvalid; }
-    if (!elastic && team > 1) { set_error("ficp_batch_create: team_warps > 1 needs the elastic kernel (no_helpers = 0)"); return kErrInvalid; }
+    if (!cta_mode && !elastic && team > 1) { set_error("ficp_batch_create: team_warps > 1 needs the elastic kernel (no_helpers = 0)"); return kErrInvalid; }
     if (team == 0) {
         team = 1;
         const long long n_icps = (long long)n_plots * n_hyp_local, slots16 = (long long)sms * 16;
@@ -522,9 +530,13 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
     const int wcap_rows = 256;
     // per-ICP state (distances, neighbours, search list, trim order, slack: 18 B per tree) must leave room for a window
-    while (slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
+    while (!cta_mode && slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
     warps = slots_per_cta * team;
-    const size_t fixed_bytes = icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows);
+    if (cta_mode) { warps = e; team = e; slots_per_cta = 1; }
+    auto smem_of = [&](int wp, int wc) -> size_t {
+        return cta_mode ? icp_team_smem_bytes(e, z3, wp, wc, wcap_rows) : icp_smem_bytes(e, z3, slots_per_cta, wp, wc, wcap_rows);
+    };
+    const size_t fixed_bytes = smem_of(0, 0);
     const size_t per_pt = 16 + (z3 ? 8 : 0), per_cell = 4;
     // bytes left for the window (point records + cell table) with `ctas` CTAs resident per SM
     auto window_bytes = [&](int ctas) -> size_t {
@@ -536,7 +548,9 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         return est <= 32767.0 && (size_t)std::ceil(est) * per_pt + (size_t)cells * per_cell + 64 <= bytes;
     };
     // a window with a modest margin (one ring of cells + a few metres of drift) must fit for the worst plot
-    int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm : std::max(1, std::min(8, 16 / warps));
+    int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm
+                           : cta_mode ? std::max(1, std::min(16, 32 / warps))   // 64 registers per thread: 1024 threads per SM
+                                      : std::max(1, std::min(8, 16 / warps));
     if (prm->ctas_per_sm <= 0) {  // fewer resident CTAs when that is what it takes for the windows to fit on-chip
         auto modest_fits = [&](int ctas) -> bool {
             const size_t bytes = window_bytes(ctas);
@@ -571,10 +585,10 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         }
     }
     const int wcap_cells = (int)need_cells;
-    const size_t smem = icp_smem_bytes(e, z3, slots_per_cta, wcap_pts, wcap_cells, wcap_rows);
+    const size_t smem = smem_of(wcap_pts, wcap_cells);
     if (smem > (size_t)smem_optin) { set_error("ficp_batch_create: shared-memory plan exceeds the device limit"); return kErrTooLarge; }
     int occ = 0;
-    int rc = icp_max_ctas_per_sm(e, z3, warps, elastic, smem, &occ);
+    int rc = cta_mode ? icp_team_max_ctas_per_sm(e, z3, smem, &occ) : icp_max_ctas_per_sm(e, z3, warps, elastic, smem, &occ);
     if (rc) return rc;
     if (occ < 1) { set_error("ficp_batch_create: kernel does not fit on an SM with this configuration"); return kErrTooLarge; }
     const int ctas_per_sm = prm->ctas_per_sm > 0 ? std::min(occ, prm->ctas_per_sm) : occ;
@@ -650,7 +664,8 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     P.trace_cap = b->trace_cap; P.trace_stride = b->trace_stride;
     P.tr_idx = b->d_tr_idx; P.tr_d2 = b->d_tr_d2; P.tr_in = b->d_tr_in; P.tr_k = b->d_tr_k; P.tr_f = b->d_tr_f;
     b->launch.e = e; b->launch.z3 = z3; b->launch.warps = warps; b->launch.slots = slots_per_cta; b->launch.elastic = elastic; b->launch.smem = smem;
-    b->launch.ctas = (int)std::min<long long>(n_slices, resident);
+    b->launch.ctas = (int)std::min<long long>(cta_mode ? n_icps_all : n_slices, resident);
+    b->launch.cta_per_icp = cta_mode;
     b->ctas_per_sm = ctas_per_sm;
     guard.armed = false;
     *out = reinterpret_cast<ficp_batch*>(b);
@@ -665,7 +680,7 @@ int ficp_batch_get_info(const ficp_batch* bh, ficp_batch_info* info) {
     info->ctas = b->launch.ctas; info->ctas_per_sm = b->ctas_per_sm; info->slices_per_plot = b->params.slices_per_plot;
     info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells; info->team_warps = b->launch.warps / b->launch.slots; info->helpers = b->launch.elastic ? 1 : 0;
     info->smem_bytes = (int64_t)b->launch.smem; info->rows = b->rows;
-    info->trace_passes = b->trace_cap; info->trace_stride = b->trace_stride;
+    info->trace_passes = b->trace_cap; info->trace_stride = b->trace_stride; info->cta_per_icp = b->launch.cta_per_icp ? 1 : 0;
     return kOk;
 }
 
@@ -676,7 +691,8 @@ int ficp_batch_run(ficp_batch* bh, void* stream) {
     FICP_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * (size_t)(b->n_plots + 1), s));
     FICP_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(unsigned long long) * 8, s));
     FICP_CUDA(cudaMemsetAsync(b->d_best, 0xFF, sizeof(unsigned long long) * (size_t)b->n_plots, s));
-    const int rc = launch_icp(b->params, b->launch, s);
+    const int rc = b->launch.cta_per_icp ? launch_icp_team(b->params, b->launch.e, b->launch.z3, b->launch.ctas, b->launch.smem, s)
+                                         : launch_icp(b->params, b->launch, s);
     b->used.record(s);
     b->tgt->used.record(s);
     return rc;

@@ -153,9 +153,14 @@ struct IcpLaunch {
     int warps;        // warps per CTA
     int slots;        // lead warps per CTA (= warps unless elastic)
     bool elastic;     // idle warps help the ICPs in flight (icp_kernel<..., true>)
+    bool cta_per_icp; // icp_team_kernel: the whole CTA (32 e threads) works on one ICP
     int ctas;         // grid size
     size_t smem;      // dynamic shared memory per CTA
 };
+// CTA-per-ICP kernel (icp_team.cu): T = 32 e threads work on one ICP
+size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows);
+int icp_team_max_ctas_per_sm(int e, bool z3, size_t smem, int* out);
+int launch_icp_team(const IcpParams& p, int e, bool z3, int ctas, size_t smem, cudaStream_t stream);
 int icp_max_warps(int e);
 size_t icp_smem_bytes(int e, bool z3, int slots, int wcap_pts, int wcap_cells, int wcap_rows);
 int icp_max_ctas_per_sm(int e, bool z3, int warps, bool elastic, size_t smem, int* out);

@@ -32,25 +32,17 @@
 //     from a per-plot counter (dynamic load balance across the whole GPU).
 #include <algorithm>
 #include <climits>
-#include <cuda_fp16.h>
-#include "ficp_internal.h"
-#include "nn_search.cuh"
+#include "icp_shared.cuh"
 
 namespace ficp {
 
 namespace {
-
-constexpr unsigned kFull = 0xFFFFFFFFu;
 
 template <int E>
 struct LaneCfg {
     static constexpr int kNPad = 32 * E;
     static constexpr int kIdxBits = (E == 1) ? 5 : (E == 2) ? 6 : (E == 4) ? 7 : (E == 8) ? 8 : (E == 16) ? 9 : 10;
     static constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
-};
-
-struct Pose {  // q = M u + c ; warp-uniform
-    double m00, m01, m10, m11, cx, cy;
 };
 
 // Elastic mode: what a lead warp publishes for the helper warps of its CTA (warps that have no ICP of their own).
@@ -150,68 +142,6 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned (&key)[E], int lane) 
     }
 }
 
-__device__ __forceinline__ bool key_greater(double da, unsigned ka, double db, unsigned kb) {
-    return (da > db) || (da == db && ka > kb);
-}
-
-struct PassOut {
-    int k;          // trimmed subset size (0: none, like ficp.py:125)
-    double f;       // FRMSD at k
-    double rmse;    // sqrt(S_k / k)
-    double thr;     // d2 of the k-th point in trim order
-    int thr_idx;    // its source index (ties in d2 are ordered by index)
-};
-
-struct PlotCtx {
-    const double2* s_u;
-    const double* s_z;
-    int n;
-    int fixed_k;
-    double ubx, uby;
-};
-
-__device__ __forceinline__ void pose_apply(const Pose& P, const double2 u, double& qx, double& qy) {
-    // same expression, same order, no FMA, as oracle.pre_transform
-    qx = dadd(dadd(dmul(P.m00, u.x), dmul(P.m01, u.y)), P.cx);
-    qy = dadd(dadd(dmul(P.m10, u.x), dmul(P.m11, u.y)), P.cy);
-}
-
-// Global-grid form of the query (window miss): rare, so kept out of line to keep the hot loop small.
-// measured (profiles/r01_variants.md): inlining the rare global-grid / tie / ring paths beats calling them
-#if defined(FICP_NOINLINE_GLOBAL)
-#define FICP_GLOBAL_ATTR __device__ __noinline__
-#else
-#define FICP_GLOBAL_ATTR __device__ __forceinline__
-#endif
-template <bool Z3>
-FICP_GLOBAL_ATTR int nn_query_global(const GridView& G, double qx, double qy, double qz, int prev, double* best_out) {
-    const GlobalAcc ga = make_global_acc(G);
-    double best;
-    int pos;
-    nn_search_stream<Z3>(ga, G.g, qx, qy, qz, prev, best, pos);
-    *best_out = best;
-    return pos;
-}
-
-// Neighbour code of a query (`snn`): -1 = none; bit 31 set = position in the GLOBAL cell-sorted target (the query ran
-// on the global grid); otherwise two window-local positions (< 32768): bits 0-15 the nearest neighbour, bits 16-30 the
-// runner-up of its last search (== the neighbour: none).
-__device__ __forceinline__ int code_pack(int pos, int pos2) {
-    return (pos < 0) ? -1 : (pos | (((pos2 < 0) ? pos : pos2) << 16));
-}
-__device__ __forceinline__ int code_win(int code) { return (code < 0) ? -1 : (code & 0xFFFF); }
-
-__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-
-// A warp-uniform view of a shared word that other warps change: ONE lane reads, everybody gets that value.  (Every lane
-// reading for itself can split the warp on a loop or branch condition when the lanes are not converged at the load.)
-__device__ __forceinline__ int ld_volatile_uniform(const int* p, int lane) {
-    __syncwarp();
-    int v = 0;
-    if (lane == 0) v = ld_volatile(p);
-    return __shfl_sync(kFull, v, 0);
-}
-
 // Hand out the next work unit of a slot's epoch in flight: -1 when none is left (or the slot is closed).
 __device__ __forceinline__ int grab_unit(SlotCtrl* c, int lane) {
     int e = -1;
@@ -254,141 +184,6 @@ __device__ __forceinline__ void unit_done(SlotCtrl* c, int lane) {
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicAdd(&c->done, 1);
-}
-
-// 32 entries of the deferred list: rings >= 2 inside the window, or the whole query on the global grid.
-template <bool Z3, bool ELASTIC>
-__device__ __forceinline__ void nn_deferred_chunk(const GridView& G, const WindowAcc& W, const PlotCtx& pc, const Pose& P,
-                                                  double* __restrict__ sd2, int* __restrict__ snn,
-                                                  const unsigned short* __restrict__ sord, int base, int n_def,
-                                                  int lane, unsigned& n_global) {
-    if (base + lane < n_def) {
-        const int d = sord[base + lane];
-        const int i = d & 0x7FFF;
-        FICP_ASSERT(i < pc.n);
-        double qx, qy;
-        pose_apply(P, pc.s_u[i], qx, qy);
-        const double qz = Z3 ? pc.s_z[i] : 0.0;
-        double best = kInf;
-        int pos = -1;
-        bool ok = false;
-        if (!(d & 0x8000)) {
-            best = ELASTIC ? fabs(sd2[i]) : sd2[i];
-            pos = code_win(snn[i]);
-            const int cx = clamp_cell((qx - G.g.x0) * G.g.inv_h, G.g.gw);
-            const int cy = clamp_cell((qy - G.g.y0) * G.g.inv_h, G.g.gh);
-            ok = nn_ring_loop_impl<Z3>(W, G.g, qx, qy, qz, cx, cy, 2, best, pos);
-        }
-        int code = code_pack(pos, -1);
-        if (!ok) {
-            // window miss: whole query on the global grid, seeded with the best candidate known so far
-            const int seed = snn[i];
-            const int gprev = (seed == -1) ? -1 : (seed >= 0 ? W.global_pos(seed & 0xFFFF) : (seed & 0x7FFFFFFF));
-            pos = nn_query_global<Z3>(G, qx, qy, qz, gprev, &best);
-            code = (int)((unsigned)pos | 0x80000000u);
-            ++n_global;
-        }
-        sd2[i] = best;
-        snn[i] = code;
-    }
-}
-
-// One round of nearest-neighbour queries: the 32 queries at positions 32e..32e+31 of the PREVIOUS pass's trim order
-// (identity on the first pass): neighbours in that order have similar residuals, hence similar search radii and
-// candidate counts, so the lanes of a warp finish together and the rare wide searches (ring >= 2) fall into the same
-// rounds.  Queries whose 3x3 block does not settle the search (wide search radius, or the block is not inside the
-// shared-memory window) are NOT finished inline - a handful of lanes would drag the whole warp through the ring loop
-// in almost every round - they are returned as `defer` (point index | 0x8000 if it must run on the global grid) and
-// finished afterwards with all lanes busy.  MARK: also flag them in the sign bit of sd2 (-best: in-window candidate
-// known, -inf: nothing known) for rounds that complete out of order.
-template <bool Z3, bool MARK>
-__device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, bool win_ok, const PlotCtx& pc,
-                                        const Pose& P, double* __restrict__ sd2, int* __restrict__ snn,
-                                        __half* __restrict__ ssl, const unsigned short* __restrict__ sord, int e,
-                                        int count, int lane, bool have_prev) {
-    const int p = e * 32 + lane;
-    int defer = -1;
-    if (p < count) {
-        const int i = sord[p];
-        FICP_ASSERT(i >= 0 && i < pc.n);
-        double qx, qy;
-        pose_apply(P, pc.s_u[i], qx, qy);
-        const double qz = Z3 ? pc.s_z[i] : 0.0;
-        // seed with the neighbour found by the previous pass of this hypothesis (same index space only)
-        const int pc_prev = have_prev ? code_win(snn[i]) : -1;
-        double best = kInf;
-        int pos = -1, cx, cy;
-        bool ok = false;
-        int lb_hi = kHiInf, pos2 = -1;
-        if (win_ok) ok = nn_search_block3_impl<Z3, true>(W, G.g, qx, qy, qz, pc_prev, best, pos, cx, cy, lb_hi, pos2);
-        float slack = 0.f;  // deferred / global-grid queries carry no bound: they are searched again next pass
-        if (ok) {
-            snn[i] = code_pack(pos, pos2);
-            const double border2 = nn_block_border2(G.g, qx, qy, cx, cy, 1);
-            if ((border2 == kInf) || best < border2) {   // == nn_block_settles
-                // every target point other than the winner and the runner-up is at least sqrt(lb2) away (third-best
-                // streamed, pruned cells of the block, the block's border): rounded DOWN at every step
-                const double lb2 = fmin(hi_to_double(lb_hi), border2);
-                slack = fminf(__fsqrt_rd(__double2float_rd(lb2)), 60000.f);
-            } else {
-                defer = i;
-                if (MARK) best = -best;
-            }
-            sd2[i] = best;
-        } else {
-            if (!have_prev) snn[i] = -1;  // keep the previous pass's code as the seed of the deferred query
-            if (MARK) sd2[i] = -kInf;
-            defer = i | 0x8000;
-        }
-        ssl[i] = __float2half_rd(slack);
-    }
-    return defer;
-}
-
-// Skip test of one round of 32 queries (i = 32e + lane), passes after the first.  `D` = pose of this pass minus the
-// pose of the previous pass.  The query moved by |D.M u + D.c| (+ rounding of the two positions, `1e-14 |q|` is
-// 50x what they can differ by); every point other than the winner and the runner-up of the query's last search is
-// therefore still at least slack - move away (triangle inequality; in 3-D too, Z does not move).  If the smaller of
-// their two distances - evaluated in the canonical arithmetic, it is the value the full search would return - is
-// below that, that point is the unique nearest neighbour: no tie, nothing to search.  All roundings are directed against passing.  Returns the point
-// index if the query must be searched, -1 if it is settled.
-template <bool Z3>
-__device__ __forceinline__ int nn_test_round(const WindowAcc& W, const PlotCtx& pc, const Pose& P, const Pose& D,
-                                             double* __restrict__ sd2, int* __restrict__ snn,
-                                             __half* __restrict__ ssl, int e, int lane) {
-    const int i = e * 32 + lane;
-    int need = -1;
-    if (i < pc.n) {
-        need = i;
-        const int code = snn[i];
-        const float s0 = __half2float(ssl[i]);
-        if (code >= 0 && s0 > 0.f) {
-            const double2 u = pc.s_u[i];
-            const double ex = D.m00 * u.x + D.m01 * u.y + D.cx;
-            const double ey = D.m10 * u.x + D.m11 * u.y + D.cy;
-            const double pad = 1e-14 * ((fabs(P.cx) + fabs(P.cy)) + (fabs(u.x) + fabs(u.y)));
-            const float move = __fadd_ru(__fsqrt_ru(__double2float_ru(ex * ex + ey * ey)), __double2float_ru(pad));
-            const float s1 = __fmul_rd(__fsub_rd(s0, move), 0.99999904632568359375f);  // (1 - 2^-20): rounding of d2
-            const __half sh = __float2half_rd(fmaxf(s1, 0.f));
-            ssl[i] = sh;
-            const float s = __half2float(sh);
-            double qx, qy;
-            pose_apply(P, u, qx, qy);
-            const double qz = Z3 ? pc.s_z[i] : 0.0;
-            const int p1 = code & 0xFFFF, p2 = code >> 16;
-            const double d1 = nn_dist2<Z3>(W, p1, qx, qy, qz);
-            const double dr = nn_dist2<Z3>(W, p2, qx, qy, qz);   // p2 == p1 when there is no runner-up
-            const bool swap = dr < d1;
-            const double dmin = swap ? dr : d1;
-            // an exact tie between the two is left to the search (lowest original index wins there)
-            if (dmin < (double)s * (double)s && (p2 == p1 || d1 != dr)) {
-                sd2[i] = dmin;
-                if (swap) snn[i] = p2 | (p1 << 16);
-                need = -1;
-            }
-        }
-    }
-    return need;
 }
 
 // Everything a warp needs to work on the plot staged in this CTA, rebuilt from the kernel parameters and the plot's
@@ -742,16 +537,16 @@ __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const doubl
     return out;
 }
 
-// Closed-form rigid fit on the trimmed subset and composition into the pose.
+// Closed-form rigid fit on the trimmed subset and composition into the pose (arithmetic: icp_shared.cuh).
 template <int E, bool Z3>
 __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, const PlotCtx& pc, Pose& P, Pose& D,
                                         const PassOut& po, const double* __restrict__ sd2,
                                         const int* __restrict__ snn, int lane, int allow_reflection) {
     const int n = pc.n;
     // shift point: the plot centroid under the current pose (keeps the running sums well conditioned)
-    const double ax = P.m00 * pc.ubx + P.m01 * pc.uby + P.cx;
-    const double ay = P.m10 * pc.ubx + P.m11 * pc.uby + P.cy;
-    double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0, habs = 0;
+    double ax, ay;
+    fit_shift(P, pc.ubx, pc.uby, ax, ay);
+    FitSums s = fit_zero();
 #pragma unroll 2
     for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
@@ -762,52 +557,13 @@ __device__ __forceinline__ void icp_fit(const GridView& G, const WindowAcc& W, c
                 pose_apply(P, pc.s_u[i], qx, qy);
                 const int code = snn[i];
                 FICP_ASSERT(code != -1 && ((code < 0) ? ((code & 0x7FFFFFFF) < G.m) : ((code & 0xFFFF) < W.rowoff[W.wh])));
-                const double2 t = (code < 0) ? grid_xy(G, code & 0x7FFFFFFF) : W.xy[code & 0xFFFF];
-                const double ux = qx - ax, uy = qy - ay, vx = t.x - ax, vy = t.y - ay;
-                su0 += ux; su1 += uy; sv0 += vx; sv1 += vy;
-                h00 += ux * vx; h01 += ux * vy; h10 += uy * vx; h11 += uy * vy;
-                habs += (fabs(ux) + fabs(uy)) * (fabs(vx) + fabs(vy));  // magnitude of the terms (noise scale)
+                const double2 t = corr_xy(G, W, code);
+                fit_term(s, qx, qy, t.x, t.y, ax, ay);
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        habs += __shfl_xor_sync(kFull, habs, o);
-        su0 += __shfl_xor_sync(kFull, su0, o); su1 += __shfl_xor_sync(kFull, su1, o);
-        sv0 += __shfl_xor_sync(kFull, sv0, o); sv1 += __shfl_xor_sync(kFull, sv1, o);
-        h00 += __shfl_xor_sync(kFull, h00, o); h01 += __shfl_xor_sync(kFull, h01, o);
-        h10 += __shfl_xor_sync(kFull, h10, o); h11 += __shfl_xor_sync(kFull, h11, o);
-    }
-    const double inv_k = 1.0 / (double)po.k;
-    const double mu0 = su0 * inv_k, mu1 = su1 * inv_k, mv0 = sv0 * inv_k, mv1 = sv1 * inv_k;
-    // centred cross-covariance H = sum (u - mu)(v - mv)^T, from the shifted sums.  When the exact H is zero
-    // (k == 1, or all inlier trees coincide - the reference's centred sums are then exactly 0 and its SVD
-    // returns R = I) the subtraction below leaves only rounding noise, of the order 1e-16 * sum |u||v|: detect
-    // that (against the magnitude sum `habs`, not the signed sums, which may cancel too) and use H = 0.
-    h00 -= su0 * mv0; h01 -= su0 * mv1; h10 -= su1 * mv0; h11 -= su1 * mv1;
-    if (fabs(h00) + fabs(h01) + fabs(h10) + fabs(h11) <= 1e-12 * habs) h00 = h01 = h10 = h11 = 0.0;
-    double r00, r01, r10, r11;
-    // reflection only when det(H) is negative beyond rounding noise (det == 0: SVD's choice is arbitrary)
-    if (allow_reflection && (h00 * h11 - h01 * h10) < -1e-14 * (fabs(h00 * h11) + fabs(h01 * h10))) {
-        const double a = h00 - h11, b = h01 + h10, nrm = sqrt(a * a + b * b);
-        const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
-        r00 = c; r01 = s; r10 = s; r11 = -c;
-    } else {
-        const double a = h00 + h11, b = h01 - h10, nrm = sqrt(a * a + b * b);
-        const double c = (nrm == 0.0) ? 1.0 : a / nrm, s = (nrm == 0.0) ? 0.0 : b / nrm;
-        r00 = c; r01 = -s; r10 = s; r11 = c;
-    }
-    // q' = R (q - a - mu) + a + mv   with q = M u + c   ->   M' = R M ;  c' = R (c - a - mu) + a + mv
-    const double ex = P.cx - ax - mu0, ey = P.cy - ay - mu1;
-    Pose Q;
-    Q.m00 = r00 * P.m00 + r01 * P.m10; Q.m01 = r00 * P.m01 + r01 * P.m11;
-    Q.m10 = r10 * P.m00 + r11 * P.m10; Q.m11 = r10 * P.m01 + r11 * P.m11;
-    Q.cx = (r00 * ex + r01 * ey) + (ax + mv0);
-    Q.cy = (r10 * ex + r11 * ey) + (ay + mv1);
-    // pose update of this fit, for the next pass's skip test
-    D.m00 = Q.m00 - P.m00; D.m01 = Q.m01 - P.m01; D.m10 = Q.m10 - P.m10; D.m11 = Q.m11 - P.m11;
-    D.cx = Q.cx - P.cx; D.cy = Q.cy - P.cy;
-    P = Q;
+    fit_reduce(s);
+    fit_solve(s, po.k, allow_reflection, ax, ay, P, D);
 }
 
 template <int E, bool Z3, int NT, bool ELASTIC>

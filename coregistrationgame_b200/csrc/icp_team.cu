@@ -1,0 +1,522 @@
+// Kernel 4b: the two-stage Fractional ICP loop with ONE CTA PER ICP - the latency shape of the persistent kernel.
+//
+//   run()/_iterate()             /root/reference/ficp.py:122-154   -> team_run_icp
+//   find_correspondences          ficp.py:65-71                     -> skip test + search, one tree per thread
+//   find_optimal_fraction, frmsd  ficp.py:54-60,73-86               -> block bitonic sort + canonical scan + block arg-min
+//   get_n_first_elements          ficp.py:62-63                     -> (d2, index) threshold of the k-th element
+//   compute_optimal_transform_2d  ficp.py:89-110                    -> fit_term / fit_reduce / fit_solve (icp_shared.cuh)
+//
+// Why it exists (DESIGN.md "strong scaling"): in icp_persistent.cu one warp owns an ICP, so a batch smaller than the
+// machine - the literal BASELINE config 3, ONE stand x 4096 start poses, sharded over 8 GPUs = 512 ICPs per GPU for
+// 2368 warp slots - is bounded by the serial chain of its longest hypothesis (115 passes x ~20 us per pass = 2.4 ms
+// measured, 1.83x at 8 GPUs).  Here a whole CTA of T = 32 E threads (one tree per thread, 512 threads for the 500-tree
+// stand) works on one ICP and EVERY phase of a pass is cooperative:
+//   * skip test: one tree per thread; the trees that fail it are ballot-compacted into the search list;
+//   * search: one list entry per thread (first pass: every tree), deferred queries re-compacted and finished in
+//     chunks of 32 by all warps;
+//   * trimming: block bitonic sort of 64-bit keys (d2 bits | tree index) - register shuffles for strides < 32,
+//     double-buffered shared-memory exchanges above - verified against the exact (d2, index) order;
+//   * prefix sums of d2 in the association of the one-warp kernel (serial inside chunks of E, Kogge-Stone across
+//     the 32 chunks), FRMSD filter and exact arg-min as block reductions (min is order-free);
+//   * fit: every thread prepares its tree's term, warp 0 adds them in the one-warp kernel's order.
+// The results are BIT-IDENTICAL to icp_persistent.cu (shared arithmetic in icp_shared.cuh; the skip test and search
+// bookkeeping only decide whether a query is searched, never its result).  All warps of the CTA are in the same phase,
+// so the instruction-cache thrash of 16 independent warps (the top stall of the one-warp kernel) does not occur.
+#include <algorithm>
+#include <climits>
+#include "icp_shared.cuh"
+
+namespace ficp {
+
+namespace {
+
+struct TeamLayout {
+    size_t s_u, s_z, s_g, w_xy, w_z, w_cell, rowoff, rowdelta, rowg, sd2, snn, ssl, list, dlist, sidx, kbuf, sdd, tmp, misc, total;
+};
+__host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
+    TeamLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+    L.s_u = take((size_t)t * 16);
+    L.s_z = take(z3 ? (size_t)t * 8 : 0);
+    L.s_g = take((size_t)kMaxStages * t * 8);
+    L.w_xy = take((size_t)wcap_pts * 16);
+    L.w_z = take(z3 ? (size_t)wcap_pts * 8 : 0);
+    L.w_cell = take((size_t)wcap_cells * 4);
+    L.rowoff = take((size_t)(wcap_rows + 1) * 4);
+    L.rowdelta = take((size_t)wcap_rows * 4);
+    L.rowg = take((size_t)wcap_rows * 4);
+    L.sd2 = take((size_t)t * 8);
+    L.snn = take((size_t)t * 4);
+    L.ssl = take((size_t)t * 2);
+    L.list = take((size_t)t * 2);
+    L.dlist = take((size_t)t * 2);
+    L.sidx = take((size_t)t * 2);
+    L.kbuf = take((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms qx, qy
+    L.sdd = take((size_t)t * 8);     // d2 in trim order; later the fit term tx
+    L.tmp = take((size_t)t * 8);     // fit term ty
+    L.misc = take(1536);
+    L.total = o;
+    return L;
+}
+
+// small per-CTA scratch (inside TeamLayout::misc)
+struct TeamMisc {
+    double stot[32], sexcl[32];     // chunk totals / exclusive prefixes of the canonical scan
+    double red_a[32], red_b[32];    // block reductions
+    int red_k[32];
+    double pose[12];                // new pose + pose update, broadcast by warp 0
+    double sk;                      // S at the chosen k (fixed-fraction mode)
+    int nlist, ndef, nglob, icp, win_ok, pad;
+};
+static_assert(sizeof(TeamMisc) <= 1536, "TeamMisc must fit its reservation");
+
+// Block bitonic sort, one 64-bit key per thread, ascending in thread order.  Strides below 32 exchange through
+// shuffles; larger strides through two alternating shared-memory buffers (one barrier per step).
+template <int T>
+__device__ __forceinline__ unsigned long long block_sort64(unsigned long long key, unsigned long long* buf, int tid) {
+    int flip = 0;
+#pragma unroll 1
+    for (int k = 2; k <= T; k <<= 1) {
+        const bool up = ((tid & k) == 0) || (k == T);
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long other;
+            if (j >= 32) {
+                unsigned long long* b = buf + flip * T;
+                b[tid] = key;
+                __syncthreads();
+                other = b[tid ^ j];
+                flip ^= 1;
+            } else {
+                other = __shfl_xor_sync(kFull, key, j);
+            }
+            const bool lower = ((tid & j) == 0);
+            const unsigned long long mn = (key < other) ? key : other, mx = (key < other) ? other : key;
+            key = (lower == up) ? mn : mx;
+        }
+    }
+    return key;
+}
+
+template <bool Z3, int T>
+__global__ void __launch_bounds__(T, (T >= 1024) ? 1 : (T == 512) ? 2 : (T == 256) ? 4 : (T == 128) ? 8 : 16)
+icp_team_kernel(const __grid_constant__ IcpParams P) {
+    constexpr int E = T / 32;
+    constexpr int NW = T / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TeamLayout L = team_layout(T, Z3, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    double2* s_u = reinterpret_cast<double2*>(smem + L.s_u);
+    double* s_z = reinterpret_cast<double*>(smem + L.s_z);
+    double* s_g = reinterpret_cast<double*>(smem + L.s_g);
+    double2* w_xy = reinterpret_cast<double2*>(smem + L.w_xy);
+    double* w_z = reinterpret_cast<double*>(smem + L.w_z);
+    unsigned* w_cell = reinterpret_cast<unsigned*>(smem + L.w_cell);
+    int* rowoff = reinterpret_cast<int*>(smem + L.rowoff);
+    int* rowdelta = reinterpret_cast<int*>(smem + L.rowdelta);
+    int* rowg = reinterpret_cast<int*>(smem + L.rowg);
+    double* sd2 = reinterpret_cast<double*>(smem + L.sd2);
+    int* snn = reinterpret_cast<int*>(smem + L.snn);
+    __half* ssl = reinterpret_cast<__half*>(smem + L.ssl);
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + L.list);
+    unsigned short* dlist = reinterpret_cast<unsigned short*>(smem + L.dlist);
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(smem + L.sidx);
+    unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem + L.kbuf);
+    double* sdd = reinterpret_cast<double*>(smem + L.sdd);
+    double* f_qx = reinterpret_cast<double*>(smem + L.kbuf);          // fit terms alias the (dead) sort buffers
+    double* f_qy = reinterpret_cast<double*>(smem + L.kbuf) + T;
+    double* f_tx = reinterpret_cast<double*>(smem + L.sdd);
+    double* f_ty = reinterpret_cast<double*>(smem + L.tmp);
+    TeamMisc* M = reinterpret_cast<TeamMisc*>(smem + L.misc);
+
+    const GridView& G = P.grid;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long n_icps = (long long)P.n_plots * P.n_hyp_local;
+    int staged_plot = -1;
+    unsigned long long acc_passes = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0, acc_deferred = 0;
+    unsigned n_global = 0;   // per thread
+
+    for (;;) {
+        __syncthreads();   // everyone is done with the previous ICP (and with M->icp)
+        if (tid == 0) M->icp = atomicAdd(P.slice_counter, 1);
+        __syncthreads();
+        const int c = M->icp;
+        if (c >= n_icps) break;
+        const int plot = c / P.n_hyp_local, j = c - plot * P.n_hyp_local;
+        const PlotMeta pm = P.plots[plot];
+
+        if (plot != staged_plot) {
+            // ---- stage the plot: source rows, weight tables, window of grid cells (as in icp_persistent.cu) ----
+            s_u[tid] = (tid < pm.n) ? P.src_u[pm.off + tid] : make_double2(0.0, 0.0);
+            if (Z3) s_z[tid] = (tid < pm.n) ? P.src_z[pm.off + tid] : 0.0;
+            const double* tab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;
+            for (int i = tid; i < P.n_stages * T; i += T) s_g[i] = tab[(size_t)(i / T) * 2 * T + (i % T)];
+            const int ww = pm.wx1 - pm.wx0, wh = pm.wy1 - pm.wy0;
+            bool ok = (ww > 0 && wh > 0 && (long long)ww * wh <= P.wcap_cells && wh <= P.wcap_rows && G.m > 0);
+            if (ok) {
+                for (int r = tid; r < wh; r += T) {
+                    const size_t rowbase = (size_t)(pm.wy0 + r) * G.g.gw;
+                    const unsigned gs = G.cell_start[rowbase + pm.wx0], ge = G.cell_start[rowbase + pm.wx1];
+                    rowg[r] = (int)gs;
+                    rowdelta[r] = (int)(ge - gs);  // temporarily: the row's point count
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (ok) {
+                    int o = 0;
+                    for (int r = 0; r < wh; ++r) {
+                        const int cnt = rowdelta[r];
+                        rowoff[r] = o;
+                        rowdelta[r] = rowg[r] - o;
+                        o += cnt;
+                    }
+                    rowoff[wh] = o;
+                    if (o > P.wcap_pts || o > 32767) ok = false;  // window positions are packed in 15 bits
+                }
+                M->win_ok = ok ? 1 : 0;
+                if (!ok) atomicAdd(P.stats + 2, 1ull);
+            }
+            __syncthreads();
+            ok = (M->win_ok != 0);
+            if (ok) {
+                for (int cc = tid; cc < ww * wh; cc += T) {
+                    const int r = cc / ww, col = cc - r * ww;
+                    const size_t g = (size_t)(pm.wy0 + r) * G.g.gw + pm.wx0 + col;
+                    const unsigned a = G.cell_start[g], b = G.cell_start[g + 1];
+                    w_cell[cc] = (unsigned)(rowoff[r] + (int)(a - (unsigned)rowg[r])) | ((b - a) << 16);
+                }
+                for (int r = warp; r < wh; r += NW) {
+                    const int cnt = rowoff[r + 1] - rowoff[r], gs = rowg[r], lo = rowoff[r];
+                    for (int q = lane; q < cnt; q += 32) {
+                        w_xy[lo + q] = grid_xy(G, gs + q);
+                        if (Z3) w_z[lo + q] = grid_z(G, gs + q);
+                    }
+                }
+            }
+            staged_plot = plot;
+            __syncthreads();
+        }
+        const bool win_ok = (M->win_ok != 0);
+        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G.orig, G.rec,
+                          pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0};
+        const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
+        const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;  // [stage][0]=g [stage][1]=c
+        const int n = pm.n;
+
+        // ---- one ICP: start pose of hypothesis h (the expression of icp_persistent.cu / oracle.pre_transform)
+        const int h = P.hyp_begin + j * P.hyp_stride;
+        const double* hr = P.hyp + (size_t)h * 6;
+        Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
+        Pose dpose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int passes = 0;
+        unsigned n_fix = 0, n_searched = 0, n_deferred = 0;
+        if (tid >= n) { sd2[tid] = kInf; snn[tid] = -1; }   // padding never changes
+        PassOut po{0, kInf, 0.0, -1.0, -1};
+        // position of this thread in trim order: chunk (= lane of the one-warp kernel) and element inside it
+        const int lp = tid / E, r = tid - lp * E;
+
+        for (int st = 0; st < P.n_stages; ++st) {
+            const double* sg = s_g + (size_t)st * T;
+            const double* gc = g_ctab + ((size_t)st * 2 + 1) * T;
+            double cur = 0.0;
+            int it = 0;
+            bool first = true;
+            for (;;) {
+                // ================= nearest neighbours (ficp.py:65-71)
+                const bool have_prev = passes > 0;
+                if (tid == 0) { M->nlist = have_prev ? 0 : n; M->ndef = 0; }
+                __syncthreads();
+                if (have_prev) {
+                    const int need = nn_test_round<Z3>(W, pc, pose, dpose, sd2, snn, ssl, warp, lane);
+                    const unsigned m = __ballot_sync(kFull, need >= 0);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&M->nlist, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (need >= 0) list[base + __popc(m & lt_mask)] = (unsigned short)need;
+                } else {
+                    list[tid] = (unsigned short)tid;
+                }
+                __syncthreads();
+                const int n_list = M->nlist;
+                {
+                    const int defer = (warp * 32 < n_list)
+                                          ? nn_round<Z3, false>(G, W, win_ok, pc, pose, sd2, snn, ssl, list, warp, n_list, lane, have_prev)
+                                          : -1;
+                    const unsigned m = __ballot_sync(kFull, defer >= 0);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&M->ndef, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (defer >= 0) dlist[base + __popc(m & lt_mask)] = (unsigned short)defer;
+                }
+                __syncthreads();
+                const int n_def = M->ndef;
+                for (int base = warp * 32; base < n_def; base += NW * 32)
+                    nn_deferred_chunk<Z3, false>(G, W, pc, pose, sd2, snn, dlist, base, n_def, lane, n_global);
+                n_searched += (unsigned)n_list;
+                n_deferred += (unsigned)n_def;
+                dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
+                __syncthreads();
+
+                // ================= trimming (ficp.py:62-63,73-86)
+                const double my_d2 = sd2[tid];
+                unsigned long long key = ((unsigned long long)__double_as_longlong(my_d2) & ~0x3FFull) | (unsigned)tid;
+                key = block_sort64<T>(key, kbuf, tid);
+                int sidx_t = (int)(key & 0x3FFull);
+                double dd = sd2[sidx_t];
+                sdd[tid] = dd;
+                sidx[tid] = (unsigned short)sidx_t;
+                __syncthreads();
+                {
+                    // the key drops the low 10 bits of d2: verify the exact (d2, index) order, repair if needed (rare)
+                    bool inv = false;
+                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[tid + 1], (unsigned)sidx[tid + 1]);
+                    if (__syncthreads_or(inv)) {
+                        ++n_fix;
+                        bool sw;
+                        do {
+                            sw = false;
+#pragma unroll 1
+                            for (int par = 0; par < 2; ++par) {
+                                if ((tid & 1) == par && tid + 1 < T) {
+                                    const double a = sdd[tid], b = sdd[tid + 1];
+                                    const unsigned short ia = sidx[tid], ib = sidx[tid + 1];
+                                    if (key_greater(a, ia, b, ib)) {
+                                        sdd[tid] = b; sdd[tid + 1] = a; sidx[tid] = ib; sidx[tid + 1] = ia;
+                                        sw = true;
+                                    }
+                                }
+                                __syncthreads();
+                            }
+                        } while (__syncthreads_or(sw));
+                        dd = sdd[tid];
+                        sidx_t = sidx[tid];
+                    }
+                }
+                // inclusive prefix sums S_k of d2 in trim order, in the association of the one-warp kernel: serial
+                // inside the chunk of E consecutive positions, Kogge-Stone over the 32 chunk totals, prefix + partial
+                double run = 0.0;
+                {
+                    const double* chunk = sdd + lp * E;
+#pragma unroll 1
+                    for (int q = 0; q <= r; ++q) run = __dadd_rn(run, chunk[q]);
+                }
+                if (r == E - 1) M->stot[lp] = run;
+                __syncthreads();
+                if (warp == 0) {
+                    double inc = M->stot[lane];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_up_sync(kFull, inc, o);
+                        if (lane >= o) inc = __dadd_rn(inc, t);
+                    }
+                    double excl = __shfl_up_sync(kFull, inc, 1);
+                    if (lane == 0) excl = 0.0;
+                    M->sexcl[lane] = excl;
+                }
+                __syncthreads();
+                const double S = __dadd_rn(M->sexcl[lp], run);
+
+                // subset size: first strict minimum of FRMSD(k) = c_k sqrt(S_k / k)  (ficp.py:80-85)
+                int kstar;
+                double fstar = kInf, rstar = 0.0;
+                if (pc.fixed_k > 0) {
+                    kstar = pc.fixed_k;
+                    if (tid == kstar - 1) M->sk = S;
+                } else {
+                    // filter with G(k) = S_k (c_k^2 / k), exact expression only within rounding distance of the minimum
+                    const double g = (tid < n) ? __dmul_rn(S, sg[r * 32 + lp]) : kInf;
+                    double gb = g;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) gb = fmin(gb, __shfl_xor_sync(kFull, gb, o));
+                    if (lane == 0) M->red_a[warp] = gb;
+                    __syncthreads();
+                    double gbest = M->red_a[0];
+#pragma unroll
+                    for (int w = 1; w < NW; ++w) gbest = fmin(gbest, M->red_a[w]);
+                    const double gthr = gbest * (1.0 + 1e-12);
+                    int kb = INT_MAX;
+                    if (tid < n && g <= gthr) {
+                        const int k = tid + 1;
+                        const double rm = sqrt(S / (double)k);
+                        fstar = __dmul_rn(__ldg(gc + r * 32 + lp), rm);
+                        kb = k;
+                        rstar = rm;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double of = __shfl_xor_sync(kFull, fstar, o);
+                        const int ok = __shfl_xor_sync(kFull, kb, o);
+                        const double orr = __shfl_xor_sync(kFull, rstar, o);
+                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
+                    }
+                    if (lane == 0) { M->red_b[warp] = fstar; M->red_k[warp] = kb; M->stot[warp] = rstar; }
+                    __syncthreads();
+                    fstar = M->red_b[0]; kb = M->red_k[0]; rstar = M->stot[0];
+#pragma unroll
+                    for (int w = 1; w < NW; ++w) {
+                        const double of = M->red_b[w];
+                        const int ok = M->red_k[w];
+                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = M->stot[w]; }
+                    }
+                    kstar = (kb == INT_MAX) ? 0 : kb;
+                }
+                po.k = kstar;
+                if (kstar == 0) {
+                    po.f = kInf; po.rmse = 0.0; po.thr = -1.0; po.thr_idx = -1;
+                } else {
+                    po.thr_idx = sidx[kstar - 1];
+                    po.thr = sd2[po.thr_idx];
+                    if (pc.fixed_k > 0) {
+                        __syncthreads();
+                        const int pstar = kstar - 1, lstar = pstar / E, rsel = pstar - lstar * E;
+                        rstar = sqrt(M->sk / (double)kstar);
+                        fstar = __dmul_rn(__ldg(gc + rsel * 32 + lstar), rstar);
+                    }
+                    po.f = fstar;
+                    po.rmse = rstar;
+                }
+                if (P.trace_cap > 0 && passes < P.trace_cap && tid < n) {
+                    // per-pass trace (tests only): original target row, squared distance, membership in the trimmed subset
+                    const size_t rec = (size_t)c * P.trace_cap + passes, base = rec * P.trace_stride;
+                    const int code = snn[tid];
+                    int orig = -1;
+                    if (code != -1) orig = grid_orig(G, (code < 0) ? (code & 0x7FFFFFFF) : W.global_pos(code & 0xFFFF));
+                    P.tr_idx[base + tid] = orig;
+                    P.tr_d2[base + tid] = my_d2;
+                    P.tr_in[base + tid] = (po.k > 0 && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) ? 1 : 0;
+                    if (tid == 0) { P.tr_k[rec] = po.k; P.tr_f[rec] = po.f; }
+                }
+                ++passes;
+
+                // ================= stage logic (ficp.py:122-147)
+                if (first) {
+                    if (po.k == 0) break;  // ficp.py:125-126
+                    cur = po.f;
+                    first = false;
+                } else {
+                    if (cur - po.f <= P.threshold) break;  // also stops on a regression, keeping the pose (ficp.py:142)
+                    cur = po.f;
+                    ++it;
+                }
+                if (it >= P.max_iter) break;
+
+                // ================= rigid fit (ficp.py:89-110): terms by every thread, summed by warp 0 in lane order
+                double ax, ay;
+                fit_shift(pose, pc.ubx, pc.uby, ax, ay);
+                __syncthreads();   // the sort buffers / sdd are dead from here: they take the fit terms
+                if (tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) {
+                    double qx, qy;
+                    pose_apply(pose, s_u[tid], qx, qy);
+                    const double2 t = corr_xy(G, W, snn[tid]);
+                    f_qx[tid] = qx; f_qy[tid] = qy; f_tx[tid] = t.x; f_ty[tid] = t.y;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    FitSums s = fit_zero();
+#pragma unroll 2
+                    for (int e = 0; e < E; ++e) {
+                        const int i = e * 32 + lane;
+                        if (i < n) {
+                            const double d2 = sd2[i];
+                            if (d2 < po.thr || (d2 == po.thr && i <= po.thr_idx))
+                                fit_term(s, f_qx[i], f_qy[i], f_tx[i], f_ty[i], ax, ay);
+                        }
+                    }
+                    fit_reduce(s);
+                    Pose np = pose, nd;
+                    fit_solve(s, po.k, P.allow_reflection, ax, ay, np, nd);
+                    if (lane == 0) {
+                        M->pose[0] = np.m00; M->pose[1] = np.m01; M->pose[2] = np.m10; M->pose[3] = np.m11;
+                        M->pose[4] = np.cx; M->pose[5] = np.cy;
+                        M->pose[6] = nd.m00; M->pose[7] = nd.m01; M->pose[8] = nd.m10; M->pose[9] = nd.m11;
+                        M->pose[10] = nd.cx; M->pose[11] = nd.cy;
+                    }
+                }
+                __syncthreads();
+                pose = Pose{M->pose[0], M->pose[1], M->pose[2], M->pose[3], M->pose[4], M->pose[5]};
+                dpose = Pose{M->pose[6], M->pose[7], M->pose[8], M->pose[9], M->pose[10], M->pose[11]};
+            }
+        }
+
+        // ---- results (same record as icp_persistent.cu)
+        if (tid == 0) M->nglob = 0;
+        __syncthreads();
+        {
+            const unsigned ng = __reduce_add_sync(kFull, n_global);
+            if (lane == 0 && ng) atomicAdd(&M->nglob, (int)ng);
+            n_global = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int ng = M->nglob;
+            HypResult res;
+            res.m00 = pose.m00; res.m01 = pose.m01; res.m10 = pose.m10; res.m11 = pose.m11;
+            res.cx = pose.cx; res.cy = pose.cy;
+            res.frmsd = po.f; res.rmse = po.rmse; res.k = po.k; res.passes = passes;
+            res.flags = (ng ? 1 : 0) | (win_ok ? 0 : 2);
+            res.pad = 0;
+            P.results[(size_t)plot * P.n_hyp_local + j] = res;
+            const float score = (po.k >= P.min_k && po.k > 0) ? (float)po.f : __int_as_float(0x7F800000);
+            const unsigned long long bk = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)h;
+            atomicMin(P.best_key + plot, bk);
+            acc_passes += passes; acc_fix += n_fix; acc_searched += n_searched; acc_deferred += n_deferred;
+            acc_queries += (unsigned long long)passes * n;
+            if (ng) atomicAdd(P.stats + 1, (unsigned long long)ng);
+        }
+        if (P.final_xy && P.n_hyp_local == 1 && tid < n) {
+            double qx, qy;
+            pose_apply(pose, s_u[tid], qx, qy);
+            P.final_xy[(pm.off + tid) * 2] = qx;
+            P.final_xy[(pm.off + tid) * 2 + 1] = qy;
+        }
+    }
+    if (tid == 0 && acc_passes) {
+        atomicAdd(P.stats + 0, acc_passes);
+        atomicAdd(P.stats + 3, acc_fix);
+        atomicAdd(P.stats + 4, acc_queries);
+        atomicAdd(P.stats + 5, acc_searched);
+        atomicAdd(P.stats + 6, acc_deferred);
+    }
+}
+
+template <bool Z3, int T>
+int team_launch_one(const IcpParams& p, int ctas, size_t smem, cudaStream_t stream) {
+    auto kern = icp_team_kernel<Z3, T>;
+    FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ctas, T, smem, stream>>>(p);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+template <bool Z3, int T>
+int team_occupancy_one(size_t smem, int* out) {
+    auto kern = icp_team_kernel<Z3, T>;
+    FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, T, smem));
+    return kOk;
+}
+
+}  // namespace
+
+size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
+    return team_layout(32 * e, z3, wcap_pts, wcap_cells, wcap_rows).total;
+}
+
+#define FICP_TEAM_DISPATCH(FN, ...)                                                                   \
+    switch (e) {                                                                                      \
+        case 2: return z3 ? FN<true, 64>(__VA_ARGS__) : FN<false, 64>(__VA_ARGS__);                   \
+        case 4: return z3 ? FN<true, 128>(__VA_ARGS__) : FN<false, 128>(__VA_ARGS__);                 \
+        case 8: return z3 ? FN<true, 256>(__VA_ARGS__) : FN<false, 256>(__VA_ARGS__);                 \
+        case 16: return z3 ? FN<true, 512>(__VA_ARGS__) : FN<false, 512>(__VA_ARGS__);                \
+        case 32: return z3 ? FN<true, 1024>(__VA_ARGS__) : FN<false, 1024>(__VA_ARGS__);              \
+        default: set_error("icp_team: unsupported elements-per-lane"); return kErrInvalid;            \
+    }
+
+int icp_team_max_ctas_per_sm(int e, bool z3, size_t smem, int* out) { FICP_TEAM_DISPATCH(team_occupancy_one, smem, out) }
+
+int launch_icp_team(const IcpParams& p, int e, bool z3, int ctas, size_t smem, cudaStream_t stream) {
+    FICP_TEAM_DISPATCH(team_launch_one, p, ctas, smem, stream)
+}
+
+}  // namespace ficp

@@ -224,8 +224,12 @@ FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& 
     t.p1 = m1 ? j : t.p1;
     nn_fold(acc, j, d2, best, bestpos);
 }
+#if !defined(FICP_TIETEST_STREAM)
+#define FICP_TIEFREE_STREAM 1
+#endif
 #if defined(FICP_TIEFREE_STREAM)
-// EXPERIMENT, off by default (not measured on the GPU yet): the same insertion, but the winner is
+// DEFAULT since round 2 (+6 % on C3, 113 GPU parity tests green on it; -DFICP_TIETEST_STREAM restores the per-candidate tie
+// test): the same insertion, but the winner is
 // kept with a plain `<` (first met wins) - no tie test, no branch in the candidate loop.  An exact tie with a different
 // point shows up afterwards as a second candidate carrying the winner's CODE; only then (rare: codes agree to 2^-20) the
 // stream is looked at again with the index rule (see nn_search_block3_impl).  Accessors whose admit() can refuse a

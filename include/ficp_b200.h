@@ -64,6 +64,10 @@ typedef struct {
     int32_t trace_passes;      /* > 0: record the first `trace_passes` passes of EVERY ICP of the batch (nearest-neighbour
                                   rows, squared distances, trimmed-subset flags, k, FRMSD) for ficp_batch_trace; 0 = off.
                                   Test instrument: direct parity with ficp.py:69-71 (indices) and :62-63,:133 (inlier set) */
+    int32_t cta_per_icp;       /* kernel shape: 0 = auto, 1 = one WARP per ICP (throughput shape, icp_persistent.cu),
+                                  2 = one CTA per ICP (latency shape for batches smaller than the machine, icp_team.cu:
+                                  every phase of a pass is cooperative).  Results are bit-identical. */
+    int32_t reserved;
 } ficp_batch_params;
 
 typedef struct {
@@ -86,7 +90,7 @@ typedef struct {
     int64_t smem_bytes;
     int64_t rows;
     int32_t trace_stride;      /* entries per pass record of ficp_batch_trace */
-    int32_t reserved;
+    int32_t cta_per_icp;       /* 1 = the CTA-per-ICP kernel was chosen */
 } ficp_batch_info;
 
 FICP_API const char* ficp_last_error(void);

@@ -84,6 +84,7 @@ def test_real_data_c1_matches_reference(gpu):
 def _check_batch_against_oracle(tgt, plots, hyp, atol_xy=1e-6, **kw):
     from coregistrationgame_b200 import IcpBatch, TargetIndex
     from coregistrationgame_b200.batch import compose_world_transform
+    kw.setdefault("cta_per_icp", False)      # small test batches would pick the CTA kernel by themselves: test_cta_per_icp_*
     ti = TargetIndex(tgt)
     b = IcpBatch(ti, plots, hyp, **kw)
     out = b.run().results()
@@ -278,7 +279,7 @@ def test_helper_warps_are_bit_identical(gpu, n, dims):
     for kw in (dict(team_warps=1, helpers=False), dict(team_warps=1), dict(team_warps=2), dict(team_warps=4),
                dict(team_warps=8), dict(team_warps=0), dict(team_warps=4, disable_window=True),
                dict(team_warps=2, warps_per_cta=6), dict(team_warps=1, warps_per_cta=3, ctas_per_sm=1)):
-        b = IcpBatch(ti, plots, hyp, **kw)
+        b = IcpBatch(ti, plots, hyp, cta_per_icp=False, **kw)
         out = b.run().results()
         assert b.info["helpers"] == int(kw.get("helpers", True))          # auto: 36 ICPs -> elastic
         want = kw["team_warps"]
@@ -296,11 +297,91 @@ def test_helper_warps_are_bit_identical(gpu, n, dims):
         np.testing.assert_array_equal(out["best_key"], base["best_key"])
         assert out["stats"]["passes"] == base["stats"]["passes"]
     # one start pose per plot (C4 shape), with final positions
-    one = [IcpBatch(ti, plots, None, want_final_xy=True, team_warps=t, helpers=(t > 1)) for t in (1, 4)]
+    one = [IcpBatch(ti, plots, None, want_final_xy=True, team_warps=t, helpers=(t > 1), cta_per_icp=False) for t in (1, 4)]
     res = [b.run().results() for b in one]
     assert _rows_equal_except_flags(res[0]["hyp"], res[1]["hyp"])
     np.testing.assert_array_equal(res[0]["final_xy"], res[1]["final_xy"])
     for b in one:
+        b.close()
+    ti.close()
+
+
+@pytest.mark.parametrize("n,dims", [(40, 2), (64, 3), (100, 3), (150, 3), (200, 2), (500, 3), (1000, 3)])
+def test_cta_per_icp_is_bit_identical(gpu, n, dims):
+    """CTA-per-ICP kernel (icp_team.cu: every phase of a pass cooperative across 32 e threads - the shape for batches
+    smaller than the machine, e.g. ONE stand x 4096 start poses sharded over 8 GPUs) vs the one-warp-per-ICP kernel:
+    identical bits in every result row, best key, final positions and pass count, for every thread-count class, on the
+    window and on the global-grid path, with duplicated targets (ties) and start poses thrown off the window."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(40000, n, seed=121 + n, dims=dims, n_plots=3, hidden_pose=True, out_frac=0.15,
+                                        dup_every=7)
+    small = plots[2][: max(33, n // 3)]                     # a smaller plot in the same size class
+    hyp = orc.hypothesis_table(6, flips=(0, 1), translations=[(0.0, 0.0), (60.0, -45.0)])
+    ti = TargetIndex(tgt)
+    outs = []
+    for kw in (dict(cta_per_icp=False), dict(cta_per_icp=True), dict(cta_per_icp=True, disable_window=True),
+               dict(cta_per_icp=True, ctas_per_sm=1), dict(cta_per_icp=True, fixed_frac=0.8), dict(cta_per_icp=False, fixed_frac=0.8)):
+        b = IcpBatch(ti, [plots[0], plots[1], small], hyp, **kw)
+        assert b.info["cta_per_icp"] == int(kw["cta_per_icp"])
+        if kw["cta_per_icp"]:
+            assert b.info["warps_per_cta"] == b.info["elems_per_lane"]
+        outs.append(b.run().results())
+        b.close()
+    for o in outs[1:4]:
+        assert _rows_equal_except_flags(o["hyp"], outs[0]["hyp"])
+        np.testing.assert_array_equal(o["best_key"], outs[0]["best_key"])
+        assert o["stats"]["passes"] == outs[0]["stats"]["passes"] and o["stats"]["queries"] == outs[0]["stats"]["queries"]
+    assert _rows_equal_except_flags(outs[4]["hyp"], outs[5]["hyp"])
+    np.testing.assert_array_equal(outs[4]["best_key"], outs[5]["best_key"])
+    assert outs[2]["stats"]["global_path_queries"] == outs[2]["stats"]["queries"]
+    # the skip test works in this shape too (first pass of each stage-1 run searches everything, later passes few)
+    assert outs[1]["stats"]["searched_queries"] < 0.6 * outs[1]["stats"]["queries"]
+    # and the oracle agrees (pass counts, k of plot 0)
+    ref = orc.run_hypotheses(plots[0], tgt, hyp[:3], centre=plots[0][:, :2].mean(axis=0), min_k=3, closed_form=True)
+    np.testing.assert_array_equal(outs[1]["hyp"]["passes"][0, :3], ref["passes"])
+    np.testing.assert_array_equal(outs[1]["hyp"]["k"][0, :3], ref["k"])
+    # one start pose per plot with final positions
+    one = [IcpBatch(ti, plots, None, want_final_xy=True, cta_per_icp=c) for c in (False, True)]
+    res = [b.run().results() for b in one]
+    assert _rows_equal_except_flags(res[0]["hyp"], res[1]["hyp"])
+    np.testing.assert_array_equal(res[0]["final_xy"], res[1]["final_xy"])
+    for b in one:
+        b.close()
+    ti.close()
+
+
+def test_cta_per_icp_against_oracle(gpu):
+    """The CTA-per-ICP kernel against the oracle directly: C2 slice, adversarial scene with the fixed-fraction sweep,
+    exact ties everywhere, reflection / single stage / iteration cap."""
+    tgt, plots, _ = orc.synthetic_scene(100000, 200, seed=2, dims=3, hidden_pose=True)
+    _check_batch_against_oracle(tgt, plots, orc.hypothesis_table(8, flips=(0, 1)), cta_per_icp=True)
+    tgt, plots, _ = orc.synthetic_scene(20000, 120, seed=5, dims=3, out_frac=0.3, omit_frac=0.3, dup_every=10,
+                                        lattice_patch=8, hidden_pose=True)
+    hyp = orc.hypothesis_table(8, flips=(0, 1))
+    _check_batch_against_oracle(tgt, plots, hyp, cta_per_icp=True)
+    for frac in (0.5, 0.7, 0.95):
+        _check_batch_against_oracle(tgt, plots, hyp[:6], fixed_frac=frac, cta_per_icp=True)
+    tgt, _, _ = orc.synthetic_scene(5000, 10, seed=9, dims=2, dup_every=5, lattice_patch=10, hidden_pose=False)
+    src = np.vstack([tgt[:60], tgt[:20] + np.array([0.5, 0.5])])
+    src = np.vstack([src, src[:7]])
+    _check_batch_against_oracle(tgt, [src], orc.hypothesis_table(4, flips=(0,), translations=[(0.0, 0.0), (1.0, 0.0)]), cta_per_icp=True)
+    tgt, plots, _ = orc.synthetic_scene(20000, 90, seed=12, dims=2, hidden_pose=True)
+    hyp = orc.hypothesis_table(6, flips=(0, 1))
+    _check_batch_against_oracle(tgt, plots, hyp, allow_reflection=True, cta_per_icp=True)
+    _check_batch_against_oracle(tgt, plots, hyp, lambda_val=1.0, max_iterations=3, cta_per_icp=True)
+
+
+def test_small_batches_pick_the_cta_kernel_by_themselves(gpu):
+    """Planner: a batch far smaller than the machine (one stand x a few hundred start poses) runs CTA-per-ICP, a batch
+    that fills it runs warp-per-ICP; plots of <= 32 trees are one warp either way."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(30000, 120, seed=3, dims=3, n_plots=2, hidden_pose=True)
+    ti = TargetIndex(tgt)
+    small = IcpBatch(ti, [plots[0]], orc.hypothesis_table(64, flips=(0, 1)))
+    big = IcpBatch(ti, plots, orc.hypothesis_table(2048, flips=(0, 1)))
+    tiny = IcpBatch(ti, [plots[0][:20]], orc.hypothesis_table(8, flips=(0, 1)), cta_per_icp=True)
+    assert small.info["cta_per_icp"] == 1 and big.info["cta_per_icp"] == 0 and tiny.info["cta_per_icp"] == 0
+    for b in (small, big, tiny):
         b.close()
     ti.close()
 

@@ -47,16 +47,17 @@ def _assert_inlier_set(inl, dist, k, what):
         assert np.allclose(dist[diff], edge, rtol=1e-9, atol=1e-12), f"{what}: inlier set differs away from the trim boundary: trees {diff}"
 
 
+@pytest.mark.parametrize("cta", [False, True], ids=["warp-per-icp", "cta-per-icp"])
 @pytest.mark.parametrize("case", CASES)
-def test_trace_matches_reference_golden_pass_by_pass(gpu, case):
-    """All 16 goldens: NN rows, distances, k, FRMSD and inlier set of every pass the reference made."""
+def test_trace_matches_reference_golden_pass_by_pass(gpu, case, cta):
+    """All 16 goldens, both kernel shapes: NN rows, distances, k, FRMSD and inlier set of every pass the reference made."""
     from coregistrationgame_b200 import IcpBatch, TargetIndex
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     src, tgt, md = g["source"], g["target"], int(g["match_dims"])
     n, n_ref = src.shape[0], len(g["k"])
     ti = TargetIndex(tgt[:, :md], use_z=(md == 3))
     b = IcpBatch(ti, [src], None, centres=np.zeros((1, 2)), lambda_val=float(g["lambda_val"]),
-                 allow_reflection=bool(g["allow_reflection"]), min_k=0, trace_passes=n_ref + 8)
+                 allow_reflection=bool(g["allow_reflection"]), min_k=0, trace_passes=n_ref + 8, cta_per_icp=cta)
     out = b.run().results()
     tr = b.trace()
     b.close()
@@ -90,6 +91,7 @@ def _check_trace_against_oracle(tgt, plots, hyp, **kw):
     from coregistrationgame_b200 import IcpBatch, TargetIndex
     ti = TargetIndex(tgt)
     cap = 160
+    kw.setdefault("cta_per_icp", False)
     b = IcpBatch(ti, plots, hyp, trace_passes=cap, **kw)
     out = b.run().results()
     tr = b.trace()
@@ -125,14 +127,15 @@ def test_trace_matches_oracle_c2_slice(gpu, dims):
     assert _check_trace_against_oracle(tgt, plots, hyp) > 100
 
 
-def test_trace_matches_oracle_c5_adversarial(gpu):
+@pytest.mark.parametrize("cta", [False, True], ids=["warp-per-icp", "cta-per-icp"])
+def test_trace_matches_oracle_c5_adversarial(gpu, cta):
     """C5: 30 % outlier trees, omissions, duplicated and lattice-tied CHM points; FRMSD-optimal and fixed fractions."""
     tgt, plots, _ = orc.synthetic_scene(20000, 120, seed=5, dims=3, out_frac=0.3, omit_frac=0.3, dup_every=10,
                                         lattice_patch=8, hidden_pose=True)
     hyp = orc.hypothesis_table(8, flips=(0, 1))
-    assert _check_trace_against_oracle(tgt, plots, hyp) > 100
+    assert _check_trace_against_oracle(tgt, plots, hyp, cta_per_icp=cta) > 100
     for frac in (0.5, 0.8, 0.95):
-        _check_trace_against_oracle(tgt, plots, hyp[:4], fixed_frac=frac)
+        _check_trace_against_oracle(tgt, plots, hyp[:4], fixed_frac=frac, cta_per_icp=cta)
 
 
 def test_trace_is_identical_on_every_launch_shape(gpu):
@@ -142,7 +145,8 @@ def test_trace_is_identical_on_every_launch_shape(gpu):
     hyp = orc.hypothesis_table(6, flips=(0, 1), translations=[(0.0, 0.0), (40.0, -30.0)])
     ti = TargetIndex(tgt)
     base = None
-    for kw in (dict(team_warps=1, helpers=False), dict(disable_window=True), dict(team_warps=4), dict(warps_per_cta=4, ctas_per_sm=2)):
+    for kw in (dict(team_warps=1, helpers=False), dict(disable_window=True), dict(team_warps=4), dict(warps_per_cta=4, ctas_per_sm=2),
+               dict(cta_per_icp=True), dict(cta_per_icp=True, disable_window=True)):
         b = IcpBatch(ti, plots, hyp, trace_passes=96, **kw)
         out = b.run().results()
         tr = b.trace()

@@ -35,7 +35,7 @@ def test_abi_struct_sizes():
     import ctypes as C
     from coregistrationgame_b200 import _lib
     assert _lib.HYP_RESULT_DTYPE.itemsize == 80
-    assert C.sizeof(_lib.BatchParams) == 56
+    assert C.sizeof(_lib.BatchParams) == 64
     assert C.sizeof(_lib.BatchInfo) == 80
     assert C.sizeof(_lib.TargetInfo) == 88
 
@@ -98,8 +98,8 @@ def test_product_path_never_imports_the_oracle():
     assert "oracle" not in open(os.path.join(ROOT, "ficp.py")).read()
 
 
-@pytest.mark.parametrize("flags", [[], ["-DFICP_TIEFREE_STREAM"], ["-DFICP_PRESCAN_OWN_CELL"]],
-                         ids=["product", "tiefree-experiment", "prescan-experiment"])
+@pytest.mark.parametrize("flags", [[], ["-DFICP_TIETEST_STREAM"], ["-DFICP_PRESCAN_OWN_CELL"]],
+                         ids=["product", "tietest-stream-variant", "prescan-experiment"])
 def test_nn_search_host_check(tmp_path, flags):
     """The grid NN search (ring/termination/tie logic, window + global accessors, streamed form with arbitrary
     seeds, runner-up and lower bound of the tracked form) is host-compilable: build it with g++ and compare 19 200

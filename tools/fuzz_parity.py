@@ -57,9 +57,14 @@ def one_case(rng):
         launch["disable_window"] = True
     if rng.random() < 0.2:
         launch["warps_per_cta"] = int(rng.choice([1, 2, 8]))
-    if rng.random() < 0.5:
-        launch["team_warps"] = int(rng.choice([1, 2, 4, 8]))    # default 0 = auto: these tiny batches team up anyway
-    elif rng.random() < 0.3:
+    u = rng.random()
+    if u < 0.35:
+        launch["cta_per_icp"] = True                             # CTA-per-ICP kernel (plots above 32 trees; else one warp)
+    elif u < 0.7:
+        launch["cta_per_icp"] = False
+        launch["team_warps"] = int(rng.choice([1, 2, 4, 8]))    # elastic kernel with helper warps
+    elif u < 0.85:
+        launch["cta_per_icp"] = False
         launch["helpers"] = False                                # the plain kernel
     return src, tgt, hyp, kw, launch
 
