@@ -205,6 +205,11 @@ class IcpBatch:
         _lib.check(_lib.load().ficp_batch_copy_best_keys_device(self._h, C.c_void_p(int(device_ptr)),
                                                                 _stream_ptr(stream)))
 
+    def pack_best_to(self, device_ptr, stream=None):
+        """Enqueue only: this GPU's best registration per plot as (n_plots, 12) int64 words in device memory at
+        ``device_ptr`` - key, the 80-byte result row, this GPU's hypothesis-iterations (see dist.PACK_WORDS)."""
+        _lib.check(_lib.load().ficp_batch_pack_best_device(self._h, C.c_void_p(int(device_ptr)), _stream_ptr(stream)))
+
     def results(self, stream=None, per_hypothesis=True):
         """Synchronise and read back.  Returns a dict:
         ``hyp`` structured array (n_plots, n_hyp_local) of per-hypothesis outcomes (see HYP_RESULT_DTYPE),

@@ -726,6 +726,15 @@ int ficp_batch_copy_best_keys_device(ficp_batch* bh, void* dst_dev, void* stream
     return kOk;
 }
 
+int ficp_batch_pack_best_device(ficp_batch* bh, void* dst_dev, void* stream) {
+    if (!bh || !dst_dev) { set_error("ficp_batch_pack_best_device: null pointer"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    const int rc = launch_pack_best(b->d_best, b->d_results, b->n_plots, b->n_hyp_local, b->params.hyp_begin, b->params.hyp_stride,
+                                    b->d_stats, reinterpret_cast<unsigned long long*>(dst_dev), (cudaStream_t)stream);
+    b->used.record((cudaStream_t)stream);
+    return rc;
+}
+
 int ficp_batch_trace(ficp_batch* bh, int32_t* idx_out, double* d2_out, uint8_t* inlier_out, int32_t* k_out,
                      double* frmsd_out, void* stream) {
     if (!bh) { set_error("ficp_batch_trace: null batch"); return kErrInvalid; }

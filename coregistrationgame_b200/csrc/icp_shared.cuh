@@ -121,6 +121,30 @@ __device__ __forceinline__ void nn_deferred_chunk(const GridView& G, const Windo
     }
 }
 
+// A query whose 3x3 block was searched inside the window: store neighbour code, squared distance and the slack of the
+// skip test; returns -1, or the tree index when the block does not settle the search (rings >= 2 follow, deferred).
+template <bool MARK>
+__device__ __forceinline__ int nn_finish_window(const GridGeom& g, int i, double qx, double qy, int cx, int cy, double best,
+                                                int pos, int pos2, int lb_hi, double* __restrict__ sd2,
+                                                int* __restrict__ snn, __half* __restrict__ ssl) {
+    int defer = -1;
+    float slack = 0.f;  // deferred queries carry no bound: they are searched again next pass
+    snn[i] = code_pack(pos, pos2);
+    const double border2 = nn_block_border2(g, qx, qy, cx, cy, 1);
+    if ((border2 == kInf) || best < border2) {   // == nn_block_settles
+        // every target point other than the winner and the runner-up is at least sqrt(lb2) away (third-best
+        // streamed, pruned cells of the block, the block's border): rounded DOWN at every step
+        const double lb2 = fmin(hi_to_double(lb_hi), border2);
+        slack = fminf(__fsqrt_rd(__double2float_rd(lb2)), 60000.f);
+    } else {
+        defer = i;
+        if (MARK) best = -best;
+    }
+    sd2[i] = best;
+    ssl[i] = __float2half_rd(slack);
+    return defer;
+}
+
 // One round of nearest-neighbour queries: the 32 queries at positions 32e..32e+31 of the PREVIOUS pass's trim order
 // (identity on the first pass): neighbours in that order have similar residuals, hence similar search radii and
 // candidate counts, so the lanes of a warp finish together and the rare wide searches (ring >= 2) fall into the same
@@ -149,28 +173,124 @@ __device__ __forceinline__ int nn_round(const GridView& G, const WindowAcc& W, b
         bool ok = false;
         int lb_hi = kHiInf, pos2 = -1;
         if (win_ok) ok = nn_search_block3_impl<Z3, true>(W, G.g, qx, qy, qz, pc_prev, best, pos, cx, cy, lb_hi, pos2);
-        float slack = 0.f;  // deferred / global-grid queries carry no bound: they are searched again next pass
         if (ok) {
-            snn[i] = code_pack(pos, pos2);
-            const double border2 = nn_block_border2(G.g, qx, qy, cx, cy, 1);
-            if ((border2 == kInf) || best < border2) {   // == nn_block_settles
-                // every target point other than the winner and the runner-up is at least sqrt(lb2) away (third-best
-                // streamed, pruned cells of the block, the block's border): rounded DOWN at every step
-                const double lb2 = fmin(hi_to_double(lb_hi), border2);
-                slack = fminf(__fsqrt_rd(__double2float_rd(lb2)), 60000.f);
-            } else {
-                defer = i;
-                if (MARK) best = -best;
-            }
-            sd2[i] = best;
+            defer = nn_finish_window<MARK>(G.g, i, qx, qy, cx, cy, best, pos, pos2, lb_hi, sd2, snn, ssl);
         } else {
             if (!have_prev) snn[i] = -1;  // keep the previous pass's code as the seed of the deferred query
             if (MARK) sd2[i] = -kInf;
             defer = i | 0x8000;
+            ssl[i] = __float2half_rd(0.f);  // deferred / global-grid queries carry no bound: they are searched again next pass
         }
-        ssl[i] = __float2half_rd(slack);
     }
     return defer;
+}
+
+// ---- group search (CTA-per-ICP kernel): G = 2..16 lanes share ONE query and split its candidate stream ---------------
+// The one-lane search above walks ~15 (up to ~50) candidates serially; when a pass searches only a few dozen queries a
+// CTA has lanes to spare.  Lanes sub = 0..G-1 of a group compute the same set-up (cell, gaps, row runs), take the
+// candidates t = sub, sub + G, ... of the flat stream and merge their (winner, runner-up, third-best code) with xor
+// shuffles.  The winner is exact (canonical d2, strict <); a POSSIBLE exact tie - another candidate carrying the
+// winner's truncated code - is not resolved here: status 2 sends the query to the one-lane search, which applies the
+// lowest-original-index rule.  The seed (previous neighbour) only bounds the pruning; it is folded in by lane 0 only
+// when the stream will not meet it.  Returns 0 ok, 1 window miss (global grid), 2 possible tie (one-lane search).
+__device__ __forceinline__ void top3_insert(Top3& t, int c, int j) {
+    const bool m1 = c < t.c1, m2 = c < t.c2, m3 = c < t.c3;
+    t.c3 = m2 ? t.c2 : (m3 ? c : t.c3);
+    t.c2 = m1 ? t.c1 : (m2 ? c : t.c2);
+    t.p2 = m1 ? t.p1 : (m2 ? j : t.p2);
+    t.c1 = m1 ? c : t.c1;
+    t.p1 = m1 ? j : t.p1;
+}
+template <bool Z3>
+__device__ __forceinline__ int nn_search_group(const WindowAcc& acc, const GridGeom& g, bool active, double qx, double qy,
+                                               double qz, int prev, int G, int sub, double& best, int& bestpos, int& cx,
+                                               int& cy, int& lb_hi, int& pos2) {
+    int status = 0, lb = kHiInf;
+    best = kInf; bestpos = -1; pos2 = -1; cx = 0; cy = 0;
+    Top3 top = top3_empty();
+    if (active) {
+        cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+        cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+        const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
+        const int yl = (cy > 0) ? cy - 1 : 0, yh = (cy < g.gh - 1) ? cy + 1 : g.gh - 1;
+        if (!acc.covers(xl, xh, yl, yh)) {
+            status = 1;
+        } else {
+            const double seed_d2 = (prev >= 0) ? nn_dist2<Z3>(acc, prev, qx, qy, qz) : kInf;
+            const double h = g.h, eps = g.eps;
+            const double ux = qx - (g.x0 + cx * h), uy = qy - (g.y0 + cy * h);
+            double gx[3], gy[3];
+            gx[0] = fmax(ux - eps, 0.0);
+            gx[1] = fmax(fmax(-ux, ux - h) - eps, 0.0);
+            gx[2] = fmax(h - ux - eps, 0.0);
+            gy[0] = fmax(uy - eps, 0.0);
+            gy[1] = fmax(fmax(-uy, uy - h) - eps, 0.0);
+            gy[2] = fmax(h - uy - eps, 0.0);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+            const double bound = seed_d2 * FICP_PRUNE_PAD;
+            int s[3], n[3];
+            bool seed_in = false;
+#pragma unroll
+            for (int ry = 0; ry < 3; ++ry) {
+                const int y = cy - 1 + ry;
+                s[ry] = 0;
+                n[ry] = 0;
+                if (y < yl || y > yh) continue;
+                int xa = cx + 2, xb = cx - 2;
+#pragma unroll
+                for (int rx = 0; rx < 3; ++rx) {
+                    const int x = cx - 1 + rx;
+                    if (x >= xl && x <= xh) {
+                        const double gap2 = gx[rx] + gy[ry];
+                        if (gap2 <= bound) {
+                            if (x < xa) xa = x;
+                            xb = x;
+                        } else {
+                            const int c = d_hi(gap2);
+                            lb = (c < lb) ? c : lb;
+                        }
+                    }
+                }
+                if (xa <= xb) {
+                    int e;
+                    acc.seg(y, xa, xb, s[ry], e);
+                    n[ry] = e - s[ry];
+                    seed_in = seed_in || (prev >= s[ry] && prev < e);
+                }
+            }
+            if (prev >= 0 && !seed_in && sub == 0) nn_fold_track_notie(prev, seed_d2, best, bestpos, top);
+            const int n01 = n[0] + n[1], total = n01 + n[2];
+            const int o1 = s[1] - n[0], o2 = s[2] - n01;
+            for (int t = sub; t < total; t += G) {
+                const int j = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+                const double d = nn_dist2<Z3>(acc, j, qx, qy, qz);
+                nn_fold_track_notie(j, d, best, bestpos, top);
+            }
+        }
+    }
+    __syncwarp();
+    for (int o = 1; o < G; o <<= 1) {
+        const double ob = __shfl_xor_sync(kFull, best, o);
+        const int op = __shfl_xor_sync(kFull, bestpos, o);
+        const int oc1 = __shfl_xor_sync(kFull, top.c1, o), oc2 = __shfl_xor_sync(kFull, top.c2, o);
+        const int oc3 = __shfl_xor_sync(kFull, top.c3, o);
+        const int op1 = __shfl_xor_sync(kFull, top.p1, o), op2 = __shfl_xor_sync(kFull, top.p2, o);
+        const bool lt = ob < best;
+        best = lt ? ob : best;
+        bestpos = lt ? op : bestpos;
+        top3_insert(top, oc1, op1);
+        top3_insert(top, oc2, op2);
+        top3_insert(top, oc3, -1);   // can only land in the third slot (oc3 >= oc2 >= what slot 2 now holds)
+    }
+    if (active && status == 0) {
+        const int cb = d_hi(best);
+        if (bestpos >= 0 && top.c1 == cb && (top.p1 != bestpos || top.c2 == cb)) status = 2;
+        const int c = top3_finish(top, bestpos, pos2);
+        lb = (c < lb) ? c : lb;
+    }
+    lb_hi = lb;
+    return status;
 }
 
 // Skip test of one round of 32 queries (i = 32e + lane), passes after the first.  `D` = pose of this pass minus the
@@ -233,9 +353,29 @@ __device__ __forceinline__ void fit_shift(const Pose& P, double ubx, double uby,
     ax = __dadd_rn(__fma_rn(P.m01, uby, __dmul_rn(P.m00, ubx)), P.cx);
     ay = __dadd_rn(__fma_rn(P.m11, uby, __dmul_rn(P.m10, ubx)), P.cy);
 }
-// one inlier: source position q (under the current pose) and its correspondence t
+// one inlier: source position q (under the current pose) and its correspondence t, both relative to the shift point
+__device__ __forceinline__ void fit_uv(double qx, double qy, double tx, double ty, double ax, double ay, double& ux, double& uy,
+                                       double& vx, double& vy) {
+    ux = __dsub_rn(qx, ax); uy = __dsub_rn(qy, ay); vx = __dsub_rn(tx, ax); vy = __dsub_rn(ty, ay);
+}
+// the nine running sums, individually (CTA-per-ICP kernel: one (sum, lane) pair per thread) ...
+__device__ __forceinline__ double fit_acc_one(int q, double acc, double ux, double uy, double vx, double vy) {
+    switch (q) {
+        case 0: return __dadd_rn(acc, ux);
+        case 1: return __dadd_rn(acc, uy);
+        case 2: return __dadd_rn(acc, vx);
+        case 3: return __dadd_rn(acc, vy);
+        case 4: return __fma_rn(ux, vx, acc);
+        case 5: return __fma_rn(ux, vy, acc);
+        case 6: return __fma_rn(uy, vx, acc);
+        case 7: return __fma_rn(uy, vy, acc);
+        default: return __fma_rn(__dadd_rn(fabs(ux), fabs(uy)), __dadd_rn(fabs(vx), fabs(vy)), acc);  // noise scale of the terms
+    }
+}
+// ... and all at once (one-warp kernel): the same operations, the same order per sum
 __device__ __forceinline__ void fit_term(FitSums& s, double qx, double qy, double tx, double ty, double ax, double ay) {
-    const double ux = __dsub_rn(qx, ax), uy = __dsub_rn(qy, ay), vx = __dsub_rn(tx, ax), vy = __dsub_rn(ty, ay);
+    double ux, uy, vx, vy;
+    fit_uv(qx, qy, tx, ty, ax, ay, ux, uy, vx, vy);
     s.su0 = __dadd_rn(s.su0, ux); s.su1 = __dadd_rn(s.su1, uy);
     s.sv0 = __dadd_rn(s.sv0, vx); s.sv1 = __dadd_rn(s.sv1, vy);
     s.h00 = __fma_rn(ux, vx, s.h00); s.h01 = __fma_rn(ux, vy, s.h01);

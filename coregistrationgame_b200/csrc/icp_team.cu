@@ -31,7 +31,7 @@ namespace ficp {
 namespace {
 
 struct TeamLayout {
-    size_t s_u, s_z, s_g, w_xy, w_z, w_cell, rowoff, rowdelta, rowg, sd2, snn, ssl, list, dlist, sidx, kbuf, sdd, tmp, misc, total;
+    size_t s_u, s_z, s_g, w_xy, w_z, w_cell, rowoff, rowdelta, rowg, sd2, snn, ssl, list, dlist, slist, sidx, kbuf, sdd, tmp, misc, total;
 };
 __host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
     TeamLayout L;
@@ -51,10 +51,11 @@ __host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, 
     L.ssl = take((size_t)t * 2);
     L.list = take((size_t)t * 2);
     L.dlist = take((size_t)t * 2);
+    L.slist = take((size_t)t * 2);   // queries the group search hands to the one-lane search (possible exact ties)
     L.sidx = take((size_t)t * 2);
-    L.kbuf = take((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms qx, qy
-    L.sdd = take((size_t)t * 8);     // d2 in trim order; later the fit term tx
-    L.tmp = take((size_t)t * 8);     // fit term ty
+    L.kbuf = take((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms ux, uy
+    L.sdd = take((size_t)t * 8);     // d2 in trim order; later the fit term vx
+    L.tmp = take((size_t)t * 8);     // fit term vy
     L.misc = take(1536);
     L.total = o;
     return L;
@@ -66,24 +67,25 @@ struct TeamMisc {
     double red_a[32], red_b[32];    // block reductions
     int red_k[32];
     double pose[12];                // new pose + pose update, broadcast by warp 0
+    double fsum[9];                 // reduced sums of the fit
     double sk;                      // S at the chosen k (fixed-fraction mode)
-    int nlist, ndef, nglob, icp, win_ok, pad;
+    int nlist, ndef, nser, nglob, icp, win_ok;
 };
 static_assert(sizeof(TeamMisc) <= 1536, "TeamMisc must fit its reservation");
 
-// Block bitonic sort, one 64-bit key per thread, ascending in thread order.  Strides below 32 exchange through
-// shuffles; larger strides through two alternating shared-memory buffers (one barrier per step).
+// Block bitonic sort, one 32-bit key per thread, ascending in thread order.  Strides below 32 exchange through
+// shuffles; larger strides through two alternating shared-memory buffers (one barrier per step).  Fully unrolled:
+// directions and buffers are compile-time, a step is shuffle + predicated min/max.
 template <int T>
-__device__ __forceinline__ unsigned long long block_sort64(unsigned long long key, unsigned long long* buf, int tid) {
+__device__ __forceinline__ unsigned block_sort32(unsigned key, unsigned* buf, int tid) {
     int flip = 0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 2; k <= T; k <<= 1) {
-        const bool up = ((tid & k) == 0) || (k == T);
-#pragma unroll 1
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            unsigned long long other;
+            unsigned other;
             if (j >= 32) {
-                unsigned long long* b = buf + flip * T;
+                unsigned* b = buf + flip * T;
                 b[tid] = key;
                 __syncthreads();
                 other = b[tid ^ j];
@@ -91,12 +93,19 @@ __device__ __forceinline__ unsigned long long block_sort64(unsigned long long ke
             } else {
                 other = __shfl_xor_sync(kFull, key, j);
             }
-            const bool lower = ((tid & j) == 0);
-            const unsigned long long mn = (key < other) ? key : other, mx = (key < other) ? other : key;
-            key = (lower == up) ? mn : mx;
+            const bool takemin = (((tid & j) == 0) == ((tid & k) == 0));   // (tid & T) == 0: the last phase ascends
+            key = takemin ? min(key, other) : max(key, other);
         }
     }
     return key;
+}
+
+// min / lexicographic arg-min over the NW per-warp partials in shared memory, by every warp for itself (5 shuffles)
+__device__ __forceinline__ double warp_min_of(const double* red, int nw, int lane) {
+    double v = (lane < nw) ? red[lane] : kInf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
 }
 
 template <bool Z3, int T>
@@ -104,6 +113,7 @@ __global__ void __launch_bounds__(T, (T >= 1024) ? 1 : (T == 512) ? 2 : (T == 25
 icp_team_kernel(const __grid_constant__ IcpParams P) {
     constexpr int E = T / 32;
     constexpr int NW = T / 32;
+    constexpr int IB = (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;   // bits of a tree index
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TeamLayout L = team_layout(T, Z3, P.wcap_pts, P.wcap_cells, P.wcap_rows);
@@ -121,16 +131,18 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     __half* ssl = reinterpret_cast<__half*>(smem + L.ssl);
     unsigned short* list = reinterpret_cast<unsigned short*>(smem + L.list);
     unsigned short* dlist = reinterpret_cast<unsigned short*>(smem + L.dlist);
+    unsigned short* slist = reinterpret_cast<unsigned short*>(smem + L.slist);
     unsigned short* sidx = reinterpret_cast<unsigned short*>(smem + L.sidx);
-    unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem + L.kbuf);
+    unsigned* kbuf = reinterpret_cast<unsigned*>(smem + L.kbuf);
     double* sdd = reinterpret_cast<double*>(smem + L.sdd);
-    double* f_qx = reinterpret_cast<double*>(smem + L.kbuf);          // fit terms alias the (dead) sort buffers
-    double* f_qy = reinterpret_cast<double*>(smem + L.kbuf) + T;
-    double* f_tx = reinterpret_cast<double*>(smem + L.sdd);
-    double* f_ty = reinterpret_cast<double*>(smem + L.tmp);
+    double* f_ux = reinterpret_cast<double*>(smem + L.kbuf);          // fit terms alias the (dead) sort buffers
+    double* f_uy = reinterpret_cast<double*>(smem + L.kbuf) + T;
+    double* f_vx = reinterpret_cast<double*>(smem + L.sdd);
+    double* f_vy = reinterpret_cast<double*>(smem + L.tmp);
+    unsigned short* finl = list;                                       // inlier flags of the fit (the search list is dead then)
     TeamMisc* M = reinterpret_cast<TeamMisc*>(smem + L.misc);
 
-    const GridView& G = P.grid;
+    const GridView& G_ = P.grid;
     const unsigned lt_mask = (1u << lane) - 1u;
     const long long n_icps = (long long)P.n_plots * P.n_hyp_local;
     int staged_plot = -1;
@@ -153,11 +165,11 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             const double* tab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;
             for (int i = tid; i < P.n_stages * T; i += T) s_g[i] = tab[(size_t)(i / T) * 2 * T + (i % T)];
             const int ww = pm.wx1 - pm.wx0, wh = pm.wy1 - pm.wy0;
-            bool ok = (ww > 0 && wh > 0 && (long long)ww * wh <= P.wcap_cells && wh <= P.wcap_rows && G.m > 0);
+            bool ok = (ww > 0 && wh > 0 && (long long)ww * wh <= P.wcap_cells && wh <= P.wcap_rows && G_.m > 0);
             if (ok) {
                 for (int r = tid; r < wh; r += T) {
-                    const size_t rowbase = (size_t)(pm.wy0 + r) * G.g.gw;
-                    const unsigned gs = G.cell_start[rowbase + pm.wx0], ge = G.cell_start[rowbase + pm.wx1];
+                    const size_t rowbase = (size_t)(pm.wy0 + r) * G_.g.gw;
+                    const unsigned gs = G_.cell_start[rowbase + pm.wx0], ge = G_.cell_start[rowbase + pm.wx1];
                     rowg[r] = (int)gs;
                     rowdelta[r] = (int)(ge - gs);  // temporarily: the row's point count
                 }
@@ -183,15 +195,15 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             if (ok) {
                 for (int cc = tid; cc < ww * wh; cc += T) {
                     const int r = cc / ww, col = cc - r * ww;
-                    const size_t g = (size_t)(pm.wy0 + r) * G.g.gw + pm.wx0 + col;
-                    const unsigned a = G.cell_start[g], b = G.cell_start[g + 1];
+                    const size_t g = (size_t)(pm.wy0 + r) * G_.g.gw + pm.wx0 + col;
+                    const unsigned a = G_.cell_start[g], b = G_.cell_start[g + 1];
                     w_cell[cc] = (unsigned)(rowoff[r] + (int)(a - (unsigned)rowg[r])) | ((b - a) << 16);
                 }
                 for (int r = warp; r < wh; r += NW) {
                     const int cnt = rowoff[r + 1] - rowoff[r], gs = rowg[r], lo = rowoff[r];
                     for (int q = lane; q < cnt; q += 32) {
-                        w_xy[lo + q] = grid_xy(G, gs + q);
-                        if (Z3) w_z[lo + q] = grid_z(G, gs + q);
+                        w_xy[lo + q] = grid_xy(G_, gs + q);
+                        if (Z3) w_z[lo + q] = grid_z(G_, gs + q);
                     }
                 }
             }
@@ -199,7 +211,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             __syncthreads();
         }
         const bool win_ok = (M->win_ok != 0);
-        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G.orig, G.rec,
+        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G_.orig, G_.rec,
                           pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0};
         const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
         const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;  // [stage][0]=g [stage][1]=c
@@ -226,7 +238,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             for (;;) {
                 // ================= nearest neighbours (ficp.py:65-71)
                 const bool have_prev = passes > 0;
-                if (tid == 0) { M->nlist = have_prev ? 0 : n; M->ndef = 0; }
+                if (tid == 0) { M->nlist = have_prev ? 0 : n; M->ndef = 0; M->nser = 0; }
                 __syncthreads();
                 if (have_prev) {
                     const int need = nn_test_round<Z3>(W, pc, pose, dpose, sd2, snn, ssl, warp, lane);
@@ -240,20 +252,71 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 __syncthreads();
                 const int n_list = M->nlist;
-                {
+                // lanes per query: a pass that searches few queries spreads each candidate stream over G lanes
+                int G = 1;
+                if (win_ok) while (G < 16 && n_list * G * 2 <= T) G <<= 1;
+                if (G == 1) {
                     const int defer = (warp * 32 < n_list)
-                                          ? nn_round<Z3, false>(G, W, win_ok, pc, pose, sd2, snn, ssl, list, warp, n_list, lane, have_prev)
+                                          ? nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, list, warp, n_list, lane, have_prev)
                                           : -1;
                     const unsigned m = __ballot_sync(kFull, defer >= 0);
                     int base = 0;
                     if (lane == 0 && m) base = atomicAdd(&M->ndef, __popc(m));
                     base = __shfl_sync(kFull, base, 0);
                     if (defer >= 0) dlist[base + __popc(m & lt_mask)] = (unsigned short)defer;
+                } else {
+                    const int slot = tid / G, sub = tid - slot * G;     // G divides 32: a group never straddles warps
+                    const bool active = slot < n_list;
+                    int i = 0, prev = -1;
+                    double qx = 0.0, qy = 0.0, qz = 0.0;
+                    if (active) {
+                        i = list[slot];
+                        pose_apply(pose, s_u[i], qx, qy);
+                        if (Z3) qz = s_z[i];
+                        prev = have_prev ? code_win(snn[i]) : -1;
+                    }
+                    double best;
+                    int pos, cx, cy, lb_hi, pos2;
+                    const int status = nn_search_group<Z3>(W, G_.g, active, qx, qy, qz, prev, G, sub, best, pos, cx, cy, lb_hi, pos2);
+                    int defer = -1, ser = -1;
+                    if (active && sub == 0) {
+                        if (status == 0) {
+                            defer = nn_finish_window<false>(G_.g, i, qx, qy, cx, cy, best, pos, pos2, lb_hi, sd2, snn, ssl);
+                        } else if (status == 1) {
+                            if (!have_prev) snn[i] = -1;
+                            ssl[i] = __float2half_rd(0.f);
+                            defer = i | 0x8000;
+                        } else {
+                            ser = i;
+                        }
+                    }
+                    unsigned m = __ballot_sync(kFull, defer >= 0);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&M->ndef, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (defer >= 0) dlist[base + __popc(m & lt_mask)] = (unsigned short)defer;
+                    m = __ballot_sync(kFull, ser >= 0);
+                    base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&M->nser, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (ser >= 0) slist[base + __popc(m & lt_mask)] = (unsigned short)ser;
+                    __syncthreads();
+                    const int n_ser = M->nser;
+                    if (n_ser > 0) {    // possible exact ties: the one-lane search applies the lowest-original-index rule
+                        const int d2nd = (warp * 32 < n_ser)
+                                             ? nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, slist, warp, n_ser, lane, have_prev)
+                                             : -1;
+                        const unsigned m2 = __ballot_sync(kFull, d2nd >= 0);
+                        int b2 = 0;
+                        if (lane == 0 && m2) b2 = atomicAdd(&M->ndef, __popc(m2));
+                        b2 = __shfl_sync(kFull, b2, 0);
+                        if (d2nd >= 0) dlist[b2 + __popc(m2 & lt_mask)] = (unsigned short)d2nd;
+                    }
                 }
                 __syncthreads();
                 const int n_def = M->ndef;
                 for (int base = warp * 32; base < n_def; base += NW * 32)
-                    nn_deferred_chunk<Z3, false>(G, W, pc, pose, sd2, snn, dlist, base, n_def, lane, n_global);
+                    nn_deferred_chunk<Z3, false>(G_, W, pc, pose, sd2, snn, dlist, base, n_def, lane, n_global);
                 n_searched += (unsigned)n_list;
                 n_deferred += (unsigned)n_def;
                 dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
@@ -261,15 +324,18 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
 
                 // ================= trimming (ficp.py:62-63,73-86)
                 const double my_d2 = sd2[tid];
-                unsigned long long key = ((unsigned long long)__double_as_longlong(my_d2) & ~0x3FFull) | (unsigned)tid;
-                key = block_sort64<T>(key, kbuf, tid);
-                int sidx_t = (int)(key & 0x3FFull);
+                // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
+                // (d2, index) order is verified below and repaired where codes collide
+                const unsigned fb = __float_as_uint(__double2float_rd(my_d2));
+                unsigned key = ((fb >> (IB - 1)) << IB) | (unsigned)tid;
+                key = block_sort32<T>(key, kbuf, tid);
+                int sidx_t = (int)(key & ((1u << IB) - 1u));
                 double dd = sd2[sidx_t];
                 sdd[tid] = dd;
                 sidx[tid] = (unsigned short)sidx_t;
                 __syncthreads();
                 {
-                    // the key drops the low 10 bits of d2: verify the exact (d2, index) order, repair if needed (rare)
+                    // verify the exact (d2, index) order; odd-even transposition rounds where quantised codes collided
                     bool inv = false;
                     if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[tid + 1], (unsigned)sidx[tid + 1]);
                     if (__syncthreads_or(inv)) {
@@ -332,9 +398,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     for (int o = 16; o > 0; o >>= 1) gb = fmin(gb, __shfl_xor_sync(kFull, gb, o));
                     if (lane == 0) M->red_a[warp] = gb;
                     __syncthreads();
-                    double gbest = M->red_a[0];
-#pragma unroll
-                    for (int w = 1; w < NW; ++w) gbest = fmin(gbest, M->red_a[w]);
+                    const double gbest = warp_min_of(M->red_a, NW, lane);
                     const double gthr = gbest * (1.0 + 1e-12);
                     int kb = INT_MAX;
                     if (tid < n && g <= gthr) {
@@ -353,12 +417,15 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     }
                     if (lane == 0) { M->red_b[warp] = fstar; M->red_k[warp] = kb; M->stot[warp] = rstar; }
                     __syncthreads();
-                    fstar = M->red_b[0]; kb = M->red_k[0]; rstar = M->stot[0];
+                    fstar = (lane < NW) ? M->red_b[lane] : kInf;
+                    kb = (lane < NW) ? M->red_k[lane] : INT_MAX;
+                    rstar = (lane < NW) ? M->stot[lane] : 0.0;
 #pragma unroll
-                    for (int w = 1; w < NW; ++w) {
-                        const double of = M->red_b[w];
-                        const int ok = M->red_k[w];
-                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = M->stot[w]; }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double of = __shfl_xor_sync(kFull, fstar, o);
+                        const int ok = __shfl_xor_sync(kFull, kb, o);
+                        const double orr = __shfl_xor_sync(kFull, rstar, o);
+                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
                     }
                     kstar = (kb == INT_MAX) ? 0 : kb;
                 }
@@ -382,7 +449,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     const size_t rec = (size_t)c * P.trace_cap + passes, base = rec * P.trace_stride;
                     const int code = snn[tid];
                     int orig = -1;
-                    if (code != -1) orig = grid_orig(G, (code < 0) ? (code & 0x7FFFFFFF) : W.global_pos(code & 0xFFFF));
+                    if (code != -1) orig = grid_orig(G_, (code < 0) ? (code & 0x7FFFFFFF) : W.global_pos(code & 0xFFFF));
                     P.tr_idx[base + tid] = orig;
                     P.tr_d2[base + tid] = my_d2;
                     P.tr_in[base + tid] = (po.k > 0 && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) ? 1 : 0;
@@ -402,31 +469,39 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 if (it >= P.max_iter) break;
 
-                // ================= rigid fit (ficp.py:89-110): terms by every thread, summed by warp 0 in lane order
+                // ================= rigid fit (ficp.py:89-110).  Every thread prepares its tree's term; the nine running
+                // sums are formed one (sum, lane) pair per thread in the order of the one-warp kernel - lane l adds the
+                // trees l, l + 32, ... in turn, then an xor butterfly over the 32 lanes - and one warp solves.
                 double ax, ay;
                 fit_shift(pose, pc.ubx, pc.uby, ax, ay);
-                __syncthreads();   // the sort buffers / sdd are dead from here: they take the fit terms
-                if (tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) {
-                    double qx, qy;
-                    pose_apply(pose, s_u[tid], qx, qy);
-                    const double2 t = corr_xy(G, W, snn[tid]);
-                    f_qx[tid] = qx; f_qy[tid] = qy; f_tx[tid] = t.x; f_ty[tid] = t.y;
+                {
+                    const bool inl = tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx));
+                    finl[tid] = inl ? 1 : 0;
+                    if (inl) {
+                        double qx, qy, ux, uy, vx, vy;
+                        pose_apply(pose, s_u[tid], qx, qy);
+                        const double2 t = corr_xy(G_, W, snn[tid]);
+                        fit_uv(qx, qy, t.x, t.y, ax, ay, ux, uy, vx, vy);
+                        f_ux[tid] = ux; f_uy[tid] = uy; f_vx[tid] = vx; f_vy[tid] = vy;
+                    }
+                }
+                __syncthreads();
+                for (int q = warp; q < 9; q += NW) {
+                    double acc = 0.0;
+#pragma unroll 4
+                    for (int e = 0; e < E; ++e) {
+                        const int i = e * 32 + lane;
+                        if (finl[i]) acc = fit_acc_one(q, acc, f_ux[i], f_uy[i], f_vx[i], f_vy[i]);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(kFull, acc, o));
+                    if (lane == 0) M->fsum[q] = acc;
                 }
                 __syncthreads();
                 if (warp == 0) {
-                    FitSums s = fit_zero();
-#pragma unroll 2
-                    for (int e = 0; e < E; ++e) {
-                        const int i = e * 32 + lane;
-                        if (i < n) {
-                            const double d2 = sd2[i];
-                            if (d2 < po.thr || (d2 == po.thr && i <= po.thr_idx))
-                                fit_term(s, f_qx[i], f_qy[i], f_tx[i], f_ty[i], ax, ay);
-                        }
-                    }
-                    fit_reduce(s);
+                    const FitSums fs{M->fsum[0], M->fsum[1], M->fsum[2], M->fsum[3], M->fsum[4], M->fsum[5], M->fsum[6], M->fsum[7], M->fsum[8]};
                     Pose np = pose, nd;
-                    fit_solve(s, po.k, P.allow_reflection, ax, ay, np, nd);
+                    fit_solve(fs, po.k, P.allow_reflection, ax, ay, np, nd);
                     if (lane == 0) {
                         M->pose[0] = np.m00; M->pose[1] = np.m01; M->pose[2] = np.m10; M->pose[3] = np.m11;
                         M->pose[4] = np.cx; M->pose[5] = np.cy;

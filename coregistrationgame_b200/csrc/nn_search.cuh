@@ -227,7 +227,6 @@ FICP_HD void nn_fold_track(const Acc& acc, int j, double d2, double& best, int& 
 #if !defined(FICP_TIETEST_STREAM)
 #define FICP_TIEFREE_STREAM 1
 #endif
-#if defined(FICP_TIEFREE_STREAM)
 // DEFAULT since round 2 (+6 % on C3, 113 GPU parity tests green on it; -DFICP_TIETEST_STREAM restores the per-candidate tie
 // test): the same insertion, but the winner is
 // kept with a plain `<` (first met wins) - no tie test, no branch in the candidate loop.  An exact tie with a different
@@ -247,7 +246,6 @@ FICP_HD void nn_fold_track_notie(int j, double d2, double& best, int& bestpos, T
     best = lt ? d2 : best;
     bestpos = lt ? j : bestpos;
 }
-#endif
 // Runner-up and the code of a lower bound on every streamed candidate other than winner and runner-up.
 FICP_HD int top3_finish(const Top3& t, int bestpos, int& pos2) {
     if (t.p1 == bestpos) { pos2 = t.p2; return t.c3; }

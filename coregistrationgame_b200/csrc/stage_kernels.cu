@@ -204,7 +204,42 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ a
     if (threadIdx.x == 0) *out = s;
 }
 
+// Per-plot best registration of a finished batch, packed for the multi-GPU exchange (dist.py): 12 words per plot:
+// [0] the packed key (fp32 score bits << 32 | hypothesis id), [1..10] the 80-byte result row of that hypothesis,
+// [11] the hypothesis-iterations this GPU ran in the launch.  One all_gather of these records is the whole exchange.
+__global__ void __launch_bounds__(256) pack_best_kernel(const unsigned long long* __restrict__ best,
+                                                        const HypResult* __restrict__ results, int n_plots, int n_hyp_local,
+                                                        int hyp_begin, int hyp_stride,
+                                                        const unsigned long long* __restrict__ stats,
+                                                        unsigned long long* __restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = t / 12, w = t - p * 12;
+    if (p >= n_plots) return;
+    const unsigned long long key = best[p];
+    unsigned long long v;
+    if (w == 0) {
+        v = key;
+    } else if (w == 11) {
+        v = stats[0];
+    } else {
+        long long j = ((long long)(unsigned)(key & 0xFFFFFFFFull) - hyp_begin) / hyp_stride;
+        if (j < 0 || j >= n_hyp_local) j = 0;
+        v = reinterpret_cast<const unsigned long long*>(results + (size_t)p * n_hyp_local + j)[w - 1];
+    }
+    dst[t] = v;
+}
+
 }  // namespace
+
+int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, int n_plots, int n_hyp_local, int hyp_begin,
+                     int hyp_stride, const unsigned long long* d_stats, unsigned long long* d_dst, cudaStream_t stream) {
+    static_assert(sizeof(HypResult) == 80, "pack_best_kernel copies ten 8-byte words per row");
+    if (n_plots <= 0) return kOk;
+    const int n = n_plots * 12;
+    pack_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_best, d_results, n_plots, n_hyp_local, hyp_begin, hyp_stride, d_stats, d_dst);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
 
 int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, int ld_c, const double* d_dist,
                            int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,

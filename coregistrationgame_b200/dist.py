@@ -2,41 +2,26 @@
 NVLink/NVSwitch) for the only exchange the path has - picking the best registration per plot.
 
 Every (plot, hypothesis) ICP is independent, so the hypotheses of every plot are dealt round-robin
-to the ranks (``hyp_shard=(rank, world)``), each rank keeps a replica of the target grid (<= 280 MB
-for 1e7 points) and runs the persistent kernel on its share with no data-path collective.  The
-exchange step is one all-reduce(MIN) over the packed per-plot keys ``(fp32 score bits << 32) |
-hypothesis id`` (8 bytes per plot) followed by one all-reduce(SUM) that carries the winner's pose
-from the rank that owns it.  The payload is bytes to kilobytes, i.e. latency-bound, so a fused
-compute+collective kernel over peer memory would buy nothing here (DESIGN.md "multi-GPU").
+to the ranks (``hyp_shard=(rank, world)``), each rank keeps a replica of the target grid (<= 320 MB
+for 1e7 points) and runs the persistent kernel on its share with no data-path collective.
+
+The exchange is ONE collective on device memory: every rank packs, per plot, its best key
+``(fp32 score bits << 32) | hypothesis id``, the 80-byte result row of that hypothesis and its pass
+count (``ficp_batch_pack_best_device``, 96 bytes per plot) and the records are all-gathered; the
+winner of a plot is the record with the smallest key (ties in score resolve to the lowest
+hypothesis id, exactly like the single-GPU ``atomicMin``).  Nothing is read back to the host before
+the exchange; the result leaves the device once, as ``world x n_plots x 96`` bytes.  The payload
+is bytes to kilobytes, i.e. latency-bound, so a fused compute+collective kernel over peer memory
+would have nothing to overlap (DESIGN.md "multi-GPU").
 """
 from __future__ import annotations
 
 import numpy as np
 
+from . import _lib
 from .batch import IcpBatch, TargetIndex, compose_world_transform, decode_best_keys
 
-DETAIL_FIELDS = ("m00", "m01", "m10", "m11", "cx", "cy", "frmsd", "rmse", "k", "passes")
-
-
-def reduce_best(local_keys, local_detail, group=None):
-    """Pick the global winner per plot.
-
-    local_keys   int64 tensor (n_plots,), this rank's best packed key per plot (non-negative).
-    local_detail float64 tensor (n_plots, D): payload describing this rank's best hypothesis per plot.
-    Returns (global_keys, global_detail) - identical on every rank.  Works on any backend
-    (NCCL on GPU tensors, gloo on CPU tensors)."""
-    import torch
-    import torch.distributed as dist
-
-    keys = local_keys.clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
-        mine = (local_keys == keys).to(local_detail.dtype).unsqueeze(1)
-        detail = local_detail * mine
-        dist.all_reduce(detail, op=dist.ReduceOp.SUM, group=group)
-    else:
-        detail = local_detail.clone()
-    return keys, detail
+PACK_WORDS = 12          # int64 words per plot record: key, 10 words of ficp_hyp_result, passes of the rank
 
 
 def shard_of(rank, world):
@@ -50,28 +35,50 @@ def plot_shard(n_plots, rank, world):
     return np.arange(int(rank), int(n_plots), int(world))
 
 
-def gather_plot_shards(local_detail, local_plots, n_plots, group=None):
-    """Assemble per-plot rows computed on different ranks: every rank contributes the rows of the plots it owns,
-    everything else is zero, one all-reduce(SUM) puts the table together on all ranks (no arg-min needed)."""
+def gather_packed(packed, group=None):
+    """All-gather of the per-rank records: (n, PACK_WORDS) int64 -> (world, n, PACK_WORDS).  The one collective of the
+    path; any backend (NCCL on device tensors, gloo on CPU tensors)."""
     import torch
     import torch.distributed as dist
 
-    full = torch.zeros((int(n_plots), local_detail.shape[1]), dtype=local_detail.dtype, device=local_detail.device)
-    if len(local_plots):
-        full[torch.as_tensor(np.asarray(local_plots), device=local_detail.device, dtype=torch.long)] = local_detail
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
-    return full
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    if world > 1:
+        dist.all_gather_into_tensor(out.view(-1), packed.contiguous().view(-1), group=group)
+    else:
+        out[0].copy_(packed)
+    return out
 
 
-def local_best_detail(batch, out):
-    """(n_plots, len(DETAIL_FIELDS)) float64 rows of this rank's best hypothesis per plot."""
-    det = np.zeros((batch.n_plots, len(DETAIL_FIELDS)), dtype=np.float64)
-    for p in range(batch.n_plots):
-        j = (int(out["best_hyp"][p]) - batch.hyp_begin) // batch.hyp_stride
-        row = out["hyp"][p, j]
-        det[p] = [float(row[f]) for f in DETAIL_FIELDS]
-    return det
+def exchange_best(batch, packed, group=None, stream=None):
+    """Enqueue-only exchange step of a finished (enqueued) batch: pack on the device, all-gather.  `packed` is a device
+    int64 tensor (n_rows >= batch.n_plots, PACK_WORDS) whose unused rows stay as they are (callers zero them once).
+    Returns the gathered device tensor (world, n_rows, PACK_WORDS).  bench.py's device-timed step and
+    register_batch_distributed both call exactly this."""
+    batch.pack_best_to(packed.data_ptr(), stream)
+    return gather_packed(packed, group)
+
+
+def select_best(gathered, by_plots=False, n_plots=None):
+    """Host-side decode of the gathered records (numpy int64 (world, n_rows, PACK_WORDS)).
+
+    by_plots=False: every rank holds a record for every plot; the winner is the smallest key.
+    by_plots=True : rank r holds the records of plots r, r + world, ... (row i = plot r + world * i).
+    Returns best_key (uint64), rows (HYP_RESULT_DTYPE, one per plot) and the pass counts per rank."""
+    g = np.ascontiguousarray(np.asarray(gathered, dtype=np.int64))
+    world, n_rows = g.shape[0], g.shape[1]
+    passes = g[:, 0, 11].astype(np.int64) if n_rows else np.zeros(world, dtype=np.int64)
+    if by_plots:
+        n_plots = int(n_plots)
+        # plot p lives in row p // world of rank p % world
+        sel = g[np.arange(n_plots) % world, np.arange(n_plots) // world]
+    else:
+        keys = g[:, :, 0]                                   # non-negative as int64 (fp32 score bits of a value >= 0)
+        win = np.argmin(keys, axis=0)                       # first minimum; equal keys cannot occur across ranks (ids differ)
+        sel = g[win, np.arange(n_rows)]
+    best_key = sel[:, 0].astype(np.uint64)
+    rows = np.ascontiguousarray(sel[:, 1:11]).view(_lib.HYP_RESULT_DTYPE).reshape(-1)
+    return best_key, rows, passes
 
 
 def register_batch_distributed(sources, target, hyp_table, index=None, group=None, device=None, **kw):
@@ -94,21 +101,12 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         stream = torch.cuda.current_stream()
         n_plots = len(sources)
-        if hyp_table.shape[0] >= world:
-            # ---- shard the hypotheses of every plot; winner = all-reduce(MIN) over packed keys
+        by_plots = hyp_table.shape[0] < world
+        if not by_plots:
+            # ---- shard the hypotheses of every plot; winner = smallest key among the gathered records
             batch = IcpBatch(index, sources, hyp_table, hyp_shard=shard_of(rank, world), **kw)
-            try:
-                batch.run(stream)
-                out = batch.results(stream)
-                keys = torch.from_numpy(out["best_key"].astype(np.int64)).to(dev)
-                detail = torch.from_numpy(local_best_detail(batch, out)).to(dev)
-                centres = batch.centres
-                h2d, d2h, local_passes = batch.h2d_bytes, batch.d2h_bytes, out["stats"]["passes"]
-            finally:
-                batch.close()
-            gkeys, gdetail = reduce_best(keys, detail, group)
-            gk = gkeys.cpu().numpy().astype(np.uint64)
-            gd = gdetail.cpu().numpy()
+            centres = batch.centres
+            packed = torch.empty((n_plots, PACK_WORDS), dtype=torch.int64, device=dev)
         else:
             # ---- fewer hypotheses than ranks (e.g. one start pose per plot): shard the PLOTS, gather the rows
             mine = plot_shard(n_plots, rank, world)
@@ -116,37 +114,32 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
             if centres_all is None:
                 centres_all = np.array([np.asarray(s, dtype=np.float64)[:, :2].mean(axis=0) for s in sources])
             centres = np.asarray(centres_all, dtype=np.float64).reshape(n_plots, 2)
-            ncol = len(DETAIL_FIELDS) + 2   # + the packed key as two exactly-representable halves
-            if len(mine):
-                batch = IcpBatch(index, [sources[p] for p in mine], hyp_table, centres=centres[mine], **kw)
-                try:
-                    batch.run(stream)
-                    out = batch.results(stream)
-                    k64 = out["best_key"].astype(np.uint64)
-                    local = np.concatenate([local_best_detail(batch, out), (k64 >> np.uint64(32)).astype(np.float64)[:, None],
-                                            (k64 & np.uint64(0xFFFFFFFF)).astype(np.float64)[:, None]], axis=1)
-                    h2d, d2h, local_passes = batch.h2d_bytes, batch.d2h_bytes, out["stats"]["passes"]
-                finally:
-                    batch.close()
+            n_rows = (n_plots + world - 1) // world
+            packed = torch.zeros((n_rows, PACK_WORDS), dtype=torch.int64, device=dev)
+            batch = IcpBatch(index, [sources[p] for p in mine], hyp_table, centres=centres[mine], **kw) if len(mine) else None
+        try:
+            if batch is not None:
+                batch.run(stream)
+                gathered = exchange_best(batch, packed, group, stream)
+                h2d = batch.h2d_bytes
             else:
-                local, h2d, d2h, local_passes = np.zeros((0, ncol)), 0, 0, 0
-            full = gather_plot_shards(torch.from_numpy(local).to(dev), mine, n_plots, group).cpu().numpy()
-            gd = full[:, :len(DETAIL_FIELDS)]
-            gk = (full[:, -2].astype(np.uint64) << np.uint64(32)) | full[:, -1].astype(np.uint64)
-        passes = torch.tensor([local_passes], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(passes, op=dist.ReduceOp.SUM, group=group)
+                gathered = gather_packed(packed, group)
+                h2d = 0
+            g = gathered.cpu().numpy()                       # the one read-back: world x rows x 96 bytes
+        finally:
+            if batch is not None:
+                batch.close()
+        gk, rows, passes = select_best(g, by_plots=by_plots, n_plots=n_plots)
         res = decode_best_keys(gk)
         res["best_key"] = gk
-        rows = {f: gd[:, i] for i, f in enumerate(DETAIL_FIELDS)}
-        res["best_transform"] = np.stack([compose_world_transform({f: rows[f][p] for f in DETAIL_FIELDS}, centres[p])
-                                          for p in range(n_plots)])
+        res["best_row"] = rows
+        res["best_transform"] = np.stack([compose_world_transform(rows[p], centres[p]) for p in range(n_plots)])
         res["k"] = rows["k"].astype(np.int64)
-        res["rmse"], res["frmsd"] = rows["rmse"], rows["frmsd"]
-        res["passes_local"] = local_passes
-        res["passes_global"] = int(passes.item())
+        res["rmse"], res["frmsd"] = rows["rmse"].copy(), rows["frmsd"].copy()
+        res["passes_local"] = int(passes[rank])
+        res["passes_global"] = int(passes.sum())
         res["h2d_bytes"] = h2d + (int(np.asarray(target).nbytes) if own else 0)
-        res["d2h_bytes"] = d2h + int(gk.nbytes + gd.nbytes)
+        res["d2h_bytes"] = int(g.nbytes)
         return res
     finally:
         if own:

@@ -177,6 +177,11 @@ FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_
 /* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then
  * all-reduced with MIN over NCCL). */
 FICP_API int ficp_batch_copy_best_keys_device(ficp_batch* b, void* dst_dev, void* stream);
+/* enqueue only: packs this GPU's best registration per plot into caller DEVICE memory, 12 x 8 bytes per plot:
+ * word 0 the packed key, words 1..10 the ficp_hyp_result row (80 bytes) of that hypothesis, word 11 the
+ * hypothesis-iterations this GPU ran.  One NCCL all_gather of these records is the whole multi-GPU exchange
+ * (coregistrationgame_b200/dist.py); the winner per plot is the record with the smallest key. */
+FICP_API int ficp_batch_pack_best_device(ficp_batch* b, void* dst_dev, void* stream);
 /* per-pass trace of a batch created with trace_passes > 0 (waits for `stream`).  For ICP c = plot * n_hyp_local + j and
  * pass p < min(passes of that ICP, trace_passes), entry t = (c * trace_passes + p) * trace_stride + tree:
  *   idx_out[t]    original target row of the tree's nearest neighbour (`tree.query`, ficp.py:70; lowest row among ties)

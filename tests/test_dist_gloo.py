@@ -20,11 +20,27 @@ def _free_port():
     return p
 
 
+def _pack(keys, rank, n_plots, passes):
+    """What ficp_batch_pack_best_device writes: key, ten row words (here: a recognisable payload), passes of the rank."""
+    from coregistrationgame_b200 import _lib
+    from coregistrationgame_b200.dist import PACK_WORDS
+    rec = np.zeros((n_plots, PACK_WORDS), dtype=np.int64)
+    rec[:, 0] = keys
+    rows = np.zeros(n_plots, dtype=_lib.HYP_RESULT_DTYPE)
+    rows["m00"] = 1.0 + rank
+    rows["cx"] = (keys.astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.float64)     # the hypothesis id
+    rows["k"] = 100 + rank
+    rows["passes"] = 7
+    rec[:, 1:11] = rows.view(np.int64).reshape(n_plots, 10)
+    rec[:, 11] = passes
+    return rec
+
+
 def _worker(rank, world, port, n_plots, n_hyp, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from coregistrationgame_b200.dist import reduce_best, shard_of
+    from coregistrationgame_b200.dist import gather_packed, select_best, shard_of
     rng = np.random.default_rng(123)                      # same table on every rank
     score = rng.uniform(0.1, 5.0, (n_plots, n_hyp))
     score[1, :] = np.inf                                  # a plot where every hypothesis is disqualified
@@ -32,19 +48,17 @@ def _worker(rank, world, port, n_plots, n_hyp, q):
     begin, stride = shard_of(rank, world)
     mine = np.arange(begin, n_hyp, stride)
     keys = np.empty(n_plots, dtype=np.int64)
-    detail = np.zeros((n_plots, 3))
     for p in range(n_plots):
         ks = np.array([orc.pack_best_key(score[p, h], h) for h in mine], dtype=np.uint64)
-        j = int(np.argmin(ks))
-        keys[p] = np.int64(ks[j])
-        detail[p] = [mine[j], score[p, mine[j]], rank]
-    gk, gd = reduce_best(torch.from_numpy(keys), torch.from_numpy(detail))
-    q.put((rank, gk.numpy().copy(), gd.numpy().copy(), score))
+        keys[p] = np.int64(ks.min())
+    g = gather_packed(torch.from_numpy(_pack(keys, rank, n_plots, 1000 + rank)))       # the ONE collective of the path
+    gk, rows, passes = select_best(g.numpy())
+    q.put((rank, gk.copy(), rows.copy(), passes.copy(), score))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_reduce_best_two_ranks_gloo():
+def test_exchange_best_two_ranks_gloo():
     world, n_plots, n_hyp = 2, 4, 16
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -57,26 +71,30 @@ def test_reduce_best_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     outs.sort(key=lambda t: t[0])
-    score = outs[0][3]
-    want = np.array([min(int(orc.pack_best_key(score[p, h], h)) for h in range(n_hyp)) for p in range(n_plots)], dtype=np.int64)
-    for rank, gk, gd, _ in outs:
+    score = outs[0][4]
+    want = np.array([min(int(orc.pack_best_key(score[p, h], h)) for h in range(n_hyp)) for p in range(n_plots)], dtype=np.uint64)
+    for rank, gk, rows, passes, _ in outs:
         np.testing.assert_array_equal(gk, want)                     # identical winner on every rank
-        win = (gk.astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(int)
-        np.testing.assert_array_equal(gd[:, 0], win)                # payload comes from the owner of the winner
-        np.testing.assert_array_equal(gd[:, 2], win % world)
-    assert (outs[0][1].astype(np.uint64)[2] & np.uint64(0xFFFFFFFF)) == 5   # tie -> lowest id
-    assert (outs[0][1].astype(np.uint64)[1] & np.uint64(0xFFFFFFFF)) == 0   # all disqualified -> id 0, score inf
+        win = (gk & np.uint64(0xFFFFFFFF)).astype(int)
+        np.testing.assert_array_equal(rows["cx"], win)              # the row comes from the owner of the winner
+        np.testing.assert_array_equal(rows["m00"], 1.0 + win % world)
+        np.testing.assert_array_equal(rows["k"], 100 + win % world)
+        np.testing.assert_array_equal(passes, [1000, 1001])         # pass counts piggy-back on the same collective
+    assert (outs[0][1][2] & np.uint64(0xFFFFFFFF)) == 5             # tie -> lowest id
+    assert (outs[0][1][1] & np.uint64(0xFFFFFFFF)) == 0             # all disqualified -> id 0, score inf
 
 
 def _gather_worker(rank, world, port, n_plots, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from coregistrationgame_b200.dist import gather_plot_shards, plot_shard
+    from coregistrationgame_b200.dist import PACK_WORDS, gather_packed, plot_shard, select_best
     mine = plot_shard(n_plots, rank, world)
-    local = np.stack([np.array([p, 10.0 * p + 0.5, rank], dtype=np.float64) for p in mine]) if len(mine) else np.zeros((0, 3))
-    full = gather_plot_shards(torch.from_numpy(local), mine, n_plots)
-    q.put((rank, full.numpy().copy()))
+    n_rows = (n_plots + world - 1) // world
+    packed = np.zeros((n_rows, PACK_WORDS), dtype=np.int64)
+    packed[:len(mine)] = _pack(np.array([orc.pack_best_key(0.5 + p, 0) for p in mine], dtype=np.uint64).astype(np.int64), rank, len(mine), 50 + rank)
+    gk, rows, passes = select_best(gather_packed(torch.from_numpy(packed)).numpy(), by_plots=True, n_plots=n_plots)
+    q.put((rank, gk.copy(), rows.copy(), passes.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -93,9 +111,11 @@ def test_plot_sharding_gather_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = np.stack([np.array([p, 10.0 * p + 0.5, p % world]) for p in range(n_plots)])
-    for _, full in outs:
-        np.testing.assert_array_equal(full, want)          # every plot exactly once, from its owner
+    want = np.array([orc.pack_best_key(0.5 + p, 0) for p in range(n_plots)], dtype=np.uint64)
+    for _, gk, rows, passes in outs:
+        np.testing.assert_array_equal(gk, want)                     # every plot exactly once, from its owner
+        np.testing.assert_array_equal(rows["m00"], 1.0 + np.arange(n_plots) % world)
+        np.testing.assert_array_equal(passes, [50, 51])
 
 
 def test_shards_partition_the_hypotheses():
@@ -107,9 +127,12 @@ def test_shards_partition_the_hypotheses():
         assert sorted(seen.tolist()) == list(range(4096))
 
 
-def test_reduce_best_single_process_passthrough():
-    from coregistrationgame_b200.dist import reduce_best
-    k = torch.tensor([5, 3], dtype=torch.int64)
-    d = torch.ones(2, 4, dtype=torch.float64)
-    gk, gd = reduce_best(k, d)
-    assert torch.equal(gk, k) and torch.equal(gd, d)
+def test_single_process_passthrough():
+    from coregistrationgame_b200.dist import gather_packed, select_best
+    keys = np.array([orc.pack_best_key(0.25, 3), orc.pack_best_key(1.5, 0)], dtype=np.uint64).astype(np.int64)
+    g = gather_packed(torch.from_numpy(_pack(keys, 0, 2, 9)))
+    assert tuple(g.shape) == (1, 2, 12)
+    gk, rows, passes = select_best(g.numpy())
+    np.testing.assert_array_equal(gk.astype(np.int64), keys)
+    np.testing.assert_array_equal(rows["cx"], [3, 0])
+    assert passes.tolist() == [9]

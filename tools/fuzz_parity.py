@@ -87,7 +87,10 @@ def check(src, tgt, hyp, kw, launch):
             # residuals equal to the last ulp across the trim boundary (e.g. the two mirror-image residuals of a
             # 2-point fit): which tree is the k-th is decided by rounding - parity is defined modulo such ties
             ds = np.sort(r.d2)
-            if 0 < r.k < len(ds) and abs(ds[r.k] - ds[r.k - 1]) <= 1e-11 * max(ds[r.k], 1e-300):
+            # (rounding of the coordinates themselves counts: at a UTM northing of 6.5e6 one ulp is 9e-10 m, which moves
+            # a squared distance d2 by ~2 sqrt(d2) ulp - seed 11 case 2989: two residuals 9e-11 apart at d = 0.129 m)
+            ulp = 2.3e-16 * float(np.abs(tgt[:, :2]).max())
+            if 0 < r.k < len(ds) and abs(ds[r.k] - ds[r.k - 1]) <= max(1e-11 * ds[r.k], 16.0 * np.sqrt(ds[r.k]) * ulp, 1e-300):
                 real[h] = False
             uniq = np.unique(r.idx[r.inliers])
             if r.k > 1 and len(uniq) < 2:

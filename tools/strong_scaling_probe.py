@@ -17,6 +17,7 @@ ap.add_argument("--trees", type=int, default=500)
 ap.add_argument("--points", type=int, default=1_000_000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--worlds", default="1,2,4,8")
+ap.add_argument("--kernels", default="warp,cta,cta1,auto")
 args = ap.parse_args()
 tgt, plots, _ = syn.synthetic_scene(args.points, args.trees, seed=3, dims=args.dims, n_plots=1, hidden_pose=True)
 hyp = hypothesis_table(128, flips=(0, 1), translations=translation_lattice(4, 2.5))
@@ -27,6 +28,8 @@ base = None
 for w in [int(x) for x in args.worlds.split(",")]:
     for name, kw in (("warp", dict(cta_per_icp=False)), ("cta", dict(cta_per_icp=True)), ("cta1", dict(cta_per_icp=True, ctas_per_sm=1)),
                      ("auto", dict())):
+        if name not in args.kernels.split(","):
+            continue
         b = IcpBatch(ti, [plots[0]], hyp, hyp_shard=(0, w), **kw)
         for _ in range(2):
             b.run(stream)
