@@ -507,7 +507,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // batch smaller than that is bounded by the serial chain of its longest ICP, and the CTA-per-ICP kernel (icp_team.cu:
     // every phase of a pass cooperative across 32 e threads) runs that chain several times faster.  Plots of <= 32
     // trees (e == 1) are one warp either way.  Auto: below kCtaAutoIcpsPerSm ICPs per SM (measured, profiles/r02_summary.md).
-    constexpr long long kCtaAutoIcpsPerSm = 12;
+    constexpr long long kCtaAutoIcpsPerSm = 8;
     const bool cta_mode = (e >= 2) && (prm->cta_per_icp == 2 || (prm->cta_per_icp == 0 && prm->team_warps == 0 && prm->no_helpers == 0 &&
                                                                  prm->warps_per_cta == 0 && n_icps_all <= kCtaAutoIcpsPerSm * sms));
     // Elastic kernel: warps without an ICP of their own help the ICPs in flight in their CTA.  It pays while the

@@ -207,6 +207,8 @@ __device__ __forceinline__ int nn_search_group(const WindowAcc& acc, const GridG
                                                int& cy, int& lb_hi, int& pos2) {
     int status = 0, lb = kHiInf;
     best = kInf; bestpos = -1; pos2 = -1; cx = 0; cy = 0;
+    lb_hi = kHiInf;
+    if (__ballot_sync(kFull, active) == 0u) return 0;   // a warp without a query has nothing to merge either
     Top3 top = top3_empty();
     if (active) {
         cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);

@@ -54,8 +54,8 @@ __host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, 
     L.slist = take((size_t)t * 2);   // queries the group search hands to the one-lane search (possible exact ties)
     L.sidx = take((size_t)t * 2);
     L.kbuf = take((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms ux, uy
-    L.sdd = take((size_t)t * 8);     // d2 in trim order; later the fit term vx
-    L.tmp = take((size_t)t * 8);     // fit term vy
+    L.sdd = take((size_t)(t + 32) * 8);   // d2 in trim order (padded: p + p / E); later the fit term vx
+    L.tmp = take((size_t)(t + 32) * 8);   // chunk-serial partial sums of the scan (padded); later the fit term vy
     L.misc = take(1536);
     L.total = o;
     return L;
@@ -100,6 +100,32 @@ __device__ __forceinline__ unsigned block_sort32(unsigned key, unsigned* buf, in
     return key;
 }
 
+// Odd-even transposition rounds on the (d2, tree index) pairs in trim order until a round swaps nothing (-> true) or
+// `max_rounds` rounds are spent (-> false).  `sdd` uses the padded layout of the scan (PAD).
+#define PAD(p) ((p) + (p) / E)
+constexpr int kRepairMaxInversions = 12;   // adjacent inversions above which the order is rebuilt by the block sort
+constexpr int kRepairMaxRounds = 5;
+template <int T, int E>
+__device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* sidx, int tid, int max_rounds) {
+    for (int round = 0; round < max_rounds; ++round) {
+        bool sw = false;
+#pragma unroll 1
+        for (int par = 0; par < 2; ++par) {
+            if ((tid & 1) == par && tid + 1 < T) {
+                const double a = sdd[PAD(tid)], b = sdd[PAD(tid + 1)];
+                const unsigned short ia = sidx[tid], ib = sidx[tid + 1];
+                if (key_greater(a, ia, b, ib)) {
+                    sdd[PAD(tid)] = b; sdd[PAD(tid + 1)] = a; sidx[tid] = ib; sidx[tid + 1] = ia;
+                    sw = true;
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(sw)) return true;
+    }
+    return false;
+}
+
 // min / lexicographic arg-min over the NW per-warp partials in shared memory, by every warp for itself (5 shuffles)
 __device__ __forceinline__ double warp_min_of(const double* red, int nw, int lane) {
     double v = (lane < nw) ? red[lane] : kInf;
@@ -139,6 +165,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     double* f_uy = reinterpret_cast<double*>(smem + L.kbuf) + T;
     double* f_vx = reinterpret_cast<double*>(smem + L.sdd);
     double* f_vy = reinterpret_cast<double*>(smem + L.tmp);
+    double* spart = reinterpret_cast<double*>(smem + L.tmp);
     unsigned short* finl = list;                                       // inlier flags of the fit (the search list is dead then)
     TeamMisc* M = reinterpret_cast<TeamMisc*>(smem + L.misc);
 
@@ -225,6 +252,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
         int passes = 0;
         unsigned n_fix = 0, n_searched = 0, n_deferred = 0;
         if (tid >= n) { sd2[tid] = kInf; snn[tid] = -1; }   // padding never changes
+        sidx[tid] = (unsigned short)tid;                     // no previous trim order yet
         PassOut po{0, kInf, 0.0, -1.0, -1};
         // position of this thread in trim order: chunk (= lane of the one-warp kernel) and element inside it
         const int lp = tid / E, r = tid - lp * E;
@@ -323,55 +351,53 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 __syncthreads();
 
                 // ================= trimming (ficp.py:62-63,73-86)
+                // Trim order = the exact order of (d2, tree index).  Passes of a converging ICP barely change it, so
+                // the PREVIOUS pass's order is tried first: verified against the new distances, repaired by a few
+                // odd-even transposition rounds when only a handful of neighbours swapped, and only otherwise rebuilt by
+                // the block sort.  The order is a total order, so every route ends in the same permutation.
                 const double my_d2 = sd2[tid];
-                // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
-                // (d2, index) order is verified below and repaired where codes collide
-                const unsigned fb = __float_as_uint(__double2float_rd(my_d2));
-                unsigned key = ((fb >> (IB - 1)) << IB) | (unsigned)tid;
-                key = block_sort32<T>(key, kbuf, tid);
-                int sidx_t = (int)(key & ((1u << IB) - 1u));
+                int sidx_t = sidx[tid];
                 double dd = sd2[sidx_t];
-                sdd[tid] = dd;
-                sidx[tid] = (unsigned short)sidx_t;
+                sdd[PAD(tid)] = dd;
                 __syncthreads();
+                bool sorted;
                 {
-                    // verify the exact (d2, index) order; odd-even transposition rounds where quantised codes collided
                     bool inv = false;
-                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[tid + 1], (unsigned)sidx[tid + 1]);
+                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[PAD(tid + 1)], (unsigned)sidx[tid + 1]);
+                    const int ninv = __syncthreads_count(inv);
+                    sorted = (ninv == 0);
+                    if (!sorted && ninv <= kRepairMaxInversions) sorted = team_repair_order<T, E>(sdd, sidx, tid, kRepairMaxRounds);
+                }
+                if (!sorted) {
+                    // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
+                    // order is verified afterwards and repaired where quantised codes collide
+                    const unsigned fb = __float_as_uint(__double2float_rd(my_d2));
+                    unsigned key = ((fb >> (IB - 1)) << IB) | (unsigned)tid;
+                    key = block_sort32<T>(key, kbuf, tid);
+                    sidx_t = (int)(key & ((1u << IB) - 1u));
+                    dd = sd2[sidx_t];
+                    __syncthreads();    // the verification above may still be reading the old order
+                    sdd[PAD(tid)] = dd;
+                    sidx[tid] = (unsigned short)sidx_t;
+                    __syncthreads();
+                    bool inv = false;
+                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[PAD(tid + 1)], (unsigned)sidx[tid + 1]);
                     if (__syncthreads_or(inv)) {
                         ++n_fix;
-                        bool sw;
-                        do {
-                            sw = false;
-#pragma unroll 1
-                            for (int par = 0; par < 2; ++par) {
-                                if ((tid & 1) == par && tid + 1 < T) {
-                                    const double a = sdd[tid], b = sdd[tid + 1];
-                                    const unsigned short ia = sidx[tid], ib = sidx[tid + 1];
-                                    if (key_greater(a, ia, b, ib)) {
-                                        sdd[tid] = b; sdd[tid + 1] = a; sidx[tid] = ib; sidx[tid + 1] = ia;
-                                        sw = true;
-                                    }
-                                }
-                                __syncthreads();
-                            }
-                        } while (__syncthreads_or(sw));
-                        dd = sdd[tid];
-                        sidx_t = sidx[tid];
+                        (void)team_repair_order<T, E>(sdd, sidx, tid, 1 << 30);
                     }
                 }
                 // inclusive prefix sums S_k of d2 in trim order, in the association of the one-warp kernel: serial
-                // inside the chunk of E consecutive positions, Kogge-Stone over the 32 chunk totals, prefix + partial
-                double run = 0.0;
-                {
-                    const double* chunk = sdd + lp * E;
-#pragma unroll 1
-                    for (int q = 0; q <= r; ++q) run = __dadd_rn(run, chunk[q]);
-                }
-                if (r == E - 1) M->stot[lp] = run;
-                __syncthreads();
+                // inside the chunk of E consecutive positions (lane l of warp 0 walks chunk l; the padded layout keeps the
+                // 32 lanes on different banks), Kogge-Stone over the 32 chunk totals, prefix + partial
                 if (warp == 0) {
-                    double inc = M->stot[lane];
+                    double run = 0.0;
+#pragma unroll 4
+                    for (int q = 0; q < E; ++q) {
+                        run = __dadd_rn(run, sdd[PAD(lane * E + q)]);
+                        spart[PAD(lane * E + q)] = run;
+                    }
+                    double inc = run;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const double t = __shfl_up_sync(kFull, inc, o);
@@ -382,7 +408,8 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     M->sexcl[lane] = excl;
                 }
                 __syncthreads();
-                const double S = __dadd_rn(M->sexcl[lp], run);
+                sidx_t = sidx[tid];
+                const double S = __dadd_rn(M->sexcl[lp], spart[PAD(tid)]);
 
                 // subset size: first strict minimum of FRMSD(k) = c_k sqrt(S_k / k)  (ficp.py:80-85)
                 int kstar;
