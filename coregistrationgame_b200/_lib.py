@@ -69,6 +69,7 @@ SIGNATURES = {
     "ficp_batch_results": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_copy_best_keys_device": (c_i32, [c_vp, c_vp, c_vp]),
     "ficp_batch_pack_best_device": (c_i32, [c_vp, c_vp, c_vp]),
+    "ficp_batch_best": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_trace": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_destroy": (None, [c_vp]),
 }

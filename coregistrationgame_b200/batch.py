@@ -210,6 +210,22 @@ class IcpBatch:
         ``device_ptr`` - key, the 80-byte result row, this GPU's hypothesis-iterations (see dist.PACK_WORDS)."""
         _lib.check(_lib.load().ficp_batch_pack_best_device(self._h, C.c_void_p(int(device_ptr)), _stream_ptr(stream)))
 
+    def best(self, stream=None):
+        """Synchronise and read back only the winner per plot (96 bytes each) - the per-hypothesis table stays on the device.
+        Returns ``best_key``, ``best_hyp``, ``best_score``, ``best_row`` (HYP_RESULT_DTYPE per plot) and ``stats``."""
+        packed = np.empty((self.n_plots, 12), dtype=np.uint64)
+        stats = np.zeros(8, dtype=np.uint64)
+        _lib.check(_lib.load().ficp_batch_best(self._h, _lib.ptr(packed), _lib.ptr(stats), _stream_ptr(stream)), "ficp_batch_best")
+        keys = np.ascontiguousarray(packed[:, 0])
+        out = {"best_key": keys, "best_row": np.ascontiguousarray(packed[:, 1:11]).view(_lib.HYP_RESULT_DTYPE).reshape(-1),
+               "hyp": None, "final_xy": None,
+               "stats": {"passes": int(stats[0]), "global_path_queries": int(stats[1]),
+                         "windows_disabled": int(stats[2]), "fixup_rounds": int(stats[3]), "queries": int(stats[4]),
+                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6])}}
+        out.update(decode_best_keys(keys))
+        self.d2h_bytes = int(packed.nbytes + stats.nbytes)
+        return out
+
     def results(self, stream=None, per_hypothesis=True):
         """Synchronise and read back.  Returns a dict:
         ``hyp`` structured array (n_plots, n_hyp_local) of per-hypothesis outcomes (see HYP_RESULT_DTYPE),
@@ -273,33 +289,44 @@ def decode_best_keys(keys):
     return {"best_hyp": (keys & np.uint64(0xFFFFFFFF)).astype(np.int64), "best_score": score}
 
 
+def compose_world_transforms(rows, centres):
+    """final = M (p - centre) + c  ->  [M | c - M centre] for many result rows at once: (n, 2, 3).  Elementwise arithmetic in
+    one fixed order, so one row or ten thousand give the same bits."""
+    f = lambda name: np.asarray(rows[name], dtype=np.float64).reshape(-1)
+    c = np.asarray(centres, dtype=np.float64).reshape(-1, 2)
+    m00, m01, m10, m11 = f("m00"), f("m01"), f("m10"), f("m11")
+    out = np.empty((m00.shape[0], 2, 3), dtype=np.float64)
+    out[:, 0, 0], out[:, 0, 1], out[:, 1, 0], out[:, 1, 1] = m00, m01, m10, m11
+    out[:, 0, 2] = f("cx") - (m00 * c[:, 0] + m01 * c[:, 1])
+    out[:, 1, 2] = f("cy") - (m10 * c[:, 0] + m11 * c[:, 1])
+    return out
+
+
 def compose_world_transform(row, centre):
-    """final = M (p - centre) + c  ->  [M | c - M centre]."""
-    m = np.array([[row["m00"], row["m01"]], [row["m10"], row["m11"]]], dtype=np.float64)
-    b = np.array([row["cx"], row["cy"]]) - m @ np.asarray(centre, dtype=np.float64)
-    return np.hstack([m, b[:, None]])
+    """2x3 world transform [A | b] of ONE result row (final = A p + b)."""
+    return compose_world_transforms(row, centre)[0]
 
 
-def register_batch(sources, target, hyp_table=None, index=None, **kw):
+def register_batch(sources, target, hyp_table=None, index=None, per_hypothesis=True, **kw):
     """One-call batched registration from HOST arrays (the end-to-end path bench.py times as ``e2e``):
     build the target index (unless one is passed), upload plots + hypotheses, run, read back.
 
     Returns per plot: best hypothesis id, its score (final FRMSD, fp32-rounded), its 2x3 transform,
-    trimmed size ``k``, RMSE and the number of passes, plus the per-hypothesis table."""
+    trimmed size ``k``, RMSE and the number of passes (``best_row``); with ``per_hypothesis`` (default) also the whole
+    per-hypothesis table ``hyp`` - without it only the winners (96 bytes per plot) leave the device."""
     own = index is None
     if own:
         index = TargetIndex(target)
     try:
         batch = IcpBatch(index, sources, hyp_table, **kw)
         try:
-            out = batch.run().results()
-            best_rows = []
-            for p in range(batch.n_plots):
-                j = (int(out["best_hyp"][p]) - batch.hyp_begin) // batch.hyp_stride
-                best_rows.append(out["hyp"][p, j])
-            out["best_row"] = np.array(best_rows, dtype=_lib.HYP_RESULT_DTYPE)
-            out["best_transform"] = np.stack([compose_world_transform(best_rows[p], batch.centres[p])
-                                              for p in range(batch.n_plots)])
+            if per_hypothesis:
+                out = batch.run().results()
+                j = (out["best_hyp"] - batch.hyp_begin) // batch.hyp_stride
+                out["best_row"] = out["hyp"][np.arange(batch.n_plots), j].copy()
+            else:
+                out = batch.run().best()
+            out["best_transform"] = compose_world_transforms(out["best_row"], batch.centres)
             out["h2d_bytes"] = batch.h2d_bytes + (int(np.asarray(target).nbytes) if own else 0)
             out["d2h_bytes"] = batch.d2h_bytes
             out["launch"] = dict(batch.info)

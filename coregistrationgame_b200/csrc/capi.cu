@@ -735,6 +735,22 @@ int ficp_batch_pack_best_device(ficp_batch* bh, void* dst_dev, void* stream) {
     return rc;
 }
 
+int ficp_batch_best(ficp_batch* bh, uint64_t* packed_out, uint64_t* stats, void* stream) {
+    if (!bh || !packed_out) { set_error("ficp_batch_best: null pointer"); return kErrInvalid; }
+    Batch* b = reinterpret_cast<Batch*>(bh);
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<unsigned long long> tmp(s);
+    int rc;
+    if ((rc = tmp.alloc((size_t)b->n_plots * 12))) return rc;
+    if ((rc = launch_pack_best(b->d_best, b->d_results, b->n_plots, b->n_hyp_local, b->params.hyp_begin, b->params.hyp_stride,
+                               b->d_stats, tmp.p, s)))
+        return rc;
+    FICP_CUDA(cudaMemcpyAsync(packed_out, tmp.p, sizeof(uint64_t) * 12 * (size_t)b->n_plots, cudaMemcpyDeviceToHost, s));
+    if (stats) FICP_CUDA(cudaMemcpyAsync(stats, b->d_stats, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaStreamSynchronize(s));
+    return kOk;
+}
+
 int ficp_batch_trace(ficp_batch* bh, int32_t* idx_out, double* d2_out, uint8_t* inlier_out, int32_t* k_out,
                      double* frmsd_out, void* stream) {
     if (!bh) { set_error("ficp_batch_trace: null batch"); return kErrInvalid; }

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .batch import IcpBatch, TargetIndex, compose_world_transform, decode_best_keys
+from .batch import IcpBatch, TargetIndex, compose_world_transforms, decode_best_keys
 
 PACK_WORDS = 12          # int64 words per plot record: key, 10 words of ficp_hyp_result, passes of the rank
 
@@ -133,7 +133,7 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
         res = decode_best_keys(gk)
         res["best_key"] = gk
         res["best_row"] = rows
-        res["best_transform"] = np.stack([compose_world_transform(rows[p], centres[p]) for p in range(n_plots)])
+        res["best_transform"] = compose_world_transforms(rows, centres)
         res["k"] = rows["k"].astype(np.int64)
         res["rmse"], res["frmsd"] = rows["rmse"].copy(), rows["frmsd"].copy()
         res["passes_local"] = int(passes[rank])

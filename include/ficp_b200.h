@@ -182,6 +182,10 @@ FICP_API int ficp_batch_copy_best_keys_device(ficp_batch* b, void* dst_dev, void
  * hypothesis-iterations this GPU ran.  One NCCL all_gather of these records is the whole multi-GPU exchange
  * (coregistrationgame_b200/dist.py); the winner per plot is the record with the smallest key. */
 FICP_API int ficp_batch_pack_best_device(ficp_batch* b, void* dst_dev, void* stream);
+/* waits for `stream` and returns ONLY the best registration per plot (host buffers): packed_out[n_plots * 12] in the layout
+ * of ficp_batch_pack_best_device (key, 80-byte result row, hypothesis-iterations), stats[8] as in ficp_batch_results.
+ * The per-hypothesis table (80 B x plots x hypotheses) stays on the device: what app.py:658-661 needs is the winner. */
+FICP_API int ficp_batch_best(ficp_batch* b, uint64_t* packed_out, uint64_t* stats, void* stream);
 /* per-pass trace of a batch created with trace_passes > 0 (waits for `stream`).  For ICP c = plot * n_hyp_local + j and
  * pass p < min(passes of that ICP, trace_passes), entry t = (c * trace_passes + p) * trace_stride + tree:
  *   idx_out[t]    original target row of the tree's nearest neighbour (`tree.query`, ficp.py:70; lowest row among ties)
