@@ -20,7 +20,8 @@ P = C.POINTER
 
 class TargetInfo(C.Structure):
     _fields_ = [("m", c_i64), ("has_z", c_i32), ("grid_w", c_i32), ("grid_h", c_i32), ("cell", c_f64),
-                ("x0", c_f64), ("y0", c_f64), ("bbox", c_f64 * 4), ("build_ms", c_f64)]
+                ("x0", c_f64), ("y0", c_f64), ("bbox", c_f64 * 4), ("build_ms", c_f64), ("clamped", c_i32),
+                ("max_cell_pts", c_i32)]
 
 
 class BatchParams(C.Structure):

@@ -100,7 +100,8 @@ class TargetIndex:
         ti = _lib.TargetInfo()
         _lib.check(_lib.load().ficp_target_get_info(self.handle, C.byref(ti)))
         return {"m": ti.m, "has_z": bool(ti.has_z), "grid_w": ti.grid_w, "grid_h": ti.grid_h, "cell": ti.cell,
-                "x0": ti.x0, "y0": ti.y0, "bbox": tuple(ti.bbox), "build_ms": ti.build_ms}
+                "x0": ti.x0, "y0": ti.y0, "bbox": tuple(ti.bbox), "build_ms": ti.build_ms, "clamped": bool(ti.clamped),
+                "max_cell_pts": int(ti.max_cell_pts)}
 
     def query(self, points, use_z=None, stream=None):
         """Exact NN of every row: (original target index int64, Euclidean distance float64)."""

@@ -192,6 +192,8 @@ int ficp_target_get_info(const ficp_target* th, ficp_target_info* info) {
     info->y0 = t->view.g.y0;
     for (int i = 0; i < 4; ++i) info->bbox[i] = t->bbox[i];
     info->build_ms = t->build_ms;
+    info->clamped = t->view.g.clamped;
+    info->max_cell_pts = (int32_t)std::min<long long>(t->max_cell_pts, 2147483647LL);
     return kOk;
 }
 

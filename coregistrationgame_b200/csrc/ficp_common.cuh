@@ -41,10 +41,16 @@ constexpr double kInf = __builtin_huge_val();  // +inf (nvcc and gcc both accept
 
 // Geometry of the uniform grid over the Layer-2 (CHM) points.
 struct GridGeom {
-    double x0, y0;     // lower-left corner (min x, min y of the target)
+    double x0, y0;     // lower-left corner of the grid
     double h, inv_h;   // cell edge and its reciprocal
     double eps;        // conservative slack for cell-box bounds (covers binning round-off)
     int gw, gh;        // cells per row / number of rows
+    // True bounding box of ALL target points.  Normally the grid spans it.  For skewed targets (a stray placeholder
+    // row at (0, 0) in UTM data, a far outlier, long thin tails) the grid spans a robust core extent instead and the
+    // points outside are CLAMPED into the border cells (`clamped` != 0): a border cell then reaches outward without
+    // bound, which the search's box tests account for; results stay exact either way.
+    double tx0, tx1, ty0, ty1;
+    int clamped, pad;
 };
 
 // Device view of a built target index (cell-sorted copy of the target + CSR cell table).  Two layouts:

@@ -63,6 +63,7 @@ struct Target {
     int* d_orig = nullptr;     // XY layout
     unsigned* d_cell_start = nullptr;
     float build_ms = 0.f;  // device time of the build kernels (CUDA events)
+    long long max_cell_pts = 0;  // heaviest cell (diagnostic: skew of the target)
     mutable UseEvent used;  // last enqueued work that reads the index (queries, ICP batches)
 };
 

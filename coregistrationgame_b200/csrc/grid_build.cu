@@ -3,12 +3,25 @@
 // Replaces the kd-tree construction the reference repeats on every ICP pass
 // (/root/reference/ficp.py:69 `cKDTree(self._xyz_or_xy(target))`); here it is built ONCE per target.
 //
-// Passes (all HBM-streaming, DESIGN.md "grid build": ~48 B of traffic per point):
-//   bbox      read xyz                     -> min/max + finiteness flag
-//   bin_count read xy, write cell id       -> per-cell histogram (L2 atomics)
-//   scan      exclusive prefix of the histogram -> cell_start (CSR)
-//   scatter   read xyz + cell id           -> cell-sorted records (XY: double2 + index; XYZ: one 32 B record)
-//   cell_sort orders each cell by original index, so the layout is deterministic (stable sort)
+// One stream-ordered chain, no host round-trip before the end (round 1 synchronised twice mid-build):
+//   geometry   read xyz: bounding box + finiteness; the last CTA to finish reduces the partials, takes the robust
+//              extent from a 1024-point sample (skewed targets, see below) and writes the grid geometry to DEVICE memory
+//   bin        read xy + geometry: cell id and arrival rank of every point (one L2 atomic per point)
+//   scan       single-pass chained scan (decoupled look-back) of the per-cell counts -> cell_start (CSR)
+//   scatter    read xyz + cell id + rank -> cell-sorted records (XY: double2 + index; XYZ: one 32 B record)
+//   order      cells of 2..32 points are put in original-index order by one thread each (a stable counting sort:
+//              the layout does not depend on atomic timing); heavier cells are queued ...
+//   heavy      ... and ordered by one warp each (odd-even transposition, cells up to 4096 points).  Cells above that
+//              keep arrival order: search RESULTS never depend on the order inside a cell (exact distance ties are
+//              settled by original index, tests/hostcheck), only the layout would.
+// HBM traffic ~116 B per point (DESIGN.md "grid build"); sizes that depend on the geometry (cell count) are bounded by
+// max(m, 1024) cells up front, so nothing has to come back to the host before the last kernel is enqueued.
+//
+// Skewed targets: the cell edge follows from extent and mean density, so ONE stray coordinate (a (0, 0)
+// placeholder row in UTM data) or long thin tails would put almost every point into a handful of cells.  The grid
+// therefore spans a ROBUST extent per axis - the central 99 % of a 1024-point sample, widened by a quarter - whenever the
+// full extent is more than 1.5x wider than that; points outside are clamped into the border cells (GridGeom::clamped),
+// which the search treats as unbounded outward.  Clean data (uniform stands) keeps the full bounding box, unclamped.
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -19,10 +32,24 @@ namespace ficp {
 namespace {
 
 constexpr int kT = 256;
+constexpr int kSample = 256;           // points sampled for the robust extent (one per thread of the last CTA)
+constexpr int kHeavyCap = 4096;        // heavy-cell queue entries
+constexpr int kHeavyMaxPts = 4096;     // cells above this keep arrival order
 
 struct BBox {
     double xmin, xmax, ymin, ymax;
     int nonfinite;
+};
+
+// device-resident build state (read back once, at the end)
+struct BuildState {
+    BBox bb;                  // true bounding box of all points + finiteness
+    GridGeom g;
+    long long nc;             // cells
+    unsigned ticket;          // geometry kernel: CTAs finished
+    unsigned scan_ticket;     // scan kernel: dynamic block ids
+    unsigned n_heavy;         // cells queued for the heavy-cell kernel
+    unsigned max_cell;        // largest cell (diagnostic)
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -36,9 +63,40 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// grid-stride partial bounding boxes; one BBox per block
-__global__ void __launch_bounds__(kT) bbox_kernel(const double* __restrict__ pts, long long m, int ld, int use_z,
-                                                  BBox* __restrict__ partial) {
+// Sorts the kSample (= kT) sample values of one axis by counting: thread i ranks its value among all (ties by index)
+// and drops it into its slot - no barriers inside, every read a shared-memory broadcast.
+__device__ void rank_sort_sample(const double* in, double* out) {
+    const double v = in[threadIdx.x];
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < kSample; ++j) {
+        const double o = in[j];
+        rank += (o < v || (o == v && j < (int)threadIdx.x)) ? 1 : 0;
+    }
+    out[rank] = v;
+}
+
+// Robust extent of one axis from the sorted sample (see the file header).  Returns clamped?.
+__device__ bool robust_axis(const double* sorted, int ns, double lo_all, double hi_all, double& lo, double& hi) {
+    lo = lo_all; hi = hi_all;
+    if (ns < 200) return false;
+    const int r = (ns + 127) / 128;                          // ~0.8 % from either end
+    const double a = sorted[r], b = sorted[ns - 1 - r], w = b - a;
+    if (!(hi_all - lo_all > 1.5 * w) || !(w >= 0.0)) return false;
+    if (w == 0.0) return false;                              // > 99 % of the sample on one coordinate: keep the full extent
+    lo = fmax(lo_all, a - 0.25 * w);
+    hi = fmin(hi_all, b + 0.25 * w);
+    return (lo > lo_all) || (hi < hi_all);
+}
+
+// grid-stride partial bounding boxes; the last CTA finishes the geometry
+__global__ void __launch_bounds__(kT) geometry_kernel(const double* __restrict__ pts, long long m, int ld, int use_z,
+                                                      double pts_per_cell, BBox* __restrict__ partial,
+                                                      BuildState* __restrict__ st) {
+    __shared__ BBox sh[kT / 32];
+    __shared__ double sx[kSample], sy[kSample], tx[kSample], ty[kSample];
+    static_assert(kSample == kT, "one sample per thread");
+    __shared__ bool last;
     double xmin = kInf, xmax = -kInf, ymin = kInf, ymax = -kInf;
     int bad = 0;
     for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < m; i += (long long)gridDim.x * kT) {
@@ -48,7 +106,6 @@ __global__ void __launch_bounds__(kT) bbox_kernel(const double* __restrict__ pts
         xmin = fmin(xmin, x); xmax = fmax(xmax, x);
         ymin = fmin(ymin, y); ymax = fmax(ymax, y);
     }
-    __shared__ BBox sh[kT / 32];
     xmin = warp_min(xmin); xmax = warp_max(xmax); ymin = warp_min(ymin); ymax = warp_max(ymax);
     bad = __any_sync(0xFFFFFFFFu, bad);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -62,114 +119,178 @@ __global__ void __launch_bounds__(kT) bbox_kernel(const double* __restrict__ pts
             b.nonfinite |= sh[i].nonfinite;
         }
         partial[blockIdx.x] = b;
+        __threadfence();
+        last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
     }
-}
-
-__global__ void bbox_final_kernel(const BBox* __restrict__ partial, int n, BBox* __restrict__ out) {
-    double xmin = kInf, xmax = -kInf, ymin = kInf, ymax = -kInf;
-    int bad = 0;
-    for (int i = threadIdx.x; i < n; i += 32) {
-        const BBox b = partial[i];
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // ---- last CTA: reduce the partials
+    xmin = kInf; xmax = -kInf; ymin = kInf; ymax = -kInf; bad = 0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kT) {
+        BBox b;
+        {
+            const double* pv = reinterpret_cast<const double*>(partial + i);   // written by other CTAs: read through L2
+            b.xmin = __ldcg(pv); b.xmax = __ldcg(pv + 1); b.ymin = __ldcg(pv + 2); b.ymax = __ldcg(pv + 3);
+            b.nonfinite = __ldcg(reinterpret_cast<const int*>(pv + 4));
+        }
         xmin = fmin(xmin, b.xmin); xmax = fmax(xmax, b.xmax);
         ymin = fmin(ymin, b.ymin); ymax = fmax(ymax, b.ymax);
         bad |= b.nonfinite;
     }
     xmin = warp_min(xmin); xmax = warp_max(xmax); ymin = warp_min(ymin); ymax = warp_max(ymax);
     bad = __any_sync(0xFFFFFFFFu, bad);
-    if (threadIdx.x == 0) *out = BBox{xmin, xmax, ymin, ymax, bad};
+    __syncthreads();
+    if (l == 0) sh[w] = BBox{xmin, xmax, ymin, ymax, bad};
+    __syncthreads();
+    BBox bb = sh[0];
+    for (int i = 1; i < kT / 32; ++i) {
+        bb.xmin = fmin(bb.xmin, sh[i].xmin); bb.xmax = fmax(bb.xmax, sh[i].xmax);
+        bb.ymin = fmin(bb.ymin, sh[i].ymin); bb.ymax = fmax(bb.ymax, sh[i].ymax);
+        bb.nonfinite |= sh[i].nonfinite;
+    }
+    // ---- robust extent from an evenly strided sample
+    const int ns = (int)((m < kSample) ? m : kSample);
+    {
+        const int k = threadIdx.x;
+        if (k < ns && !bb.nonfinite) {
+            const long long i = (long long)(((unsigned long long)k * (unsigned long long)m) / (unsigned long long)ns);
+            tx[k] = pts[i * ld]; ty[k] = pts[i * ld + 1];
+        } else {
+            tx[k] = kInf; ty[k] = kInf;      // sorts to the end
+        }
+    }
+    __syncthreads();
+    rank_sort_sample(tx, sx);
+    rank_sort_sample(ty, sy);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double x0, x1, y0, y1;
+    const bool cx = robust_axis(sx, ns, bb.xmin, bb.xmax, x0, x1);
+    const bool cy = robust_axis(sy, ns, bb.ymin, bb.ymax, y0, y1);
+    // ---- grid geometry: ~pts_per_cell points per cell on average over the (robust) extent
+    GridGeom gg;
+    const double ex = x1 - x0, ey = y1 - y0;
+    const double big = fmax(ex, ey);
+    double h;
+    if (!(big > 0.0)) {
+        h = 1.0;
+    } else {
+        const double exx = fmax(ex, big * 1e-6), eyy = fmax(ey, big * 1e-6);
+        h = sqrt(pts_per_cell * exx * eyy / (double)m);
+        if (!(h > 0.0) || !isfinite(h)) h = big;
+    }
+    const double max_cells = fmax((double)m, 1024.0);
+    for (;;) {
+        const double gw = floor(ex / h) + 1.0, gh = floor(ey / h) + 1.0;
+        if (gw * gh <= max_cells && gw < 2.0e9 && gh < 2.0e9) {
+            gg.gw = (int)gw;
+            gg.gh = (int)gh;
+            break;
+        }
+        h *= 1.25;
+    }
+    gg.x0 = x0; gg.y0 = y0; gg.h = h; gg.inv_h = 1.0 / h;
+    gg.eps = h * 1e-9 + (fabs(x0) + fabs(y0) + big) * 8e-16;
+    gg.tx0 = bb.xmin; gg.tx1 = bb.xmax; gg.ty0 = bb.ymin; gg.ty1 = bb.ymax;
+    gg.clamped = (cx || cy) ? 1 : 0;
+    gg.pad = 0;
+    if (bb.nonfinite) { gg.gw = 1; gg.gh = 1; gg.x0 = gg.y0 = 0.0; gg.h = gg.inv_h = 1.0; gg.eps = 0.0; gg.clamped = 0; }
+    st->bb = bb;
+    st->g = gg;
+    st->nc = (long long)gg.gw * gg.gh;
 }
 
-__global__ void __launch_bounds__(kT) bin_count_kernel(const double* __restrict__ pts, long long m, int ld, GridGeom g,
-                                                       unsigned* __restrict__ cellid, unsigned* __restrict__ counts) {
+__global__ void __launch_bounds__(kT) bin_kernel(const double* __restrict__ pts, long long m, int ld,
+                                                 const BuildState* __restrict__ st, unsigned* __restrict__ cellid,
+                                                 unsigned* __restrict__ rank, unsigned* __restrict__ counts) {
     const long long i = blockIdx.x * (long long)kT + threadIdx.x;
     if (i >= m) return;
+    const GridGeom g = st->g;
     const double x = pts[i * ld], y = pts[i * ld + 1];
     const int cx = clamp_cell((x - g.x0) * g.inv_h, g.gw);
     const int cy = clamp_cell((y - g.y0) * g.inv_h, g.gh);
     const unsigned c = (unsigned)cy * (unsigned)g.gw + (unsigned)cx;
     cellid[i] = c;
-    atomicAdd(counts + c, 1u);
+    rank[i] = atomicAdd(counts + c, 1u);
 }
 
-// ---- 3-kernel exclusive scan over the histogram ------------------------------------------------
+// ---- single-pass chained scan (decoupled look-back) over the per-cell counts ----------------------------------------
 constexpr int kScanPer = 8;
 constexpr int kScanChunk = kT * kScanPer;  // 2048 cells per block
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
 
-__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* total) {
-    // exclusive scan of one value per thread across a kT-thread block
+__global__ void __launch_bounds__(kT) scan_kernel(const unsigned* __restrict__ counts, BuildState* __restrict__ st,
+                                                  unsigned long long* __restrict__ desc, unsigned* __restrict__ cell_start) {
     __shared__ unsigned wsum[kT / 32];
+    __shared__ unsigned s_block, s_prefix;
+    const long long nc = st->nc;
+    if (threadIdx.x == 0) s_block = atomicAdd(&st->scan_ticket, 1u);   // blocks are numbered in the order they start
+    __syncthreads();
+    const unsigned blk = s_block;
+    const long long base = (long long)blk * kScanChunk + (long long)threadIdx.x * kScanPer;
+    if ((long long)blk * kScanChunk >= nc) return;
+    unsigned v[kScanPer];
+    unsigned s = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) {
+        v[j] = (base + j < nc) ? counts[base + j] : 0u;
+        s += v[j];
+        mx = max(mx, v[j]);
+    }
+    // block-exclusive scan of the per-thread sums
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned inc = v;
+    unsigned inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
         if (l >= o) inc += t;
     }
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
     if (l == 31) wsum[w] = inc;
+    if (l == 0 && mx) atomicMax(&st->max_cell, mx);
     __syncthreads();
     if (w == 0) {
-        unsigned s = (l < kT / 32) ? wsum[l] : 0u;
+        unsigned ws = (l < kT / 32) ? wsum[l] : 0u;
 #pragma unroll
         for (int o = 1; o < kT / 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-            if (l >= o) s += t;
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, ws, o);
+            if (l >= o) ws += t;
         }
-        if (l < kT / 32) wsum[l] = s;  // inclusive over warps
+        if (l < kT / 32) wsum[l] = ws;  // inclusive over warps
     }
     __syncthreads();
-    const unsigned base = (w > 0) ? wsum[w - 1] : 0u;
-    if (total) *total = wsum[kT / 32 - 1];
-    const unsigned r = base + inc - v;
+    const unsigned total = wsum[kT / 32 - 1];
+    const unsigned in_block = ((w > 0) ? wsum[w - 1] : 0u) + inc - s;
+    // publish the aggregate, then warp 0 looks back for the exclusive prefix of this block, 32 predecessors per step:
+    // sum the aggregates down to (and including) the nearest block that already knows its inclusive prefix
+    if (w == 0) {
+        unsigned prefix = 0;
+        if (blk == 0) {
+            if (l == 0) atomicExch(desc + 0, kFlagIncl | (unsigned long long)total);
+        } else {
+            if (l == 0) atomicExch(desc + blk, kFlagAgg | (unsigned long long)total);
+            long long hi = (long long)blk - 1;     // nearest predecessor not yet accounted for
+            for (;;) {
+                const long long p = hi - l;
+                unsigned long long d = kFlagIncl;   // lanes before block 0 read as "inclusive 0"
+                if (p >= 0) {
+                    do { d = *reinterpret_cast<volatile unsigned long long*>(desc + p); } while ((d >> 62) == 0);
+                }
+                const unsigned incl = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+                const int first = incl ? (__ffs(incl) - 1) : 32;      // nearest predecessor with an inclusive prefix
+                unsigned v2 = (l <= first) ? (unsigned)(d & kValMask) : 0u;
+                v2 = __reduce_add_sync(0xFFFFFFFFu, v2);
+                prefix += v2;
+                if (incl) break;
+                hi -= 32;
+            }
+            if (l == 0) atomicExch(desc + blk, kFlagIncl | (unsigned long long)(prefix + total));
+        }
+        if (l == 0) s_prefix = prefix;
+    }
     __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(kT) scan_block_sums_kernel(const unsigned* __restrict__ counts, long long nc,
-                                                             unsigned* __restrict__ block_sums) {
-    const long long base = blockIdx.x * (long long)kScanChunk;
-    unsigned s = 0;
-#pragma unroll
-    for (int j = 0; j < kScanPer; ++j) {
-        const long long i = base + j * kT + threadIdx.x;
-        if (i < nc) s += counts[i];
-    }
-    unsigned tot;
-    block_exclusive_scan(s, &tot);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(kT) scan_partials_kernel(unsigned* __restrict__ block_sums, int nb) {
-    // single block: exclusive scan in place, chunk by chunk with a running carry
-    __shared__ unsigned carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < nb; base += kT) {
-        const int i = base + threadIdx.x;
-        const unsigned v = (i < nb) ? block_sums[i] : 0u;
-        unsigned tot;
-        const unsigned ex = block_exclusive_scan(v, &tot);
-        const unsigned carry = carry_s;
-        if (i < nb) block_sums[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(kT) scan_apply_kernel(const unsigned* __restrict__ counts, long long nc,
-                                                        const unsigned* __restrict__ block_offsets,
-                                                        unsigned* __restrict__ cell_start) {
-    // thread t owns kScanPer CONSECUTIVE cells of the block's chunk
-    const long long base = blockIdx.x * (long long)kScanChunk + (long long)threadIdx.x * kScanPer;
-    unsigned v[kScanPer];
-    unsigned s = 0;
-#pragma unroll
-    for (int j = 0; j < kScanPer; ++j) {
-        v[j] = (base + j < nc) ? counts[base + j] : 0u;
-        s += v[j];
-    }
-    unsigned tot;
-    unsigned run = block_exclusive_scan(s, &tot) + block_offsets[blockIdx.x];
+    unsigned run = s_prefix + in_block;
 #pragma unroll
     for (int j = 0; j < kScanPer; ++j) {
         if (base + j < nc) cell_start[base + j] = run;
@@ -179,14 +300,12 @@ __global__ void __launch_bounds__(kT) scan_apply_kernel(const unsigned* __restri
 }
 
 __global__ void __launch_bounds__(kT) scatter_kernel(const double* __restrict__ pts, long long m, int ld, int use_z,
-                                                     const unsigned* __restrict__ cellid,
-                                                     const unsigned* __restrict__ cell_start,
-                                                     unsigned* __restrict__ fill, double2* __restrict__ xy,
+                                                     const unsigned* __restrict__ cellid, const unsigned* __restrict__ rank,
+                                                     const unsigned* __restrict__ cell_start, double2* __restrict__ xy,
                                                      double4* __restrict__ rec, int* __restrict__ orig) {
     const long long i = blockIdx.x * (long long)kT + threadIdx.x;
     if (i >= m) return;
-    const unsigned c = cellid[i];
-    const unsigned p = cell_start[c] + atomicAdd(fill + c, 1u);
+    const unsigned p = cell_start[cellid[i]] + rank[i];
     if (use_z) {
         rec[p] = make_double4(pts[i * ld], pts[i * ld + 1], pts[i * ld + 2], index_to_bits((int)i));
     } else {
@@ -195,14 +314,22 @@ __global__ void __launch_bounds__(kT) scatter_kernel(const double* __restrict__ 
     }
 }
 
-// Orders every cell by original index (insertion sort; cells hold ~2-3 points).  Makes the
-// cell-sorted layout independent of atomic ordering, i.e. a stable counting sort.
-__global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsigned* __restrict__ cell_start,
-                                                       double2* __restrict__ xy, double4* __restrict__ rec,
-                                                       int* __restrict__ orig, int use_z) {
+// Orders every cell by original index: the arrival ranks of the bin kernel depend on atomic timing, the final layout
+// must not.  One thread per cell for cells of 2..32 points (insertion sort, at most 496 moves); heavier cells are queued.
+__global__ void __launch_bounds__(kT) cell_order_kernel(BuildState* __restrict__ st, const unsigned* __restrict__ cell_start,
+                                                        double2* __restrict__ xy, double4* __restrict__ rec,
+                                                        int* __restrict__ orig, int use_z, unsigned* __restrict__ heavy) {
     const long long c = blockIdx.x * (long long)kT + threadIdx.x;
-    if (c >= nc) return;
+    if (c >= st->nc) return;
     const unsigned s = cell_start[c], e = cell_start[c + 1];
+    if (e - s < 2) return;
+    if (e - s > 32) {
+        if (e - s <= (unsigned)kHeavyMaxPts) {
+            const unsigned k = atomicAdd(&st->n_heavy, 1u);
+            if (k < (unsigned)kHeavyCap) heavy[k] = (unsigned)c;
+        }
+        return;
+    }
     if (use_z) {
         for (unsigned a = s + 1; a < e; ++a) {
             const double4 kr = rec[a];
@@ -227,6 +354,49 @@ __global__ void __launch_bounds__(kT) cell_sort_kernel(long long nc, const unsig
             orig[b] = key;
             xy[b] = kxy;
         }
+    }
+}
+
+// One warp per queued heavy cell (33..4096 points: clustered targets, duplicates): odd-even transposition on the
+// original index, in place.  O(c^2 / 32) warp steps - milliseconds for the largest cell, and only for skewed input.
+__global__ void __launch_bounds__(kT) heavy_cell_kernel(const BuildState* __restrict__ st, const unsigned* __restrict__ cell_start,
+                                                        double2* __restrict__ xy, double4* __restrict__ rec,
+                                                        int* __restrict__ orig, int use_z, const unsigned* __restrict__ heavy) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_heavy = min(st->n_heavy, (unsigned)kHeavyCap);
+    for (unsigned k = blockIdx.x * (kT / 32) + (threadIdx.x >> 5); k < n_heavy; k += gridDim.x * (kT / 32)) {
+        const unsigned c = heavy[k];
+        const unsigned s = cell_start[c], cnt = cell_start[c + 1] - s;
+        for (unsigned round = 0; round < cnt; ++round) {
+            bool sw = false;
+            for (unsigned a = (round & 1u) + 2u * lane; a + 1 < cnt; a += 64u) {
+                if (use_z) {
+                    const double4 p = rec[s + a], q = rec[s + a + 1];
+                    if (bits_to_index(p.w) > bits_to_index(q.w)) { rec[s + a] = q; rec[s + a + 1] = p; sw = true; }
+                } else {
+                    const int p = orig[s + a], q = orig[s + a + 1];
+                    if (p > q) {
+                        orig[s + a] = q; orig[s + a + 1] = p;
+                        const double2 t = xy[s + a]; xy[s + a] = xy[s + a + 1]; xy[s + a + 1] = t;
+                        sw = true;
+                    }
+                }
+            }
+            __syncwarp();
+            // two consecutive rounds without a swap = sorted
+            const bool any = __any_sync(0xFFFFFFFFu, sw);
+            if (!any) {
+                bool sw2 = false;
+                const unsigned r2 = round + 1;
+                for (unsigned a = (r2 & 1u) + 2u * lane; a + 1 < cnt; a += 64u) {
+                    const int p = use_z ? bits_to_index(rec[s + a].w) : orig[s + a];
+                    const int q = use_z ? bits_to_index(rec[s + a + 1].w) : orig[s + a + 1];
+                    sw2 |= (p > q);
+                }
+                if (!__any_sync(0xFFFFFFFFu, sw2)) break;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -261,16 +431,16 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     cudaGetDevice(&t->device);
     struct Guard {
         Target* t; bool armed = true;
-        double* raw = nullptr; unsigned* cellid = nullptr; unsigned* counts = nullptr; unsigned* fill = nullptr;
-        unsigned* bsum = nullptr; BBox* part = nullptr;
+        double* raw = nullptr; unsigned* cellid = nullptr; unsigned* rank = nullptr; unsigned* counts = nullptr;
+        unsigned long long* desc = nullptr; BBox* part = nullptr; BuildState* st = nullptr; unsigned* heavy = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         cudaStream_t s = nullptr;
         ~Guard() {
             if (ev0) cudaEventDestroy(ev0);
             if (ev1) cudaEventDestroy(ev1);
             // scratch is released in stream order: kernels enqueued before an early return may still use it
-            dev_free(cellid, s); dev_free(counts, s); dev_free(fill, s); dev_free(bsum, s); dev_free(part, s);
-            dev_free(raw, s);
+            dev_free(cellid, s); dev_free(rank, s); dev_free(counts, s); dev_free(desc, s); dev_free(part, s);
+            dev_free(st, s); dev_free(heavy, s); dev_free(raw, s);
             if (armed) { t->used.record(s); target_free(t); }
         }
     } g{t};
@@ -291,84 +461,51 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     }
     FICP_CUDA(cudaEventCreate(&g.ev0));
     FICP_CUDA(cudaEventCreate(&g.ev1));
-    cudaEvent_t ev0 = g.ev0, ev1 = g.ev1;
 
-    // ---- bounding box + finiteness
-    const int nb_bbox = (int)std::min<long long>((m + kT - 1) / kT, 148 * 8);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.part), sizeof(BBox) * (nb_bbox + 1), stream));
-    FICP_CUDA(cudaEventRecord(ev0, stream));
-    bbox_kernel<<<nb_bbox, kT, 0, stream>>>(d_pts, m, ld, use_z, g.part);
-    bbox_final_kernel<<<1, 32, 0, stream>>>(g.part, nb_bbox, g.part + nb_bbox);
-    FICP_CUDA(cudaEventRecord(ev1, stream));
-    BBox bb;
-    FICP_CUDA(cudaMemcpyAsync(&bb, g.part + nb_bbox, sizeof(BBox), cudaMemcpyDeviceToHost, stream));
-    FICP_CUDA(cudaStreamSynchronize(stream));
-    float bbox_ms = 0.f;
-    cudaEventElapsedTime(&bbox_ms, ev0, ev1);
-    if (bb.nonfinite) {
-        set_error("target contains non-finite coordinates ('x' must be finite)");
-        return kErrNonFinite;
-    }
-    t->bbox[0] = bb.xmin; t->bbox[1] = bb.xmax; t->bbox[2] = bb.ymin; t->bbox[3] = bb.ymax;
-
-    // ---- grid geometry: ~pts_per_cell points per cell on average
-    GridGeom gg{};
-    const double ex = bb.xmax - bb.xmin, ey = bb.ymax - bb.ymin;
-    const double big = std::max(ex, ey);
-    double h;
-    if (!(big > 0.0)) {
-        h = 1.0;
-    } else {
-        const double exx = std::max(ex, big * 1e-6), eyy = std::max(ey, big * 1e-6);
-        h = std::sqrt(pts_per_cell * exx * eyy / (double)m);
-        if (!(h > 0.0) || !std::isfinite(h)) h = big;
-    }
-    const double max_cells = std::max(4.0 * (double)m, 1024.0);
-    for (;;) {
-        const double gw = std::floor(ex / h) + 1.0, gh = std::floor(ey / h) + 1.0;
-        if (gw * gh <= max_cells && gw < 2.0e9 && gh < 2.0e9) {
-            gg.gw = (int)gw;
-            gg.gh = (int)gh;
-            break;
-        }
-        h *= 1.25;
-    }
-    gg.x0 = bb.xmin; gg.y0 = bb.ymin; gg.h = h; gg.inv_h = 1.0 / h;
-    gg.eps = h * 1e-9 + (std::fabs(bb.xmin) + std::fabs(bb.ymin) + big) * 8e-16;
-    const long long nc = (long long)gg.gw * gg.gh;
-
-    // ---- counting sort
+    // every size that depends on the geometry is bounded up front: at most max(m, 1024) cells
+    const long long nc_max = std::max<long long>(m, 1024);
+    const int nb_geo = (int)std::min<long long>((m + kT - 1) / kT, 148 * 4);
+    const int nb_scan_max = (int)((nc_max + kScanChunk - 1) / kScanChunk);
+    const unsigned nb_pts = (unsigned)((m + kT - 1) / kT);
+    const unsigned nb_cells_max = (unsigned)((nc_max + kT - 1) / kT);
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.part), sizeof(BBox) * nb_geo, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.st), sizeof(BuildState), stream));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.cellid), sizeof(unsigned) * (size_t)m, stream));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc, stream));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.fill), sizeof(unsigned) * (size_t)nc, stream));
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc + 1), stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.rank), sizeof(unsigned) * (size_t)m, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.counts), sizeof(unsigned) * (size_t)nc_max, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.desc), sizeof(unsigned long long) * (size_t)nb_scan_max, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.heavy), sizeof(unsigned) * kHeavyCap, stream));
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_cell_start), sizeof(unsigned) * (size_t)(nc_max + 1), stream));
     if (use_z) {
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_rec), sizeof(double4) * (size_t)m, stream));
     } else {
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_xy), sizeof(double2) * (size_t)m, stream));
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&t->d_orig), sizeof(int) * (size_t)m, stream));
     }
-    const int nb_scan = (int)((nc + kScanChunk - 1) / kScanChunk);
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&g.bsum), sizeof(unsigned) * (size_t)nb_scan, stream));
-    FICP_CUDA(cudaEventRecord(ev0, stream));   // device time of the build = bbox kernels + everything from here
-    FICP_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(unsigned) * (size_t)nc, stream));
-    FICP_CUDA(cudaMemsetAsync(g.fill, 0, sizeof(unsigned) * (size_t)nc, stream));
-    const unsigned nb_pts = (unsigned)((m + kT - 1) / kT);
-    bin_count_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, gg, g.cellid, g.counts);
-    scan_block_sums_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum);
-    scan_partials_kernel<<<1, kT, 0, stream>>>(g.bsum, nb_scan);
-    scan_apply_kernel<<<nb_scan, kT, 0, stream>>>(g.counts, nc, g.bsum, t->d_cell_start);
-    scatter_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, use_z, g.cellid, t->d_cell_start, g.fill, t->d_xy, t->d_rec,
-                                              t->d_orig);
-    const unsigned nb_cells = (unsigned)((nc + kT - 1) / kT);
-    cell_sort_kernel<<<nb_cells, kT, 0, stream>>>(nc, t->d_cell_start, t->d_xy, t->d_rec, t->d_orig, use_z);
+    FICP_CUDA(cudaEventRecord(g.ev0, stream));
+    FICP_CUDA(cudaMemsetAsync(g.st, 0, sizeof(BuildState), stream));
+    FICP_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(unsigned) * (size_t)nc_max, stream));
+    FICP_CUDA(cudaMemsetAsync(g.desc, 0, sizeof(unsigned long long) * (size_t)nb_scan_max, stream));
+    geometry_kernel<<<nb_geo, kT, 0, stream>>>(d_pts, m, ld, use_z, pts_per_cell, g.part, g.st);
+    bin_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, g.st, g.cellid, g.rank, g.counts);
+    scan_kernel<<<nb_scan_max, kT, 0, stream>>>(g.counts, g.st, g.desc, t->d_cell_start);
+    scatter_kernel<<<nb_pts, kT, 0, stream>>>(d_pts, m, ld, use_z, g.cellid, g.rank, t->d_cell_start, t->d_xy, t->d_rec, t->d_orig);
+    cell_order_kernel<<<nb_cells_max, kT, 0, stream>>>(g.st, t->d_cell_start, t->d_xy, t->d_rec, t->d_orig, use_z, g.heavy);
+    heavy_cell_kernel<<<64, kT, 0, stream>>>(g.st, t->d_cell_start, t->d_xy, t->d_rec, t->d_orig, use_z, g.heavy);
     FICP_CUDA(cudaGetLastError());
-    FICP_CUDA(cudaEventRecord(ev1, stream));
+    FICP_CUDA(cudaEventRecord(g.ev1, stream));
+    // ---- the one read-back: geometry, bounding box, finiteness
+    BuildState hs;
+    FICP_CUDA(cudaMemcpyAsync(&hs, g.st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
     FICP_CUDA(cudaStreamSynchronize(stream));
-    cudaEventElapsedTime(&t->build_ms, ev0, ev1);
-    t->build_ms += bbox_ms;
-
-    t->view.g = gg;
+    cudaEventElapsedTime(&t->build_ms, g.ev0, g.ev1);
+    if (hs.bb.nonfinite) {
+        set_error("target contains non-finite coordinates ('x' must be finite)");
+        return kErrNonFinite;
+    }
+    t->bbox[0] = hs.bb.xmin; t->bbox[1] = hs.bb.xmax; t->bbox[2] = hs.bb.ymin; t->bbox[3] = hs.bb.ymax;
+    t->max_cell_pts = (long long)hs.max_cell;
+    t->view.g = hs.g;
     t->view.xy = t->d_xy;
     t->view.rec = t->d_rec;
     t->view.orig = t->d_orig;

@@ -219,17 +219,8 @@ __device__ __forceinline__ int nn_search_group(const WindowAcc& acc, const GridG
             status = 1;
         } else {
             const double seed_d2 = (prev >= 0) ? nn_dist2<Z3>(acc, prev, qx, qy, qz) : kInf;
-            const double h = g.h, eps = g.eps;
-            const double ux = qx - (g.x0 + cx * h), uy = qy - (g.y0 + cy * h);
             double gx[3], gy[3];
-            gx[0] = fmax(ux - eps, 0.0);
-            gx[1] = fmax(fmax(-ux, ux - h) - eps, 0.0);
-            gx[2] = fmax(h - ux - eps, 0.0);
-            gy[0] = fmax(uy - eps, 0.0);
-            gy[1] = fmax(fmax(-uy, uy - h) - eps, 0.0);
-            gy[2] = fmax(h - uy - eps, 0.0);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+            nn_block3_gaps(g, qx, qy, cx, cy, gx, gy);
             const double bound = seed_d2 * FICP_PRUNE_PAD;
             int s[3], n[3];
             bool seed_in = false;

@@ -122,7 +122,7 @@ int launch_radial_crop(const GridView& v, double cx, double cy, double dist, uns
     if (v.m <= 0 || !(dist >= 0.0)) return kOk;
     const GridGeom& g = v.g;
     const double pad = dist + g.eps + g.h * 1e-6;
-    if (cx + pad < g.x0 || cy + pad < g.y0 || cx - pad > g.x0 + g.gw * g.h || cy - pad > g.y0 + g.gh * g.h) return kOk;
+    if (cx + pad < g.tx0 || cy + pad < g.ty0 || cx - pad > g.tx1 || cy - pad > g.ty1) return kOk;   // disc misses the points' bounding box
     const int col0 = clamp_cell((cx - pad - g.x0) * g.inv_h, g.gw), col1 = clamp_cell((cx + pad - g.x0) * g.inv_h, g.gw);
     const int row0 = clamp_cell((cy - pad - g.y0) * g.inv_h, g.gh), row1 = clamp_cell((cy + pad - g.y0) * g.inv_h, g.gh);
     radial_crop_kernel<<<row1 - row0 + 1, 128, 0, stream>>>(v, cx, cy, dist, row0, col0, col1, d_mask);

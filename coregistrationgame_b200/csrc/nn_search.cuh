@@ -297,8 +297,14 @@ FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, in
                             double qz, double& best, int& bestpos) {
     // distance from the query to the (slightly inflated) box of the segment; skip when it cannot
     // hold a point at distance <= best (ties must still be seen for the lowest-index rule)
-    const double bx0 = g.x0 + xa * g.h - g.eps, bx1 = g.x0 + (xb + 1) * g.h + g.eps;
-    const double by0 = g.y0 + y * g.h - g.eps, by1 = g.y0 + (y + 1) * g.h + g.eps;
+    double bx0 = g.x0 + xa * g.h - g.eps, bx1 = g.x0 + (xb + 1) * g.h + g.eps;
+    double by0 = g.y0 + y * g.h - g.eps, by1 = g.y0 + (y + 1) * g.h + g.eps;
+    if (g.clamped) {   // border cells hold the points clamped in from outside the grid: no bound outward
+        if (xa == 0) bx0 = -kInf;
+        if (xb == g.gw - 1) bx1 = kInf;
+        if (y == 0) by0 = -kInf;
+        if (y == g.gh - 1) by1 = kInf;
+    }
     const double dx = fmax(fmax(bx0 - qx, qx - bx1), 0.0);
     const double dy = fmax(fmax(by0 - qy, qy - by1), 0.0);
     if (dx * dx + dy * dy > best) return;
@@ -307,13 +313,13 @@ FICP_HD void nn_try_segment(const Acc& acc, const GridGeom& g, int y, int xa, in
 
 // Squared lower bound on the distance from the query to ANY point outside the block of cells of Chebyshev
 // radius `rad` around (cx, cy); +inf when the block already spans the whole grid.  A point beyond the block's
-// left/right side is at least that side's distance away in x AND at least the query's gap to the grid's
-// y-extent away in y (every point lies inside the grid), and vice versa - this keeps searches of queries far
+// left/right side is at least that side's distance away in x AND at least the query's gap to the points'
+// y-extent away in y (every point lies inside the true bounding box), and vice versa - this keeps searches of queries far
 // off the map (a start pose thrown off the stand) from walking the whole grid.
 FICP_HD double nn_block_bound2(const GridGeom& g, double qx, double qy, int cx, int cy, int rad) {
     const int xl = cx - rad, xh = cx + rad, yl = cy - rad, yh = cy + rad;
-    const double ox = fmax(fmax(g.x0 - qx, qx - (g.x0 + g.gw * g.h)) - g.eps, 0.0);  // gap to the grid's x-extent
-    const double oy = fmax(fmax(g.y0 - qy, qy - (g.y0 + g.gh * g.h)) - g.eps, 0.0);
+    const double ox = fmax(fmax(g.tx0 - qx, qx - g.tx1) - g.eps, 0.0);  // gap to the x-extent of the points (true bbox)
+    const double oy = fmax(fmax(g.ty0 - qy, qy - g.ty1) - g.eps, 0.0);
     double b2 = kInf;
     if (xl > 0) { const double b = fmax(qx - (g.x0 + xl * g.h) - g.eps, 0.0); b2 = fmin(b2, b * b + oy * oy); }
     if (xh < g.gw - 1) { const double b = fmax((g.x0 + (xh + 1) * g.h) - qx - g.eps, 0.0); b2 = fmin(b2, b * b + oy * oy); }
@@ -416,6 +422,26 @@ FICP_HD bool nn_search(const Acc& acc, const GridGeom& g, double qx, double qy, 
 // pruned.  Together with the distance to the block's border (see nn_block_border2) it bounds every other point of the
 // target - what the ICP kernel needs to prove, on later passes, that a query that moved by less than the slack still
 // has one of these two as its nearest neighbour.
+// Squared gaps between the query and the three cell columns / rows of the 3x3 block around its (clamped) cell, boxes
+// inflated by eps.  u = offset of the query from the lower-left corner of its cell; it lies in [0, h] unless the query is
+// off the grid.  With clamped targets a border cell has no outer side: a query beyond it has no gap to it.
+FICP_HD void nn_block3_gaps(const GridGeom& g, double qx, double qy, int cx, int cy, double (&gx)[3], double (&gy)[3]) {
+    const double h = g.h, eps = g.eps;
+    const double ux = qx - (g.x0 + cx * h), uy = qy - (g.y0 + cy * h);
+    gx[0] = fmax(ux - eps, 0.0);
+    gx[1] = fmax(fmax(-ux, ux - h) - eps, 0.0);
+    gx[2] = fmax(h - ux - eps, 0.0);
+    gy[0] = fmax(uy - eps, 0.0);
+    gy[1] = fmax(fmax(-uy, uy - h) - eps, 0.0);
+    gy[2] = fmax(h - uy - eps, 0.0);
+    if (g.clamped) {
+        if ((cx == 0 && ux < 0.0) || (cx == g.gw - 1 && ux > h)) gx[1] = 0.0;
+        if ((cy == 0 && uy < 0.0) || (cy == g.gh - 1 && uy > h)) gy[1] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+}
+
 template <bool Z3, bool TRACK, class Acc>
 FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int prev,
                                    double& best, int& bestpos, int& cx, int& cy, int& lb_hi, int& pos2) {
@@ -436,19 +462,8 @@ FICP_HD bool nn_search_block3_impl(const Acc& acc, const GridGeom& g, double qx,
     // of streaming all nine cells; the own cell is streamed again with the others (same candidates, same result).
     else if (TRACK) nn_scan_segment<Z3>(acc, cy, cx, cx, qx, qy, qz, best, bestpos);
 #endif
-    // squared gaps between the query and the three cell columns / rows (boxes inflated by eps).  u = offset of the
-    // query from the lower-left corner of its (clamped) cell; it lies in [0, h] unless the query is off the grid.
-    const double h = g.h, eps = g.eps;
-    const double ux = qx - (g.x0 + cx * h), uy = qy - (g.y0 + cy * h);
     double gx[3], gy[3];
-    gx[0] = fmax(ux - eps, 0.0);
-    gx[1] = fmax(fmax(-ux, ux - h) - eps, 0.0);
-    gx[2] = fmax(h - ux - eps, 0.0);
-    gy[0] = fmax(uy - eps, 0.0);
-    gy[1] = fmax(fmax(-uy, uy - h) - eps, 0.0);
-    gy[2] = fmax(h - uy - eps, 0.0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { gx[i] *= gx[i]; gy[i] *= gy[i]; }
+    nn_block3_gaps(g, qx, qy, cx, cy, gx, gy);
     // TRACK: cells a little beyond the seed's distance are streamed as well - every cell pruned caps the lower bound
     // (and with it how long the query can skip its searches) at the cell's gap, which would be barely above `best`
 #ifndef FICP_PRUNE_PAD

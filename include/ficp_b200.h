@@ -44,6 +44,8 @@ typedef struct {
     double x0, y0;        /* grid origin */
     double bbox[4];       /* xmin xmax ymin ymax */
     double build_ms;      /* device time of the build kernels */
+    int32_t clamped;      /* 1: skewed target - the grid spans a robust core extent, points outside sit in the border cells */
+    int32_t max_cell_pts; /* points in the heaviest cell */
 } ficp_target_info;
 
 typedef struct {

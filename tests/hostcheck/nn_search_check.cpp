@@ -20,14 +20,23 @@ struct HostGrid {
     std::vector<unsigned> cs;
 };
 
+// `shrink` > 0: the grid spans only the central part of the bounding box (robust extent of grid_build.cu for skewed
+// targets); the points outside are clamped into the border cells.  `shuffle`: arbitrary order inside every cell (what the
+// atomics of the scatter kernel may leave in cells too heavy to re-order) - results must not depend on it.
 static HostGrid build(const std::vector<double>& px, const std::vector<double>& py, const std::vector<double>& pz,
-                      double ppc) {
+                      double ppc, double shrink = 0.0, bool shuffle = false) {
     HostGrid G;
     const size_t m = px.size();
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
     for (size_t i = 0; i < m; ++i) {
         x0 = std::min(x0, px[i]); x1 = std::max(x1, px[i]);
         y0 = std::min(y0, py[i]); y1 = std::max(y1, py[i]);
+    }
+    G.g.tx0 = x0; G.g.tx1 = x1; G.g.ty0 = y0; G.g.ty1 = y1; G.g.clamped = 0; G.g.pad = 0;
+    if (shrink > 0.0) {
+        const double wx = x1 - x0, wy = y1 - y0;
+        x0 += shrink * wx; x1 -= shrink * wx; y0 += 0.5 * shrink * wy; y1 -= 1.5 * shrink * wy;
+        G.g.clamped = 1;
     }
     double ex = x1 - x0, ey = y1 - y0;
     double big = std::max(ex, ey);
@@ -54,6 +63,14 @@ static HostGrid build(const std::vector<double>& px, const std::vector<double>& 
     for (size_t i = 0; i < m; ++i) {  // stable: ascending original index within a cell
         unsigned p = fill[cell[i]]++;
         G.xy[p] = make_double2(px[i], py[i]); G.z[p] = pz[i]; G.org[p] = (int)i;
+    }
+    if (shuffle) {
+        std::mt19937 r2(777);
+        for (int c = 0; c < nc; ++c)
+            for (unsigned a = G.cs[c]; a + 1 < G.cs[c + 1]; ++a) {
+                const unsigned b = a + r2() % (G.cs[c + 1] - a);
+                std::swap(G.xy[a], G.xy[b]); std::swap(G.z[a], G.z[b]); std::swap(G.org[a], G.org[b]);
+            }
     }
     return G;
 }
@@ -228,14 +245,19 @@ int main() {
         }
         if (trial == 7) for (size_t i = 0; i < m; ++i) py[i] = offy;           // collinear
         if (trial == 11) for (size_t i = 0; i < m; ++i) { px[i] = offx; py[i] = offy; }  // all identical
-        HostGrid G = build(px, py, pz, trial % 2 ? 2.0 : 1.0);
+        // every third trial: far outliers in the target (placeholder rows at the origin, a stray point)
+        if (trial % 3 == 2 && m > 100) { px[1] = 0.0; py[1] = 0.0; px[2] = offx - 40 * side; py[2] = offy + 3 * side; px[3] = offx + 9 * side; py[3] = offy - 7 * side; }
+        // grids: spanning the bounding box (even trials) / robust core extent with clamped border cells (odd trials >= 5);
+        // arbitrary in-cell order on trials 2 mod 4
+        HostGrid G = build(px, py, pz, trial % 2 ? 2.0 : 1.0, (trial >= 5 && trial % 2 == 1) ? 0.07 + 0.01 * (trial % 5) : (trial % 3 == 2 && m > 100 ? 0.02 : 0.0), trial % 4 == 2);
         const size_t nq = 400;
         std::vector<double> qx(nq), qy(nq), qz(nq);
         for (size_t i = 0; i < nq; ++i) {
             double r = U(rng);
             if (r < 0.6) { qx[i] = offx + side * U(rng); qy[i] = offy + side * U(rng); }
             else if (r < 0.8) { size_t j = rng() % m; qx[i] = px[j] + 0.3 * (U(rng) - 0.5); qy[i] = py[j] + 0.3 * (U(rng) - 0.5); }
-            else if (r < 0.88) { qx[i] = offx + side * (3 * U(rng) - 1); qy[i] = offy + side * (3 * U(rng) - 1); }  // outside the grid
+            else if (r < 0.86) { qx[i] = offx + side * (3 * U(rng) - 1); qy[i] = offy + side * (3 * U(rng) - 1); }  // outside the grid
+            else if (r < 0.88) { size_t j = 1 + rng() % 3; qx[i] = px[j] + 5 * (U(rng) - 0.5); qy[i] = py[j] + 5 * (U(rng) - 0.5); }  // next to a (possibly far-off) target point
             else if (r < 0.9) { qx[i] = offx + side * (40 * U(rng) - 20); qy[i] = offy + side * (40 * U(rng) - 20); }  // far off the map
             else { qx[i] = offx + side / 2 + (rng() % 8) + 0.5; qy[i] = offy + side * 0.5 + (rng() % 8) * 0.25 + 0.125; }  // lattice centres
             qz[i] = 5 + 30 * U(rng);

@@ -67,6 +67,86 @@ def test_nn_query_degenerate_targets(gpu):
         ti.close()
 
 
+def _skewed_targets(dims):
+    """Targets the mean-density grid of round 1 could not take: one stray coordinate, long tails, clusters
+    far apart, heavy duplicates."""
+    rng = np.random.default_rng(77)
+    utm = np.array([420000.0, 6483000.0])
+    core = np.column_stack([rng.uniform(0, 700, 30000), rng.uniform(0, 500, 30000)]) + utm
+    z = lambda n: rng.uniform(5, 35, (n, 1))
+    out = {}
+    t = core.copy()
+    t[17] = [0.0, 0.0]                                        # the (0, 0) placeholder row of a UTM export
+    t[4242] = utm + [9.0e4, -3.0e4]                           # and a stray point 90 km away
+    out["placeholder_row"] = t
+    out["gaussian_tails"] = rng.normal(0.0, 60.0, (40000, 2)) * [1.0, 0.2] + utm
+    two = np.vstack([core[:15000], core[15000:] + [250000.0, 40000.0]])
+    out["two_stands_250km_apart"] = two
+    dup = np.vstack([core[:20000], np.repeat(core[:1], 2500, axis=0), np.repeat(core[5:6] + 0.25, 40, axis=0)])
+    out["heavy_duplicates"] = dup                              # one cell of > 2500 points, one of ~40
+    out["all_identical_above_heavy_cap"] = np.repeat(core[:1], 6000, axis=0)
+    if dims == 3:
+        out = {k: np.hstack([v, z(len(v))]) for k, v in out.items()}
+    return out
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_nn_query_skewed_targets_are_exact_and_fast_to_build(gpu, dims):
+    """Robust grid extent + clamped border cells: exact neighbours (bit-exact indices and distances) for queries inside
+    the core, next to the far-off points, off the map; the heaviest cell stays small where the skew is an outlier."""
+    from coregistrationgame_b200 import TargetIndex
+    rng = np.random.default_rng(3)
+    for name, tgt in _skewed_targets(dims).items():
+        ti = TargetIndex(tgt)
+        info = ti.info()
+        lo, hi = np.percentile(tgt[:, :2], 1, axis=0), np.percentile(tgt[:, :2], 99, axis=0)
+        q = np.empty((1500, dims))
+        q[:, :2] = rng.uniform(lo - 0.2 * (hi - lo + 1), hi + 0.2 * (hi - lo + 1), (1500, 2))
+        far = tgt[np.argsort(np.abs(tgt[:, :2] - np.median(tgt[:, :2], axis=0)).sum(1))[-200:], :2]
+        q[:200, :2] = far + rng.normal(0, 3.0, (200, 2))                      # next to the most remote target points
+        q[200:260, :2] = rng.uniform(-1e6, 1e7, (60, 2))                      # anywhere
+        if dims == 3:
+            q[:, 2] = rng.uniform(0, 40, 1500)
+        idx, dist = ti.query(q)
+        ref_idx, ref_d2 = orc.nn_assign_bruteforce(q, tgt, dims)
+        np.testing.assert_array_equal(idx, ref_idx, err_msg=name)
+        np.testing.assert_array_equal(dist, np.sqrt(ref_d2), err_msg=name)
+        if name in ("placeholder_row", "two_stands_250km_apart"):
+            assert info["clamped"] if name == "placeholder_row" else True
+        if name == "placeholder_row":
+            assert info["max_cell_pts"] <= 64, info                         # round 1: ~all 30 000 points in one cell
+        assert info["build_ms"] < 50.0, (name, info)                          # round 1: O(c^2) insertion sort per heavy cell
+        ti.close()
+
+
+def test_icp_on_a_skewed_target_matches_oracle(gpu):
+    """The whole ICP against a target with a placeholder row and a stray point: pass counts, k and poses as the oracle."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    from coregistrationgame_b200.batch import compose_world_transform
+    tgt, plots, _ = orc.synthetic_scene(30000, 150, seed=41, dims=3, hidden_pose=True, out_frac=0.1)
+    tgt = tgt.copy()
+    tgt[:, :2] += [420000.0, 6483000.0]
+    src = plots[0].copy()
+    src[:, :2] += [420000.0, 6483000.0]
+    tgt[11] = [0.0, 0.0, 10.0]
+    tgt[12] = [420000.0 + 5.0e4, 6483000.0, 12.0]
+    hyp = orc.hypothesis_table(6, flips=(0, 1))
+    ti = TargetIndex(tgt)
+    assert ti.info()["clamped"]
+    for cta in (False, True):
+        b = IcpBatch(ti, [src], hyp, cta_per_icp=cta)
+        out = b.run().results()
+        ref = orc.run_hypotheses(src, tgt, hyp, centre=b.centres[0], min_k=3, closed_form=True)
+        np.testing.assert_array_equal(out["hyp"]["passes"][0], ref["passes"])
+        np.testing.assert_array_equal(out["hyp"]["k"][0], ref["k"])
+        for h in range(hyp.shape[0]):
+            A = compose_world_transform(out["hyp"][0, h], b.centres[0])
+            np.testing.assert_allclose(src[:, :2] @ A[:, :2].T + A[:, 2], ref["aligned"][h][:, :2], rtol=0, atol=1e-6)
+        assert int(out["best_hyp"][0]) == ref["best_hyp"]
+        b.close()
+    ti.close()
+
+
 def test_nonfinite_inputs_raise_value_error(gpu):
     from coregistrationgame_b200 import TargetIndex
     from ficp import FractionalICP

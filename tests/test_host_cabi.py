@@ -37,7 +37,7 @@ def test_abi_struct_sizes():
     assert _lib.HYP_RESULT_DTYPE.itemsize == 80
     assert C.sizeof(_lib.BatchParams) == 64
     assert C.sizeof(_lib.BatchInfo) == 80
-    assert C.sizeof(_lib.TargetInfo) == 88
+    assert C.sizeof(_lib.TargetInfo) == 96
 
 
 def test_no_device_fails_loudly():
