@@ -120,3 +120,43 @@ def gui_hypothesis_table(rot_steps=range(-36, 36), trans_steps=(0,), flips=(0,),
                     m = hypothesis_matrix(rot_step_deg * r, f)
                     rows.append([m[0, 0], m[0, 1], m[1, 0], m[1, 1], translate_step * tx, translate_step * ty])
     return np.array(rows, dtype=np.float64).reshape(-1, 6)
+
+
+def key_hypothesis(rot_steps=0, flip=0, tx_steps=0, ty_steps=0, rot_step_deg=5.0, translate_step=0.5):
+    """The start pose a user reaches with the reference's keys, as ONE hypothesis row ``[m00 m01 m10 m11 dx dy]``:
+    `rot_steps` presses of rotate-left (+5 degrees each, negative = rotate-right; ``App.rotate_plot``, app.py:618-624),
+    `flip` presses of flip modulo 2 (``Plot.coordinate_flip``, trees.py:213-222), `tx_steps` / `ty_steps` presses of
+    right / down (+0.5 m each; ``App.shift_plot``, app.py:604-616).  Rotations and flips act about the plot centroid
+    (``Plot.current_center``), which only the shifts move, so any interleaving of the keys gives
+    ``x' = R(5 rot_steps) F^flip (x - c) + c + 0.5 (tx_steps, ty_steps)`` - checked against the unmodified ``Plot`` class in
+    tests/test_plot_keys.py (goldens: tests/golden/make_golden_keys.py)."""
+    from .batch import hypothesis_matrix
+    m = hypothesis_matrix(rot_step_deg * rot_steps, int(flip) % 2)
+    return np.array([m[0, 0], m[0, 1], m[1, 0], m[1, 1], translate_step * tx_steps, translate_step * ty_steps], dtype=np.float64)
+
+
+def write_back(plot, new_xy):
+    """``Plot.update_tree_positions`` (trees.py:296-314) for any plot-like object: sets ``currentx`` / ``currenty`` of every
+    tree from the (n, 2) array the registration returned (``icp.source[:, :2]`` in app.py:658-661), then recomputes the
+    centroid exactly like ``Plot._update_centroid`` (trees.py:149-153).  Same error for a length mismatch."""
+    new_xy = np.asarray(new_xy)
+    if len(plot.trees) != new_xy.shape[0]:
+        raise ValueError('Update array length does not match number of trees in the plot')
+    for tree, (x, y) in zip(plot.trees, new_xy):
+        tree.currentx = x
+        tree.currenty = y
+    if plot.trees:
+        plot.current_center = np.mean(np.array([(tree.currentx, tree.currenty) for tree in plot.trees]), axis=0)
+    else:
+        plot.current_center = plot.center
+    return plot
+
+
+def apply_registration(plot, transform):
+    """Moves a plot by a registration result: `transform` is the 2x3 world transform ``[A | b]`` of
+    ``register_batch(...)["best_transform"][p]`` (final = A p + b for the coordinates the batch was given, i.e. the
+    plot's current coordinates) - the batched counterpart of app.py:658-661."""
+    t = np.asarray(transform, dtype=np.float64).reshape(2, 3)
+    cur = np.array([(tree.currentx, tree.currenty) for tree in plot.trees], dtype=np.float64).reshape(-1, 2)
+    return write_back(plot, cur @ t[:, :2].T + t[:, 2])
+
