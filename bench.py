@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 (default, the metric's config) | c2: 200 trees vs 1e5 points, 1024 hypotheses | "
                          "c4: 1250 plots/GPU x 150 trees vs 1e7 points, one start pose per plot | "
-                         "c5: c3 shape on the adversarial scene (30 % outlier trees, 30 % omissions, duplicated + lattice-tied "
+                         "c5: c3 shape on the adversarial scene (30 %% outlier trees, 30 %% omissions, duplicated + lattice-tied "
                          "CHM points) with the trim-fraction sweep 0.5-0.95 reported beside the FRMSD-optimal mode")
     return ap.parse_args()
 
