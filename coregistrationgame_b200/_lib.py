@@ -57,6 +57,8 @@ SIGNATURES = {
     "ficp_target_destroy": (None, [c_vp]),
     "ficp_nn_query": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ficp_nn_query_device": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "ficp_nn_query_ex": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "ficp_nn_query_device_ex": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "ficp_match_remove": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ficp_radial_crop": (c_i32, [c_vp, c_f64, c_f64, c_f64, c_vp, c_vp]),
     "ficp_select_fraction": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, P(c_i64), P(c_f64), c_vp]),

@@ -103,8 +103,13 @@ class TargetIndex:
                 "x0": ti.x0, "y0": ti.y0, "bbox": tuple(ti.bbox), "build_ms": ti.build_ms, "clamped": bool(ti.clamped),
                 "max_cell_pts": int(ti.max_cell_pts)}
 
-    def query(self, points, use_z=None, stream=None):
-        """Exact NN of every row: (original target index int64, Euclidean distance float64)."""
+    QUERY_KERNELS = {"auto": 0, "thread": 1, "bulk": 2}
+
+    def query(self, points, use_z=None, stream=None, kernel="auto", counters=None):
+        """Exact NN of every row: (original target index int64, Euclidean distance float64).
+        kernel: "auto" (bulk kernel for large, dense batches), "thread" (one thread per query), "bulk" (cell-ordered
+        queries against shared-memory windows); identical bits either way.  counters: optional dict, filled by the bulk
+        kernel with how its queries were resolved."""
         q = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
         if q.ndim != 2 or q.shape[1] < 2:
             raise ValueError("query points must be a 2D array (N, D>=2)")
@@ -116,8 +121,12 @@ class TargetIndex:
         idx = np.empty(n, dtype=np.int64)
         dist = np.empty(n, dtype=np.float64)
         if n and self.m:
-            _lib.check(_lib.load().ficp_nn_query(self.handle, _lib.ptr(q), n, q.shape[1], int(z), _lib.ptr(idx),
-                                                 _lib.ptr(dist), _stream_ptr(stream)), "ficp_nn_query")
+            cnt = (C.c_uint64 * 3)() if counters is not None else None
+            _lib.check(_lib.load().ficp_nn_query_ex(self.handle, _lib.ptr(q), n, q.shape[1], int(z), _lib.ptr(idx),
+                                                    _lib.ptr(dist), self.QUERY_KERNELS[kernel], cnt, _stream_ptr(stream)),
+                       "ficp_nn_query")
+            if counters is not None:
+                counters.update(window=int(cnt[0]), global_grid=int(cnt[1]), rings=int(cnt[2]))
         return idx, dist
 
     def close(self):

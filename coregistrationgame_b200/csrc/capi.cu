@@ -200,19 +200,44 @@ int ficp_target_get_info(const ficp_target* th, ficp_target_info* info) {
 void ficp_target_destroy(ficp_target* t) { target_free(reinterpret_cast<Target*>(t)); }
 
 // ------------------------------------------------------------------------------------------ NN query
-int ficp_nn_query_device(const ficp_target* th, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
-                         int32_t* idx_dev, double* dist_dev, void* stream) {
+int ficp_nn_query_device_ex(const ficp_target* th, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
+                            int32_t* idx_dev, double* dist_dev, int32_t kernel, uint64_t* counters_out, void* stream) {
     if (!th) { set_error("ficp_nn_query: null target"); return kErrInvalid; }
     const Target* t = reinterpret_cast<const Target*>(th);
+    if (n <= 0) return kOk;
+    if (!q_dev || !idx_dev) { set_error("ficp_nn_query: null pointer"); return kErrInvalid; }
     if (ld < 2 || (use_z && ld < 3)) { set_error("ficp_nn_query: not enough columns"); return kErrInvalid; }
     if (use_z && !t->has_z) { set_error("ficp_nn_query: target was built without Z"); return kErrInvalid; }
-    const int rc = launch_nn_query(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, (cudaStream_t)stream);
-    t->used.record((cudaStream_t)stream);
+    if (kernel < 0 || kernel > 2) { set_error("ficp_nn_query: kernel must be 0 (auto), 1 (thread per query) or 2 (bulk)"); return kErrInvalid; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool bulk = (kernel == 2) || (kernel == 0 && nn_bulk_applies(t->view, n));
+    if (bulk && n > 0x7FFFFFFFLL) { set_error("ficp_nn_query: bulk kernel takes at most 2^31 - 1 queries per call"); return kErrTooLarge; }
+    int rc;
+    if (bulk && counters_out) {
+        DevBuf<unsigned long long> dc(s);
+        if ((rc = dc.alloc(4))) return rc;
+        FICP_CUDA(cudaMemsetAsync(dc.p, 0, sizeof(unsigned long long) * 4, s));
+        rc = launch_nn_query_bulk(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, dc.p, s);
+        t->used.record(s);
+        if (rc) return rc;
+        FICP_CUDA(cudaMemcpyAsync(counters_out, dc.p, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, s));
+        FICP_CUDA(cudaStreamSynchronize(s));
+        return kOk;
+    }
+    if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = 0;
+    rc = bulk ? launch_nn_query_bulk(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, nullptr, s)
+              : launch_nn_query(t->view, use_z != 0, q_dev, n, ld, idx_dev, dist_dev, nullptr, s);
+    t->used.record(s);
     return rc;
 }
 
-int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
-                  int64_t* idx_out, double* dist_out, void* stream) {
+int ficp_nn_query_device(const ficp_target* th, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
+                         int32_t* idx_dev, double* dist_dev, void* stream) {
+    return ficp_nn_query_device_ex(th, q_dev, n, ld, use_z, idx_dev, dist_dev, 0, nullptr, stream);
+}
+
+int ficp_nn_query_ex(const ficp_target* th, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
+                     int64_t* idx_out, double* dist_out, int32_t kernel, uint64_t* counters_out, void* stream) {
     if (n <= 0) return kOk;
     if (!th || !q_host || !idx_out) { set_error("ficp_nn_query: null pointer"); return kErrInvalid; }
     if (ld < 2 || (use_z && ld < 3)) { set_error("ficp_nn_query: not enough columns"); return kErrInvalid; }
@@ -229,13 +254,18 @@ int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_
     int rc;
     if ((rc = dq.alloc((size_t)n * ld)) || (rc = dd.alloc(n)) || (rc = di.alloc(n))) return rc;
     FICP_CUDA(cudaMemcpyAsync(dq.p, q_host, sizeof(double) * (size_t)n * ld, cudaMemcpyHostToDevice, s));
-    if ((rc = ficp_nn_query_device(th, dq.p, n, ld, use_z, di.p, dd.p, stream))) return rc;
+    if ((rc = ficp_nn_query_device_ex(th, dq.p, n, ld, use_z, di.p, dd.p, kernel, counters_out, stream))) return rc;
     std::vector<int> hi((size_t)n);
     FICP_CUDA(cudaMemcpyAsync(hi.data(), di.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
     if (dist_out) FICP_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
     FICP_CUDA(cudaStreamSynchronize(s));
     for (int64_t i = 0; i < n; ++i) idx_out[i] = hi[(size_t)i];
     return kOk;
+}
+
+int ficp_nn_query(const ficp_target* th, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
+                  int64_t* idx_out, double* dist_out, void* stream) {
+    return ficp_nn_query_ex(th, q_host, n, ld, use_z, idx_out, dist_out, 0, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------ match & remove

@@ -76,6 +76,13 @@ void target_free(Target* t);
 // ---- standalone stage kernels (host launchers; all pointers are DEVICE pointers) ----------------
 int launch_nn_query(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
                     double* d_d2, cudaStream_t stream);
+// Bulk form (nn_bulk.cu): queries brought into cell order, windows of target cells staged in shared memory by
+// cp.async.bulk.  Same outputs, same bits.  `d_counters` (optional, 3 x u64, zeroed by the caller): queries resolved
+// from a shared-memory window / on the global grid / that needed rings >= 2.
+constexpr long long kBulkMinQueries = 1 << 16;
+bool nn_bulk_applies(const GridView& v, long long n);
+int launch_nn_query_bulk(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,
+                         double* d_d2, unsigned long long* d_counters, cudaStream_t stream);
 int launch_radial_crop(const GridView& v, double cx, double cy, double dist, unsigned char* d_mask, cudaStream_t stream);
 int launch_match_remove(const GridView& v, bool z3, const double* d_trees, const long long* d_offsets, int n_plots,
                         int ld, const double* d_thr, long long* d_out, int* d_scratch, cudaStream_t stream);

@@ -26,12 +26,13 @@
 #include <cstdio>
 #include <vector>
 #include "ficp_internal.h"
+#include "chained_scan.cuh"
 
 namespace ficp {
 
 namespace {
 
-constexpr int kT = 256;
+constexpr int kT = kScanT;
 constexpr int kSample = 256;           // points sampled for the robust extent (one per thread of the last CTA)
 constexpr int kHeavyCap = 4096;        // heavy-cell queue entries
 constexpr int kHeavyMaxPts = 4096;     // cells above this keep arrival order
@@ -215,88 +216,10 @@ __global__ void __launch_bounds__(kT) bin_kernel(const double* __restrict__ pts,
     rank[i] = atomicAdd(counts + c, 1u);
 }
 
-// ---- single-pass chained scan (decoupled look-back) over the per-cell counts ----------------------------------------
-constexpr int kScanPer = 8;
-constexpr int kScanChunk = kT * kScanPer;  // 2048 cells per block
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
-
+// ---- single-pass chained scan (decoupled look-back) over the per-cell counts: chained_scan.cuh
 __global__ void __launch_bounds__(kT) scan_kernel(const unsigned* __restrict__ counts, BuildState* __restrict__ st,
                                                   unsigned long long* __restrict__ desc, unsigned* __restrict__ cell_start) {
-    __shared__ unsigned wsum[kT / 32];
-    __shared__ unsigned s_block, s_prefix;
-    const long long nc = st->nc;
-    if (threadIdx.x == 0) s_block = atomicAdd(&st->scan_ticket, 1u);   // blocks are numbered in the order they start
-    __syncthreads();
-    const unsigned blk = s_block;
-    const long long base = (long long)blk * kScanChunk + (long long)threadIdx.x * kScanPer;
-    if ((long long)blk * kScanChunk >= nc) return;
-    unsigned v[kScanPer];
-    unsigned s = 0, mx = 0;
-#pragma unroll
-    for (int j = 0; j < kScanPer; ++j) {
-        v[j] = (base + j < nc) ? counts[base + j] : 0u;
-        s += v[j];
-        mx = max(mx, v[j]);
-    }
-    // block-exclusive scan of the per-thread sums
-    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (l >= o) inc += t;
-    }
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if (l == 31) wsum[w] = inc;
-    if (l == 0 && mx) atomicMax(&st->max_cell, mx);
-    __syncthreads();
-    if (w == 0) {
-        unsigned ws = (l < kT / 32) ? wsum[l] : 0u;
-#pragma unroll
-        for (int o = 1; o < kT / 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, ws, o);
-            if (l >= o) ws += t;
-        }
-        if (l < kT / 32) wsum[l] = ws;  // inclusive over warps
-    }
-    __syncthreads();
-    const unsigned total = wsum[kT / 32 - 1];
-    const unsigned in_block = ((w > 0) ? wsum[w - 1] : 0u) + inc - s;
-    // publish the aggregate, then warp 0 looks back for the exclusive prefix of this block, 32 predecessors per step:
-    // sum the aggregates down to (and including) the nearest block that already knows its inclusive prefix
-    if (w == 0) {
-        unsigned prefix = 0;
-        if (blk == 0) {
-            if (l == 0) atomicExch(desc + 0, kFlagIncl | (unsigned long long)total);
-        } else {
-            if (l == 0) atomicExch(desc + blk, kFlagAgg | (unsigned long long)total);
-            long long hi = (long long)blk - 1;     // nearest predecessor not yet accounted for
-            for (;;) {
-                const long long p = hi - l;
-                unsigned long long d = kFlagIncl;   // lanes before block 0 read as "inclusive 0"
-                if (p >= 0) {
-                    do { d = *reinterpret_cast<volatile unsigned long long*>(desc + p); } while ((d >> 62) == 0);
-                }
-                const unsigned incl = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-                const int first = incl ? (__ffs(incl) - 1) : 32;      // nearest predecessor with an inclusive prefix
-                unsigned v2 = (l <= first) ? (unsigned)(d & kValMask) : 0u;
-                v2 = __reduce_add_sync(0xFFFFFFFFu, v2);
-                prefix += v2;
-                if (incl) break;
-                hi -= 32;
-            }
-            if (l == 0) atomicExch(desc + blk, kFlagIncl | (unsigned long long)(prefix + total));
-        }
-        if (l == 0) s_prefix = prefix;
-    }
-    __syncthreads();
-    unsigned run = s_prefix + in_block;
-#pragma unroll
-    for (int j = 0; j < kScanPer; ++j) {
-        if (base + j < nc) cell_start[base + j] = run;
-        run += v[j];
-    }
-    if (base <= nc - 1 && nc - 1 < base + kScanPer) cell_start[nc] = run;  // total, written by the owner of the last cell
+    chained_scan_block(counts, st->nc, &st->scan_ticket, &st->max_cell, desc, cell_start);
 }
 
 __global__ void __launch_bounds__(kT) scatter_kernel(const double* __restrict__ pts, long long m, int ld, int use_z,

@@ -30,6 +30,19 @@ namespace ficp {
 
 namespace {
 
+// Phase clocks (diagnostic build only, -DFICP_PHASE_CLOCKS: make variant NAME=clk FLAGS=-DFICP_PHASE_CLOCKS): thread 0 of
+// every CTA adds up the cycles between phase marks; tools/team_phase_clocks.py prints the shares.
+#if defined(FICP_PHASE_CLOCKS)
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_DECL long long ph_last = clock64(); unsigned long long ph_acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PHASE(n) do { if (tid == 0) { const long long ph_now = clock64(); ph_acc[n] += (unsigned long long)(ph_now - ph_last); ph_last = ph_now; } } while (0)
+#define PHASE_FLUSH do { if (tid == 0) { for (int q = 0; q < 13; ++q) atomicAdd(&g_phase_clk[q], ph_acc[q]); } } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(n)
+#define PHASE_FLUSH
+#endif
+
 struct TeamLayout {
     size_t s_u, s_z, s_g, w_xy, w_z, w_cell, rowoff, rowdelta, rowg, sd2, snn, ssl, list, dlist, slist, sidx, kbuf, sdd, tmp, misc, total;
 };
@@ -175,6 +188,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     int staged_plot = -1;
     unsigned long long acc_passes = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0, acc_deferred = 0;
     unsigned n_global = 0;   // per thread
+    PHASE_DECL;
 
     for (;;) {
         __syncthreads();   // everyone is done with the previous ICP (and with M->icp)
@@ -256,6 +270,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
         PassOut po{0, kInf, 0.0, -1.0, -1};
         // position of this thread in trim order: chunk (= lane of the one-warp kernel) and element inside it
         const int lp = tid / E, r = tid - lp * E;
+        PHASE(0);
 
         for (int st = 0; st < P.n_stages; ++st) {
             const double* sg = s_g + (size_t)st * T;
@@ -279,6 +294,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     list[tid] = (unsigned short)tid;
                 }
                 __syncthreads();
+                PHASE(1);
                 const int n_list = M->nlist;
                 // lanes per query: a pass that searches few queries spreads each candidate stream over G lanes
                 int G = 1;
@@ -342,6 +358,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     }
                 }
                 __syncthreads();
+                PHASE(2);
                 const int n_def = M->ndef;
                 for (int base = warp * 32; base < n_def; base += NW * 32)
                     nn_deferred_chunk<Z3, false>(G_, W, pc, pose, sd2, snn, dlist, base, n_def, lane, n_global);
@@ -349,6 +366,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 n_deferred += (unsigned)n_def;
                 dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
                 __syncthreads();
+                PHASE(3);
 
                 // ================= trimming (ficp.py:62-63,73-86)
                 // Trim order = the exact order of (d2, tree index).  Passes of a converging ICP barely change it, so
@@ -368,6 +386,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     sorted = (ninv == 0);
                     if (!sorted && ninv <= kRepairMaxInversions) sorted = team_repair_order<T, E>(sdd, sidx, tid, kRepairMaxRounds);
                 }
+                PHASE(4);
                 if (!sorted) {
                     // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
                     // order is verified afterwards and repaired where quantised codes collide
@@ -387,6 +406,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                         (void)team_repair_order<T, E>(sdd, sidx, tid, 1 << 30);
                     }
                 }
+                PHASE(5);
                 // inclusive prefix sums S_k of d2 in trim order, in the association of the one-warp kernel: serial
                 // inside the chunk of E consecutive positions (lane l of warp 0 walks chunk l; the padded layout keeps the
                 // 32 lanes on different banks), Kogge-Stone over the 32 chunk totals, prefix + partial
@@ -408,6 +428,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     M->sexcl[lane] = excl;
                 }
                 __syncthreads();
+                PHASE(6);
                 sidx_t = sidx[tid];
                 const double S = __dadd_rn(M->sexcl[lp], spart[PAD(tid)]);
 
@@ -483,6 +504,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     if (tid == 0) { P.tr_k[rec] = po.k; P.tr_f[rec] = po.f; }
                 }
                 ++passes;
+                PHASE(7);
 
                 // ================= stage logic (ficp.py:122-147)
                 if (first) {
@@ -513,6 +535,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     }
                 }
                 __syncthreads();
+                PHASE(8);
                 for (int q = warp; q < 9; q += NW) {
                     double acc = 0.0;
 #pragma unroll 4
@@ -525,6 +548,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     if (lane == 0) M->fsum[q] = acc;
                 }
                 __syncthreads();
+                PHASE(9);
                 if (warp == 0) {
                     const FitSums fs{M->fsum[0], M->fsum[1], M->fsum[2], M->fsum[3], M->fsum[4], M->fsum[5], M->fsum[6], M->fsum[7], M->fsum[8]};
                     Pose np = pose, nd;
@@ -539,8 +563,10 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 __syncthreads();
                 pose = Pose{M->pose[0], M->pose[1], M->pose[2], M->pose[3], M->pose[4], M->pose[5]};
                 dpose = Pose{M->pose[6], M->pose[7], M->pose[8], M->pose[9], M->pose[10], M->pose[11]};
+                PHASE(10);
             }
         }
+        PHASE(11);
 
         // ---- results (same record as icp_persistent.cu)
         if (tid == 0) M->nglob = 0;
@@ -574,6 +600,8 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             P.final_xy[(pm.off + tid) * 2 + 1] = qy;
         }
     }
+    PHASE(12);
+    PHASE_FLUSH;
     if (tid == 0 && acc_passes) {
         atomicAdd(P.stats + 0, acc_passes);
         atomicAdd(P.stats + 3, acc_fix);
@@ -600,6 +628,14 @@ int team_occupancy_one(size_t smem, int* out) {
 }
 
 }  // namespace
+
+#if defined(FICP_PHASE_CLOCKS)
+extern "C" __attribute__((visibility("default"))) int ficp_debug_phase_clocks(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(unsigned long long) * 16) != cudaSuccess) return -3;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_phase_clk, z, sizeof z) != cudaSuccess) return -3; }
+    return 0;
+}
+#endif
 
 size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
     return team_layout(32 * e, z3, wcap_pts, wcap_cells, wcap_rows).total;

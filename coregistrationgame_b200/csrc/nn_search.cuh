@@ -549,6 +549,80 @@ FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, doub
     return nn_search_block3_impl<Z3, false>(acc, g, qx, qy, qz, prev, best, bestpos, cx, cy, lb_hi, pos2);
 }
 
+// Unseeded form for bulk queries (nn_bulk.cu): the query's OWN cell is scored first, so that the pruning of the other
+// eight cells has a bound to work with; then the surviving cells of the 3x3 block are streamed as one flat candidate
+// list (the own cell comes by again - three candidates of ~twenty).  The winner is kept with a plain `<`; an exact tie
+// with a different point raises a flag and only then (rare) the stream is looked at again with the
+// lowest-original-index rule.  Same result as nn_search_block3: exact minimum over the block, ties to the lowest index.
+template <bool Z3, class Acc>
+FICP_HD void nn_search_block3_unseeded(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
+                                       double& best, int& bestpos) {
+    const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
+    const int yl = (cy > 0) ? cy - 1 : 0, yh = (cy < g.gh - 1) ? cy + 1 : g.gh - 1;
+    best = kInf;
+    bestpos = -1;
+    bool tie = false;
+    {
+        int s0, e0;
+        acc.seg(cy, cx, cx, s0, e0);
+        for (int j = s0; j < e0; ++j) {
+            const double d = nn_dist2<Z3>(acc, j, qx, qy, qz);
+            tie = tie || (d == best);
+            const bool lt = d < best;
+            best = lt ? d : best;
+            bestpos = lt ? j : bestpos;
+        }
+    }
+    double gx[3], gy[3];
+    nn_block3_gaps(g, qx, qy, cx, cy, gx, gy);
+    const double bound = best;
+    int s[3], n[3];
+#pragma unroll
+    for (int ry = 0; ry < 3; ++ry) {
+        const int y = cy - 1 + ry;
+        s[ry] = 0;
+        n[ry] = 0;
+        if (y < yl || y > yh) continue;
+        int xa = cx + 2, xb = cx - 2;
+#pragma unroll
+        for (int rx = 0; rx < 3; ++rx) {
+            const int x = cx - 1 + rx;
+            if (x >= xl && x <= xh && gx[rx] + gy[ry] <= bound) {
+                if (x < xa) xa = x;
+                xb = x;
+            }
+        }
+        if (xa <= xb) {
+            int e;
+            acc.seg(y, xa, xb, s[ry], e);
+            n[ry] = e - s[ry];
+        }
+    }
+    const int n01 = n[0] + n[1], total = n01 + n[2];
+    const int o1 = s[1] - n[0], o2 = s[2] - n01;
+    for (int t = 0; t < total; t += 2) {
+        const int t1 = (t + 1 < total) ? t + 1 : t;
+        const int j0 = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+        const int j1 = t1 + ((t1 < n[0]) ? s[0] : (t1 < n01) ? o1 : o2);
+        const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
+        const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
+        tie = tie || (da == best && j0 != bestpos);
+        const bool la = da < best;
+        best = la ? da : best;
+        bestpos = la ? j0 : bestpos;
+        tie = tie || (db == best && j1 != bestpos);
+        const bool lb = db < best;
+        best = lb ? db : best;
+        bestpos = lb ? j1 : bestpos;
+    }
+    if (tie) {
+        for (int t = 0; t < total; ++t) {
+            const int j = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+            nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
+        }
+    }
+}
+
 // True when the visited block of Chebyshev radius `rad` around (cx, cy) provably bounds the search (cheap form of
 // the bound: side distances only; it never exceeds nn_block_bound2, so stopping on it is safe).
 FICP_HD bool nn_block_settles(const GridGeom& g, double qx, double qy, int cx, int cy, int rad, double best) {

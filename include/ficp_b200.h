@@ -121,6 +121,15 @@ FICP_API int ficp_nn_query(const ficp_target* t, const double* q_host, int64_t n
                   int64_t* idx_out, double* dist_out, void* stream);
 FICP_API int ficp_nn_query_device(const ficp_target* t, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
                          int32_t* idx_dev, double* dist_dev, void* stream);
+/* The same with the kernel chosen by the caller (tests, benchmarks): kernel = 0 auto (what the two calls above do: the bulk
+ * kernel for batches of >= 65536 queries that are at least half as many as the grid has cells), 1 = one thread per query
+ * over the L2-resident grid, 2 = bulk (queries brought into cell order, windows of cells staged in shared memory with
+ * cp.async.bulk).  Both return identical bits.  counters_out (optional, 3 x u64, bulk kernel only; makes the call
+ * synchronous): queries resolved from a shared-memory window / on the global grid / that needed rings >= 2. */
+FICP_API int ficp_nn_query_ex(const ficp_target* t, const double* q_host, int64_t n, int32_t ld, int32_t use_z,
+                     int64_t* idx_out, double* dist_out, int32_t kernel, uint64_t* counters_out, void* stream);
+FICP_API int ficp_nn_query_device_ex(const ficp_target* t, const double* q_dev, int64_t n, int32_t ld, int32_t use_z,
+                            int32_t* idx_dev, double* dist_dev, int32_t kernel, uint64_t* counters_out, void* stream);
 
 /* ---- greedy match-and-remove.  Replaces CHMPlot.remove_matches (chm_plot.py:223-285).
  * For every plot (rows [offsets[p], offsets[p+1]) of trees_host) the trees are visited in order; a tree takes its

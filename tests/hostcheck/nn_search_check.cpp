@@ -138,6 +138,17 @@ static int check(const HostGrid& G, const std::vector<double>& px, const std::ve
                 ++bad;
             }
         }
+        // bulk-query form (nn_bulk.cu): own cell first, pruned 3x3 stream with a tie flag, then rings >= 2 if unsettled
+        {
+            const int cxq = clamp_cell((qx[i] - G.g.x0) * G.g.inv_h, G.g.gw), cyq = clamp_cell((qy[i] - G.g.y0) * G.g.inv_h, G.g.gh);
+            double b6; int p6;
+            nn_search_block3_unseeded<Z3>(ga, G.g, qx[i], qy[i], qz[i], cxq, cyq, b6, p6);
+            if (!nn_block_settles(G.g, qx[i], qy[i], cxq, cyq, 1, b6)) nn_ring_loop_impl<Z3>(ga, G.g, qx[i], qy[i], qz[i], cxq, cyq, 2, b6, p6);
+            if (p6 < 0 || G.org[p6] != bi || b6 != bb) {
+                if (bad < 5) printf("BULK(unseeded) mismatch q%zu: got %d (%.17g) want %d (%.17g)\n", i, p6 < 0 ? -1 : G.org[p6], b6, bi, bb);
+                ++bad;
+            }
+        }
         // lower bound on every OTHER point from the tracked 3x3 search (what the ICP kernel's skip test relies on)
         for (int variant = 0; variant < 4; ++variant) {
             int prev = -1;

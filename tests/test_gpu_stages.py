@@ -51,6 +51,90 @@ def test_nn_query_bit_exact(gpu, dims, offset):
     ti.close()
 
 
+@pytest.mark.parametrize("dims", [2, 3])
+def test_nn_query_bulk_kernel_bit_exact(gpu, dims):
+    """The bulk kernel (cell-ordered queries, windows of cells staged in shared memory by cp.async.bulk) returns the bits
+    of the thread-per-query kernel and of brute force: lattice ties, exact duplicates, off-grid queries, UTM offsets."""
+    from coregistrationgame_b200 import TargetIndex
+    tgt, src = _scene(20000, 400, seed=21, dims=dims, dup_every=9, lattice_patch=7)
+    rng = np.random.default_rng(6)
+    lo, hi = tgt[:, :2].min(0), tgt[:, :2].max(0)
+    nq = 70000
+    q = np.empty((nq, dims))
+    q[:, :2] = rng.uniform(lo - 0.05 * (hi - lo), hi + 0.05 * (hi - lo), (nq, 2))
+    q[:2000, :2] = rng.uniform(lo - 0.6 * (hi - lo), hi + 0.6 * (hi - lo), (2000, 2))   # far outside the grid
+    if dims == 3:
+        q[:, 2] = rng.uniform(0, 40, nq)
+        q[5000:9000, 2] = rng.uniform(-80, 150, 4000)          # wide searches: rings >= 2 on the global grid
+    q[2000:2400] = src
+    q[2400:2436, 0] = tgt[:36, 0] + 0.5                        # centres of lattice cells: 4 equidistant targets
+    q[2400:2436, 1] = tgt[:36, 1] + 0.5
+    q[2436:2500] = tgt[-64:]                                   # exact duplicates of targets
+    q[2500:3000, :2] = tgt[rng.integers(0, 49, 500), :2] + rng.integers(-2, 3, (500, 2)) * 0.5   # lattice edge / corner ties
+    off = np.zeros(dims)
+    off[:2] = (420000.0, 6483000.0)
+    tgt, q = tgt + off, q + off
+    for purpose in ("query", "icp"):
+        ti = TargetIndex(tgt, purpose=purpose)
+        cnt = {}
+        idx_b, dist_b = ti.query(q, kernel="bulk", counters=cnt)
+        idx_t, dist_t = ti.query(q, kernel="thread")
+        np.testing.assert_array_equal(idx_b, idx_t)
+        np.testing.assert_array_equal(dist_b, dist_t)
+        assert cnt["window"] + cnt["global_grid"] == nq, cnt
+        assert cnt["window"] > 0.9 * nq, cnt                    # dense batch: resolved from shared-memory windows
+        sel = np.r_[0:6000, rng.integers(0, nq, 4000)]
+        ref_idx, ref_d2 = orc.nn_assign_bruteforce(q[sel], tgt, dims)
+        np.testing.assert_array_equal(idx_b[sel], ref_idx)
+        np.testing.assert_array_equal(dist_b[sel], np.sqrt(ref_d2))
+        idx_a, dist_a = ti.query(q)                             # auto picks the bulk kernel here
+        np.testing.assert_array_equal(idx_a, idx_b)
+        ti.close()
+
+
+def test_nn_query_bulk_kernel_sparse_clustered_and_degenerate(gpu):
+    """Query batches the windows do not fit: sparse (chunks spanning many rows -> global grid, still exact), clustered
+    (thousands of queries in a handful of cells), one-row / one-cell grids, and a batch that is not a multiple of 256."""
+    from coregistrationgame_b200 import TargetIndex
+    rng = np.random.default_rng(8)
+    tgt, _ = _scene(60000, 50, seed=5, dims=3)
+    ti = TargetIndex(tgt, purpose="query")
+    lo, hi = tgt[:, :2].min(0), tgt[:, :2].max(0)
+    # sparse: far fewer queries than cells
+    q = np.column_stack([rng.uniform(lo[0], hi[0], 3001), rng.uniform(lo[1], hi[1], 3001), rng.uniform(5, 35, 3001)])
+    cnt = {}
+    ib, db = ti.query(q, kernel="bulk", counters=cnt)
+    it, dt = ti.query(q, kernel="thread")
+    np.testing.assert_array_equal(ib, it)
+    np.testing.assert_array_equal(db, dt)
+    assert cnt["global_grid"] > 0
+    # clustered: 66 000 queries inside a 30 m square
+    c = 0.5 * (lo + hi)
+    q = np.column_stack([rng.uniform(c[0] - 15, c[0] + 15, 66000), rng.uniform(c[1] - 15, c[1] + 15, 66000), rng.uniform(5, 35, 66000)])
+    q[::7] = q[3]                                               # thousands of identical queries
+    cnt = {}
+    ib, db = ti.query(q, kernel="bulk", counters=cnt)
+    it, dt = ti.query(q, kernel="thread")
+    np.testing.assert_array_equal(ib, it)
+    np.testing.assert_array_equal(db, dt)
+    assert cnt["window"] == 66000, cnt
+    ti.close()
+    # degenerate grids: a single point, all-identical points, collinear points (one row / one column of cells)
+    q2 = rng.normal(size=(70001, 2)) * 30
+    for t2 in (np.array([[1.0, 2.0]]), np.repeat(np.array([[3.0, -1.0]]), 50, axis=0),
+               np.stack([np.linspace(-100, 100, 3000), np.zeros(3000)], 1),
+               np.stack([np.zeros(3000), np.linspace(-100, 100, 3000)], 1)):
+        ti = TargetIndex(t2, purpose="query")
+        ib, db = ti.query(q2, kernel="bulk")
+        ref_idx, ref_d2 = orc.nn_assign_bruteforce(q2[:4000], t2, 2)
+        np.testing.assert_array_equal(ib[:4000], ref_idx)
+        np.testing.assert_array_equal(db[:4000], np.sqrt(ref_d2))
+        it, dt = ti.query(q2, kernel="thread")
+        np.testing.assert_array_equal(ib, it)
+        np.testing.assert_array_equal(db, dt)
+        ti.close()
+
+
 def test_nn_query_degenerate_targets(gpu):
     from coregistrationgame_b200 import TargetIndex
     rng = np.random.default_rng(0)
