@@ -231,7 +231,8 @@ class IcpBatch:
                "hyp": None, "final_xy": None,
                "stats": {"passes": int(stats[0]), "global_path_queries": int(stats[1]),
                          "windows_disabled": int(stats[2]), "fixup_rounds": int(stats[3]), "queries": int(stats[4]),
-                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6])}}
+                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6]),
+                         "order_rebuilds": int(stats[7])}}
         out.update(decode_best_keys(keys))
         self.d2h_bytes = int(packed.nbytes + stats.nbytes)
         return out
@@ -252,7 +253,8 @@ class IcpBatch:
                "hyp_ids": self.hyp_begin + self.hyp_stride * np.arange(self.n_hyp_local),
                "stats": {"passes": int(stats[0]), "global_path_queries": int(stats[1]),
                          "windows_disabled": int(stats[2]), "fixup_rounds": int(stats[3]), "queries": int(stats[4]),
-                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6])}}
+                         "searched_queries": int(stats[5]), "deferred_queries": int(stats[6]),
+                         "order_rebuilds": int(stats[7])}}
         out.update(decode_best_keys(keys))
         self.d2h_bytes = int(keys.nbytes + stats.nbytes + (res.nbytes if res is not None else 0)
                              + (final.nbytes if final is not None else 0))

@@ -560,7 +560,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     while (team > 1 && (team > e || team > warps)) team >>= 1;  // at least one round per warp of the team
     int slots_per_cta = std::max(1, std::min(warps / team, n_hyp_local));
     const size_t sm_total = 228 * 1024;  // per-SM shared memory; each resident CTA also reserves 1 KB
-    const int wcap_rows = 256;
+    const int wcap_rows = kWindowRowsCap;
     // per-ICP state (distances, neighbours, search list, trim order, slack: 18 B per tree) must leave room for a window
     while (!cta_mode && slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
     warps = slots_per_cta * team;

@@ -100,6 +100,7 @@ int launch_sumsq(const double* d_a, int ld_a, const double* d_b, int ld_b, const
 
 // ---- persistent batched ICP ---------------------------------------------------------------------
 constexpr int kMaxStages = 2;
+constexpr int kWindowRowsCap = 256;   // grid rows a shared-memory window may span (both persistent kernels)
 
 struct PlotMeta {
     long long off;       // first row of this plot in the concatenated source arrays
@@ -144,7 +145,8 @@ struct IcpParams {
     int slots;                      // elastic kernel: lead warps (ICPs in flight) per CTA; the rest help
     int dyn_leads;                  // rounds are handed out to helpers while at most this many leads are active
     unsigned long long* stats;      // [0] passes [1] queries resolved on the global path [2] window disabled
-                                    // [3] trim-order fix-up rounds [4] queries
+                                    // [3] trim-order fix-up rounds [4] queries [5] searched [6] deferred
+                                    // [7] CTA-per-ICP kernel: passes whose trim order was rebuilt by the block sort
     // optional per-pass trace (tests: direct parity of NN indices / inlier sets, ficp.py:69-71,62-63,133); off: cap 0
     int trace_cap;                  // passes recorded per ICP
     int trace_stride;               // entries per pass record (= NPAD of the launch)

@@ -351,29 +351,18 @@ __device__ __forceinline__ void fit_uv(double qx, double qy, double tx, double t
                                        double& vx, double& vy) {
     ux = __dsub_rn(qx, ax); uy = __dsub_rn(qy, ay); vx = __dsub_rn(tx, ax); vy = __dsub_rn(ty, ay);
 }
-// the nine running sums, individually (CTA-per-ICP kernel: one (sum, lane) pair per thread) ...
-__device__ __forceinline__ double fit_acc_one(int q, double acc, double ux, double uy, double vx, double vy) {
-    switch (q) {
-        case 0: return __dadd_rn(acc, ux);
-        case 1: return __dadd_rn(acc, uy);
-        case 2: return __dadd_rn(acc, vx);
-        case 3: return __dadd_rn(acc, vy);
-        case 4: return __fma_rn(ux, vx, acc);
-        case 5: return __fma_rn(ux, vy, acc);
-        case 6: return __fma_rn(uy, vx, acc);
-        case 7: return __fma_rn(uy, vy, acc);
-        default: return __fma_rn(__dadd_rn(fabs(ux), fabs(uy)), __dadd_rn(fabs(vx), fabs(vy)), acc);  // noise scale of the terms
-    }
-}
-// ... and all at once (one-warp kernel): the same operations, the same order per sum
-__device__ __forceinline__ void fit_term(FitSums& s, double qx, double qy, double tx, double ty, double ax, double ay) {
-    double ux, uy, vx, vy;
-    fit_uv(qx, qy, tx, ty, ax, ay, ux, uy, vx, vy);
+// the nine running sums of one inlier: the same operations, in the same order per sum, in both kernels
+__device__ __forceinline__ void fit_acc(FitSums& s, double ux, double uy, double vx, double vy) {
     s.su0 = __dadd_rn(s.su0, ux); s.su1 = __dadd_rn(s.su1, uy);
     s.sv0 = __dadd_rn(s.sv0, vx); s.sv1 = __dadd_rn(s.sv1, vy);
     s.h00 = __fma_rn(ux, vx, s.h00); s.h01 = __fma_rn(ux, vy, s.h01);
     s.h10 = __fma_rn(uy, vx, s.h10); s.h11 = __fma_rn(uy, vy, s.h11);
     s.habs = __fma_rn(__dadd_rn(fabs(ux), fabs(uy)), __dadd_rn(fabs(vx), fabs(vy)), s.habs);  // noise scale of the terms
+}
+__device__ __forceinline__ void fit_term(FitSums& s, double qx, double qy, double tx, double ty, double ax, double ay) {
+    double ux, uy, vx, vy;
+    fit_uv(qx, qy, tx, ty, ax, ay, ux, uy, vx, vy);
+    fit_acc(s, ux, uy, vx, vy);
 }
 __device__ __forceinline__ void fit_reduce(FitSums& s) {
 #pragma unroll
@@ -389,7 +378,7 @@ __device__ __forceinline__ void fit_reduce(FitSums& s) {
 //   q' = R (q - a - mu) + a + mv  with q = M u + c   ->   M' = R M ;  c' = R (c - a - mu) + a + mv
 // D = new pose - old pose (what the next pass's skip test moves the queries by).
 __device__ __forceinline__ void fit_solve(const FitSums& s, int k, int allow_reflection, double ax, double ay, Pose& P, Pose& D) {
-    const double inv_k = __ddiv_rn(1.0, (double)k);
+    const double inv_k = __drcp_rn((double)k);   // correctly rounded reciprocal == __ddiv_rn(1.0, k), a shorter sequence
     const double mu0 = __dmul_rn(s.su0, inv_k), mu1 = __dmul_rn(s.su1, inv_k);
     const double mv0 = __dmul_rn(s.sv0, inv_k), mv1 = __dmul_rn(s.sv1, inv_k);
     // centred cross-covariance H = sum (u - mu)(v - mv)^T, from the shifted sums.  When the exact H is zero

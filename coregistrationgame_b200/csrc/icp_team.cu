@@ -34,42 +34,47 @@ namespace {
 // every CTA adds up the cycles between phase marks; tools/team_phase_clocks.py prints the shares.
 #if defined(FICP_PHASE_CLOCKS)
 __device__ unsigned long long g_phase_clk[16];
-#define PHASE_DECL long long ph_last = clock64(); unsigned long long ph_acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PHASE_DECL long long ph_last = clock64(); unsigned long long ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define PHASE(n) do { if (tid == 0) { const long long ph_now = clock64(); ph_acc[n] += (unsigned long long)(ph_now - ph_last); ph_last = ph_now; } } while (0)
-#define PHASE_FLUSH do { if (tid == 0) { for (int q = 0; q < 13; ++q) atomicAdd(&g_phase_clk[q], ph_acc[q]); } } while (0)
+#define PHASE_FLUSH do { if (tid == 0) { for (int q = 0; q < 16; ++q) atomicAdd(&g_phase_clk[q], ph_acc[q]); } } while (0)
 #else
 #define PHASE_DECL
 #define PHASE(n)
 #define PHASE_FLUSH
 #endif
 
+// Everything whose size follows from T (and Z3) alone comes first: with T and Z3 template parameters those offsets are
+// compile-time constants (immediate offsets from the shared-memory base).  With the window arrays in front they were
+// twenty run-time pointers - more than a kernel compiled for 64 registers can keep, so they were spilled and every phase
+// of a pass began by fetching its pointers back from local memory (L2: ~400 cycles each; measured 28.0 k -> 17.7 k cycles
+// per pass when the kernel was given 128 registers).  Only the window arrays (sized by the launch) stay dynamic.
 struct TeamLayout {
-    size_t s_u, s_z, s_g, w_xy, w_z, w_cell, rowoff, rowdelta, rowg, sd2, snn, ssl, list, dlist, slist, sidx, kbuf, sdd, tmp, misc, total;
+    size_t s_u, s_z, s_g, sd2, snn, ssl, list, dlist, slist, sidx, kbuf, sdd, tmp, misc, rowoff, rowdelta, rowg, w_xy, w_z, w_cell, total;
 };
-__host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
-    TeamLayout L;
+__host__ __device__ constexpr size_t team_up16(size_t b) { return (b + 15) & ~size_t(15); }
+__host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, int wcap_cells) {
+    TeamLayout L{};
     size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
-    L.s_u = take((size_t)t * 16);
-    L.s_z = take(z3 ? (size_t)t * 8 : 0);
-    L.s_g = take((size_t)kMaxStages * t * 8);
-    L.w_xy = take((size_t)wcap_pts * 16);
-    L.w_z = take(z3 ? (size_t)wcap_pts * 8 : 0);
-    L.w_cell = take((size_t)wcap_cells * 4);
-    L.rowoff = take((size_t)(wcap_rows + 1) * 4);
-    L.rowdelta = take((size_t)wcap_rows * 4);
-    L.rowg = take((size_t)wcap_rows * 4);
-    L.sd2 = take((size_t)t * 8);
-    L.snn = take((size_t)t * 4);
-    L.ssl = take((size_t)t * 2);
-    L.list = take((size_t)t * 2);
-    L.dlist = take((size_t)t * 2);
-    L.slist = take((size_t)t * 2);   // queries the group search hands to the one-lane search (possible exact ties)
-    L.sidx = take((size_t)t * 2);
-    L.kbuf = take((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms ux, uy
-    L.sdd = take((size_t)(t + 32) * 8);   // d2 in trim order (padded: p + p / E); later the fit term vx
-    L.tmp = take((size_t)(t + 32) * 8);   // chunk-serial partial sums of the scan (padded); later the fit term vy
-    L.misc = take(1536);
+    L.s_u = o; o += team_up16((size_t)t * 16);
+    L.s_z = o; o += team_up16(z3 ? (size_t)t * 8 : 0);
+    L.s_g = o; o += team_up16((size_t)kMaxStages * t * 8);
+    L.sd2 = o; o += team_up16((size_t)t * 8);
+    L.snn = o; o += team_up16((size_t)t * 4);
+    L.ssl = o; o += team_up16((size_t)t * 2);
+    L.list = o; o += team_up16((size_t)t * 2);
+    L.dlist = o; o += team_up16((size_t)t * 2);
+    L.slist = o; o += team_up16((size_t)t * 2);   // queries the group search hands to the one-lane search (possible exact ties)
+    L.sidx = o; o += team_up16((size_t)t * 2);
+    L.kbuf = o; o += team_up16((size_t)t * 16);   // two exchange buffers of the sort; later the fit terms ux, uy
+    L.sdd = o; o += team_up16((size_t)(t + 32) * 8);   // d2 in trim order (padded: p + p / E); later the fit term vx
+    L.tmp = o; o += team_up16((size_t)(t + 32) * 8);   // chunk-serial partial sums of the scan (padded); later the fit term vy
+    L.misc = o; o += 1792;
+    L.rowoff = o; o += team_up16((size_t)(kWindowRowsCap + 1) * 4);
+    L.rowdelta = o; o += team_up16((size_t)kWindowRowsCap * 4);
+    L.rowg = o; o += team_up16((size_t)kWindowRowsCap * 4);
+    L.w_xy = o; o += team_up16((size_t)wcap_pts * 16);
+    L.w_z = o; o += team_up16(z3 ? (size_t)wcap_pts * 8 : 0);
+    L.w_cell = o; o += team_up16((size_t)wcap_cells * 4);
     L.total = o;
     return L;
 }
@@ -79,12 +84,17 @@ struct TeamMisc {
     double stot[32], sexcl[32];     // chunk totals / exclusive prefixes of the canonical scan
     double red_a[32], red_b[32];    // block reductions
     int red_k[32];
-    double pose[12];                // new pose + pose update, broadcast by warp 0
-    double fsum[9];                 // reduced sums of the fit
-    double sk;                      // S at the chosen k (fixed-fraction mode)
+    double pose[2][12];             // [buffer]: pose (6) + pose update of the last fit (6); the other buffer takes the next fit
+    double sk;                      // S at the chosen k
+    double fk[2];                   // FRMSD and RMSE of the pass (computed by the last warp while warp 0 fits)
     int nlist, ndef, nser, nglob, icp, win_ok;
+    // CTA-uniform state kept here rather than in every thread's registers (the kernel is compiled for 64)
+    int win[4];                     // window rectangle of the staged plot: wx0, wy0, wx1, wy1
+    double ub[2];                   // mean of the plot's local coordinates (shift point of the fit)
+    unsigned cnt[4];                // this ICP: fix-up rounds, searched, deferred, order rebuilds
+    unsigned long long acc[6];      // this CTA: passes, fix-ups, queries, searched, deferred, order rebuilds
 };
-static_assert(sizeof(TeamMisc) <= 1536, "TeamMisc must fit its reservation");
+static_assert(sizeof(TeamMisc) <= 1792, "TeamMisc must fit its reservation");
 
 // Block bitonic sort, one 32-bit key per thread, ascending in thread order.  Strides below 32 exchange through
 // shuffles; larger strides through two alternating shared-memory buffers (one barrier per step).  Fully unrolled:
@@ -116,8 +126,14 @@ __device__ __forceinline__ unsigned block_sort32(unsigned key, unsigned* buf, in
 // Odd-even transposition rounds on the (d2, tree index) pairs in trim order until a round swaps nothing (-> true) or
 // `max_rounds` rounds are spent (-> false).  `sdd` uses the padded layout of the scan (PAD).
 #define PAD(p) ((p) + (p) / E)
-constexpr int kRepairMaxInversions = 12;   // adjacent inversions above which the order is rebuilt by the block sort
-constexpr int kRepairMaxRounds = 5;
+#ifndef FICP_REPAIR_INV
+#define FICP_REPAIR_INV 12
+#endif
+#ifndef FICP_REPAIR_ROUNDS
+#define FICP_REPAIR_ROUNDS 5
+#endif
+constexpr int kRepairMaxInversions = FICP_REPAIR_INV;   // adjacent inversions above which the order is rebuilt by the block sort
+constexpr int kRepairMaxRounds = FICP_REPAIR_ROUNDS;
 template <int T, int E>
 __device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* sidx, int tid, int max_rounds) {
     for (int round = 0; round < max_rounds; ++round) {
@@ -139,6 +155,18 @@ __device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* s
     return false;
 }
 
+// The pose is CTA-uniform state: it lives in shared memory (TeamMisc::pose) and is read where a phase needs it - held in
+// registers across the whole pass it cost every thread 24 registers, and the kernel is compiled for 64.
+__device__ __forceinline__ Pose ld_pose(const double* p) { return Pose{p[0], p[1], p[2], p[3], p[4], p[5]}; }
+
+struct TeamPtrs {
+    const double2* w_xy; const double* w_z; const unsigned* w_cell; const int* rowoff; const int* rowdelta;
+};
+__device__ __forceinline__ WindowAcc team_window(const TeamPtrs& tp, const int* win, const GridView& G) {
+    const int wx0 = win[0], wy0 = win[1], wx1 = win[2], wy1 = win[3];
+    return WindowAcc{tp.w_xy, tp.w_z, tp.w_cell, tp.rowoff, tp.rowdelta, G.orig, G.rec, wx0, wy0, wx1, wy1, wx1 - wx0, wy1 - wy0};
+}
+
 // min / lexicographic arg-min over the NW per-warp partials in shared memory, by every warp for itself (5 shuffles)
 __device__ __forceinline__ double warp_min_of(const double* red, int nw, int lane) {
     double v = (lane < nw) ? red[lane] : kInf;
@@ -147,15 +175,18 @@ __device__ __forceinline__ double warp_min_of(const double* red, int nw, int lan
     return v;
 }
 
+#ifndef FICP_TEAM_REGS
+#define FICP_TEAM_REGS 64      // registers per thread the kernel is compiled for: 1024 threads resident per SM
+#endif
 template <bool Z3, int T>
-__global__ void __launch_bounds__(T, (T >= 1024) ? 1 : (T == 512) ? 2 : (T == 256) ? 4 : (T == 128) ? 8 : 16)
+__global__ void __launch_bounds__(T, (65536 / FICP_TEAM_REGS / T) > 0 ? (65536 / FICP_TEAM_REGS / T) : 1)
 icp_team_kernel(const __grid_constant__ IcpParams P) {
     constexpr int E = T / 32;
     constexpr int NW = T / 32;
     constexpr int IB = (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;   // bits of a tree index
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TeamLayout L = team_layout(T, Z3, P.wcap_pts, P.wcap_cells, P.wcap_rows);
+    const TeamLayout L = team_layout(T, Z3, P.wcap_pts, P.wcap_cells);
     double2* s_u = reinterpret_cast<double2*>(smem + L.s_u);
     double* s_z = reinterpret_cast<double*>(smem + L.s_z);
     double* s_g = reinterpret_cast<double*>(smem + L.s_g);
@@ -186,7 +217,8 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     const unsigned lt_mask = (1u << lane) - 1u;
     const long long n_icps = (long long)P.n_plots * P.n_hyp_local;
     int staged_plot = -1;
-    unsigned long long acc_passes = 0, acc_fix = 0, acc_queries = 0, acc_searched = 0, acc_deferred = 0;
+    if (tid < 6) M->acc[tid] = 0ull;
+    const TeamPtrs tp{w_xy, w_z, w_cell, rowoff, rowdelta};
     unsigned n_global = 0;   // per thread
     PHASE_DECL;
 
@@ -252,19 +284,26 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             __syncthreads();
         }
         const bool win_ok = (M->win_ok != 0);
-        const WindowAcc W{w_xy, w_z, w_cell, rowoff, rowdelta, G_.orig, G_.rec,
-                          pm.wx0, pm.wy0, pm.wx1, pm.wy1, pm.wx1 - pm.wx0, pm.wy1 - pm.wy0};
-        const PlotCtx pc{s_u, s_z, pm.n, pm.fixed_k, pm.ubx, pm.uby};
+        const int fixed_k = pm.fixed_k;
         const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;  // [stage][0]=g [stage][1]=c
         const int n = pm.n;
 
         // ---- one ICP: start pose of hypothesis h (the expression of icp_persistent.cu / oracle.pre_transform)
         const int h = P.hyp_begin + j * P.hyp_stride;
         const double* hr = P.hyp + (size_t)h * 6;
-        Pose pose{hr[0], hr[1], hr[2], hr[3], dadd(pm.cinx, hr[4]), dadd(pm.ciny, hr[5])};
-        Pose dpose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int pb = 0;   // current pose buffer
+        if (tid == 0) {
+            double* mp = M->pose[0];
+            mp[0] = hr[0]; mp[1] = hr[1]; mp[2] = hr[2]; mp[3] = hr[3];
+            mp[4] = dadd(pm.cinx, hr[4]); mp[5] = dadd(pm.ciny, hr[5]);
+            mp[6] = mp[7] = mp[8] = mp[9] = mp[10] = mp[11] = 0.0;
+        }   // visible after the first barrier of the pass loop
+        if (tid == 0) {
+            M->win[0] = pm.wx0; M->win[1] = pm.wy0; M->win[2] = pm.wx1; M->win[3] = pm.wy1;
+            M->ub[0] = pm.ubx; M->ub[1] = pm.uby;
+            M->cnt[0] = M->cnt[1] = M->cnt[2] = M->cnt[3] = 0u;
+        }
         int passes = 0;
-        unsigned n_fix = 0, n_searched = 0, n_deferred = 0;
         if (tid >= n) { sd2[tid] = kInf; snn[tid] = -1; }   // padding never changes
         sidx[tid] = (unsigned short)tid;                     // no previous trim order yet
         PassOut po{0, kInf, 0.0, -1.0, -1};
@@ -284,7 +323,10 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 if (tid == 0) { M->nlist = have_prev ? 0 : n; M->ndef = 0; M->nser = 0; }
                 __syncthreads();
                 if (have_prev) {
-                    const int need = nn_test_round<Z3>(W, pc, pose, dpose, sd2, snn, ssl, warp, lane);
+                    const WindowAcc Wt = team_window(tp, M->win, G_);
+                    const PlotCtx pct{s_u, s_z, n, fixed_k, 0.0, 0.0};
+                    const int need = nn_test_round<Z3>(Wt, pct, ld_pose(M->pose[pb]), ld_pose(M->pose[pb] + 6), sd2, snn, ssl, warp, lane);
+                    PHASE(14);
                     const unsigned m = __ballot_sync(kFull, need >= 0);
                     int base = 0;
                     if (lane == 0 && m) base = atomicAdd(&M->nlist, __popc(m));
@@ -296,6 +338,9 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 __syncthreads();
                 PHASE(1);
                 const int n_list = M->nlist;
+                const Pose pose = ld_pose(M->pose[pb]);
+                const WindowAcc W = team_window(tp, M->win, G_);
+                const PlotCtx pc{s_u, s_z, n, fixed_k, 0.0, 0.0};
                 // lanes per query: a pass that searches few queries spreads each candidate stream over G lanes
                 int G = 1;
                 if (win_ok) while (G < 16 && n_list * G * 2 <= T) G <<= 1;
@@ -322,6 +367,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     double best;
                     int pos, cx, cy, lb_hi, pos2;
                     const int status = nn_search_group<Z3>(W, G_.g, active, qx, qy, qz, prev, G, sub, best, pos, cx, cy, lb_hi, pos2);
+                    PHASE(13);
                     int defer = -1, ser = -1;
                     if (active && sub == 0) {
                         if (status == 0) {
@@ -362,9 +408,8 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 const int n_def = M->ndef;
                 for (int base = warp * 32; base < n_def; base += NW * 32)
                     nn_deferred_chunk<Z3, false>(G_, W, pc, pose, sd2, snn, dlist, base, n_def, lane, n_global);
-                n_searched += (unsigned)n_list;
-                n_deferred += (unsigned)n_def;
-                dpose = Pose{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // a stage may end without a fit: same pose again
+                if (tid == 0) { M->cnt[1] += (unsigned)n_list; M->cnt[2] += (unsigned)n_def; }
+                if (tid < 6) M->pose[pb][6 + tid] = 0.0;  // a stage may end without a fit: same pose again, no move
                 __syncthreads();
                 PHASE(3);
 
@@ -388,6 +433,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 PHASE(4);
                 if (!sorted) {
+                    if (tid == 0) ++M->cnt[3];
                     // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
                     // order is verified afterwards and repaired where quantised codes collide
                     const unsigned fb = __float_as_uint(__double2float_rd(my_d2));
@@ -402,7 +448,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     bool inv = false;
                     if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[PAD(tid + 1)], (unsigned)sidx[tid + 1]);
                     if (__syncthreads_or(inv)) {
-                        ++n_fix;
+                        if (tid == 0) ++M->cnt[0];
                         (void)team_repair_order<T, E>(sdd, sidx, tid, 1 << 30);
                     }
                 }
@@ -411,10 +457,14 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 // inside the chunk of E consecutive positions (lane l of warp 0 walks chunk l; the padded layout keeps the
                 // 32 lanes on different banks), Kogge-Stone over the 32 chunk totals, prefix + partial
                 if (warp == 0) {
+                    // all E loads first (independent of the chain), then the E dependent additions
+                    double vq[E];
+#pragma unroll
+                    for (int q = 0; q < E; ++q) vq[q] = sdd[PAD(lane * E + q)];
                     double run = 0.0;
-#pragma unroll 4
+#pragma unroll
                     for (int q = 0; q < E; ++q) {
-                        run = __dadd_rn(run, sdd[PAD(lane * E + q)]);
+                        run = __dadd_rn(run, vq[q]);
                         spart[PAD(lane * E + q)] = run;
                     }
                     double inc = run;
@@ -432,14 +482,19 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 sidx_t = sidx[tid];
                 const double S = __dadd_rn(M->sexcl[lp], spart[PAD(tid)]);
 
-                // subset size: first strict minimum of FRMSD(k) = c_k sqrt(S_k / k)  (ficp.py:80-85)
+                // subset size: first strict minimum of FRMSD(k) = c_k sqrt(S_k / k)  (ficp.py:80-85).
+                // The filter G(k) = S_k (c_k^2 / k) leaves the k within rounding distance of the minimum - almost always
+                // ONE: then k is known after a block count, and the FRMSD value itself (an fp64 division and a square root,
+                // ~600 cycles) is computed by the last warp while the others already work on the fit.
                 int kstar;
+                bool f_pending = false;        // FRMSD / RMSE of the pass arrive through M->fk
                 double fstar = kInf, rstar = 0.0;
-                if (pc.fixed_k > 0) {
-                    kstar = pc.fixed_k;
+                if (fixed_k > 0) {
+                    kstar = fixed_k;
                     if (tid == kstar - 1) M->sk = S;
+                    f_pending = true;
+                    __syncthreads();   // every S has been read: the fit terms below reuse the scan's buffers
                 } else {
-                    // filter with G(k) = S_k (c_k^2 / k), exact expression only within rounding distance of the minimum
                     const double g = (tid < n) ? __dmul_rn(S, sg[r * 32 + lp]) : kInf;
                     double gb = g;
 #pragma unroll
@@ -448,63 +503,116 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     __syncthreads();
                     const double gbest = warp_min_of(M->red_a, NW, lane);
                     const double gthr = gbest * (1.0 + 1e-12);
-                    int kb = INT_MAX;
-                    if (tid < n && g <= gthr) {
-                        const int k = tid + 1;
-                        const double rm = sqrt(S / (double)k);
-                        fstar = __dmul_rn(__ldg(gc + r * 32 + lp), rm);
-                        kb = k;
-                        rstar = rm;
-                    }
+                    const bool cand = (tid < n && g <= gthr);
+                    if (cand) { M->red_k[0] = tid + 1; M->sk = S; }     // meaningful when there is exactly one
+                    const int ncand = __syncthreads_count(cand);
+                    if (ncand == 1) {
+                        kstar = M->red_k[0];
+                        f_pending = true;
+                    } else {
+                        int kb = INT_MAX;
+                        if (cand) {
+                            const int k = tid + 1;
+                            const double rm = sqrt(S / (double)k);
+                            fstar = __dmul_rn(__ldg(gc + r * 32 + lp), rm);
+                            kb = k;
+                            rstar = rm;
+                        }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double of = __shfl_xor_sync(kFull, fstar, o);
-                        const int ok = __shfl_xor_sync(kFull, kb, o);
-                        const double orr = __shfl_xor_sync(kFull, rstar, o);
-                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
-                    }
-                    if (lane == 0) { M->red_b[warp] = fstar; M->red_k[warp] = kb; M->stot[warp] = rstar; }
-                    __syncthreads();
-                    fstar = (lane < NW) ? M->red_b[lane] : kInf;
-                    kb = (lane < NW) ? M->red_k[lane] : INT_MAX;
-                    rstar = (lane < NW) ? M->stot[lane] : 0.0;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double of = __shfl_xor_sync(kFull, fstar, o);
+                            const int ok = __shfl_xor_sync(kFull, kb, o);
+                            const double orr = __shfl_xor_sync(kFull, rstar, o);
+                            if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
+                        }
+                        __syncthreads();   // red_k[0] has been read by everybody
+                        if (lane == 0) { M->red_b[warp] = fstar; M->red_k[warp] = kb; M->stot[warp] = rstar; }
+                        __syncthreads();
+                        fstar = (lane < NW) ? M->red_b[lane] : kInf;
+                        kb = (lane < NW) ? M->red_k[lane] : INT_MAX;
+                        rstar = (lane < NW) ? M->stot[lane] : 0.0;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double of = __shfl_xor_sync(kFull, fstar, o);
-                        const int ok = __shfl_xor_sync(kFull, kb, o);
-                        const double orr = __shfl_xor_sync(kFull, rstar, o);
-                        if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double of = __shfl_xor_sync(kFull, fstar, o);
+                            const int ok = __shfl_xor_sync(kFull, kb, o);
+                            const double orr = __shfl_xor_sync(kFull, rstar, o);
+                            if (of < fstar || (of == fstar && ok < kb)) { fstar = of; kb = ok; rstar = orr; }
+                        }
+                        kstar = (kb == INT_MAX) ? 0 : kb;
                     }
-                    kstar = (kb == INT_MAX) ? 0 : kb;
                 }
                 po.k = kstar;
                 if (kstar == 0) {
                     po.f = kInf; po.rmse = 0.0; po.thr = -1.0; po.thr_idx = -1;
+                    f_pending = false;
                 } else {
                     po.thr_idx = sidx[kstar - 1];
                     po.thr = sd2[po.thr_idx];
-                    if (pc.fixed_k > 0) {
-                        __syncthreads();
-                        const int pstar = kstar - 1, lstar = pstar / E, rsel = pstar - lstar * E;
-                        rstar = sqrt(M->sk / (double)kstar);
-                        fstar = __dmul_rn(__ldg(gc + rsel * 32 + lstar), rstar);
-                    }
                     po.f = fstar;
                     po.rmse = rstar;
                 }
+                PHASE(7);
+
+                // ================= rigid fit (ficp.py:89-110), started BEFORE the stage logic below has the FRMSD value: the
+                // fit needs only the trimmed subset.  It is skipped when no outcome of the convergence test could use it.
+                // Every thread prepares its tree's term; warp 0 adds them in the order of the one-warp kernel - lane l adds
+                // the trees l, l + 32, ... in turn, then an xor butterfly over the 32 lanes - and solves; the last warp
+                // computes FRMSD / RMSE of the pass meanwhile.
+                const bool fit_useful = kstar > 0 && (first ? (it < P.max_iter) : (it + 1 < P.max_iter));
+                double ax = 0.0, ay = 0.0;
+                if (fit_useful) {
+                    const Pose pose = ld_pose(M->pose[pb]);
+                    fit_shift(pose, M->ub[0], M->ub[1], ax, ay);
+                    const bool inl = tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx));
+                    finl[tid] = inl ? 1 : 0;
+                    if (inl) {
+                        double qx, qy, ux, uy, vx, vy;
+                        pose_apply(pose, s_u[tid], qx, qy);
+                        const double2 t = corr_xy(G_, team_window(tp, M->win, G_), snn[tid]);
+                        fit_uv(qx, qy, t.x, t.y, ax, ay, ux, uy, vx, vy);
+                        f_ux[tid] = ux; f_uy[tid] = uy; f_vx[tid] = vx; f_vy[tid] = vy;
+                    }
+                }
+                __syncthreads();     // fit terms, M->sk
+                PHASE(8);
+                if (f_pending && warp == NW - 1) {
+                    const int pstar = kstar - 1, lstar = pstar / E, rsel = pstar - lstar * E;
+                    const double rm = sqrt(M->sk / (double)kstar);
+                    const double fv = __dmul_rn(__ldg(gc + rsel * 32 + lstar), rm);
+                    if (lane == 0) { M->fk[0] = fv; M->fk[1] = rm; }
+                }
+                if (fit_useful && warp == 0) {
+                    FitSums fs = fit_zero();
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int i = e * 32 + lane;
+                        const double ux = f_ux[i], uy = f_uy[i], vx = f_vx[i], vy = f_vy[i];
+                        if (finl[i]) fit_acc(fs, ux, uy, vx, vy);
+                    }
+                    fit_reduce(fs);
+                    PHASE(9);
+                    Pose np = ld_pose(M->pose[pb]), nd;
+                    fit_solve(fs, po.k, P.allow_reflection, ax, ay, np, nd);
+                    if (lane == 0) {
+                        double* mp = M->pose[pb ^ 1];
+                        mp[0] = np.m00; mp[1] = np.m01; mp[2] = np.m10; mp[3] = np.m11; mp[4] = np.cx; mp[5] = np.cy;
+                        mp[6] = nd.m00; mp[7] = nd.m01; mp[8] = nd.m10; mp[9] = nd.m11; mp[10] = nd.cx; mp[11] = nd.cy;
+                    }
+                }
+                __syncthreads();
+                if (f_pending) { po.f = M->fk[0]; po.rmse = M->fk[1]; }
                 if (P.trace_cap > 0 && passes < P.trace_cap && tid < n) {
                     // per-pass trace (tests only): original target row, squared distance, membership in the trimmed subset
                     const size_t rec = (size_t)c * P.trace_cap + passes, base = rec * P.trace_stride;
                     const int code = snn[tid];
                     int orig = -1;
-                    if (code != -1) orig = grid_orig(G_, (code < 0) ? (code & 0x7FFFFFFF) : W.global_pos(code & 0xFFFF));
+                    if (code != -1) orig = grid_orig(G_, (code < 0) ? (code & 0x7FFFFFFF) : team_window(tp, M->win, G_).global_pos(code & 0xFFFF));
                     P.tr_idx[base + tid] = orig;
                     P.tr_d2[base + tid] = my_d2;
                     P.tr_in[base + tid] = (po.k > 0 && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) ? 1 : 0;
                     if (tid == 0) { P.tr_k[rec] = po.k; P.tr_f[rec] = po.f; }
                 }
                 ++passes;
-                PHASE(7);
 
                 // ================= stage logic (ficp.py:122-147)
                 if (first) {
@@ -517,52 +625,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     ++it;
                 }
                 if (it >= P.max_iter) break;
-
-                // ================= rigid fit (ficp.py:89-110).  Every thread prepares its tree's term; the nine running
-                // sums are formed one (sum, lane) pair per thread in the order of the one-warp kernel - lane l adds the
-                // trees l, l + 32, ... in turn, then an xor butterfly over the 32 lanes - and one warp solves.
-                double ax, ay;
-                fit_shift(pose, pc.ubx, pc.uby, ax, ay);
-                {
-                    const bool inl = tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx));
-                    finl[tid] = inl ? 1 : 0;
-                    if (inl) {
-                        double qx, qy, ux, uy, vx, vy;
-                        pose_apply(pose, s_u[tid], qx, qy);
-                        const double2 t = corr_xy(G_, W, snn[tid]);
-                        fit_uv(qx, qy, t.x, t.y, ax, ay, ux, uy, vx, vy);
-                        f_ux[tid] = ux; f_uy[tid] = uy; f_vx[tid] = vx; f_vy[tid] = vy;
-                    }
-                }
-                __syncthreads();
-                PHASE(8);
-                for (int q = warp; q < 9; q += NW) {
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int e = 0; e < E; ++e) {
-                        const int i = e * 32 + lane;
-                        if (finl[i]) acc = fit_acc_one(q, acc, f_ux[i], f_uy[i], f_vx[i], f_vy[i]);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(kFull, acc, o));
-                    if (lane == 0) M->fsum[q] = acc;
-                }
-                __syncthreads();
-                PHASE(9);
-                if (warp == 0) {
-                    const FitSums fs{M->fsum[0], M->fsum[1], M->fsum[2], M->fsum[3], M->fsum[4], M->fsum[5], M->fsum[6], M->fsum[7], M->fsum[8]};
-                    Pose np = pose, nd;
-                    fit_solve(fs, po.k, P.allow_reflection, ax, ay, np, nd);
-                    if (lane == 0) {
-                        M->pose[0] = np.m00; M->pose[1] = np.m01; M->pose[2] = np.m10; M->pose[3] = np.m11;
-                        M->pose[4] = np.cx; M->pose[5] = np.cy;
-                        M->pose[6] = nd.m00; M->pose[7] = nd.m01; M->pose[8] = nd.m10; M->pose[9] = nd.m11;
-                        M->pose[10] = nd.cx; M->pose[11] = nd.cy;
-                    }
-                }
-                __syncthreads();
-                pose = Pose{M->pose[0], M->pose[1], M->pose[2], M->pose[3], M->pose[4], M->pose[5]};
-                dpose = Pose{M->pose[6], M->pose[7], M->pose[8], M->pose[9], M->pose[10], M->pose[11]};
+                pb ^= 1;   // the fit is taken
                 PHASE(10);
             }
         }
@@ -580,6 +643,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
         if (tid == 0) {
             const int ng = M->nglob;
             HypResult res;
+            const Pose pose = ld_pose(M->pose[pb]);
             res.m00 = pose.m00; res.m01 = pose.m01; res.m10 = pose.m10; res.m11 = pose.m11;
             res.cx = pose.cx; res.cy = pose.cy;
             res.frmsd = po.f; res.rmse = po.rmse; res.k = po.k; res.passes = passes;
@@ -589,25 +653,26 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             const float score = (po.k >= P.min_k && po.k > 0) ? (float)po.f : __int_as_float(0x7F800000);
             const unsigned long long bk = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)h;
             atomicMin(P.best_key + plot, bk);
-            acc_passes += passes; acc_fix += n_fix; acc_searched += n_searched; acc_deferred += n_deferred;
-            acc_queries += (unsigned long long)passes * n;
+            M->acc[0] += passes; M->acc[1] += M->cnt[0]; M->acc[2] += (unsigned long long)passes * n;
+            M->acc[3] += M->cnt[1]; M->acc[4] += M->cnt[2]; M->acc[5] += M->cnt[3];
             if (ng) atomicAdd(P.stats + 1, (unsigned long long)ng);
         }
         if (P.final_xy && P.n_hyp_local == 1 && tid < n) {
             double qx, qy;
-            pose_apply(pose, s_u[tid], qx, qy);
+            pose_apply(ld_pose(M->pose[pb]), s_u[tid], qx, qy);
             P.final_xy[(pm.off + tid) * 2] = qx;
             P.final_xy[(pm.off + tid) * 2 + 1] = qy;
         }
     }
     PHASE(12);
     PHASE_FLUSH;
-    if (tid == 0 && acc_passes) {
-        atomicAdd(P.stats + 0, acc_passes);
-        atomicAdd(P.stats + 3, acc_fix);
-        atomicAdd(P.stats + 4, acc_queries);
-        atomicAdd(P.stats + 5, acc_searched);
-        atomicAdd(P.stats + 6, acc_deferred);
+    if (tid == 0 && M->acc[0]) {
+        atomicAdd(P.stats + 0, M->acc[0]);
+        atomicAdd(P.stats + 3, M->acc[1]);
+        atomicAdd(P.stats + 4, M->acc[2]);
+        atomicAdd(P.stats + 5, M->acc[3]);
+        atomicAdd(P.stats + 6, M->acc[4]);
+        atomicAdd(P.stats + 7, M->acc[5]);
     }
 }
 
@@ -638,7 +703,7 @@ extern "C" __attribute__((visibility("default"))) int ficp_debug_phase_clocks(un
 #endif
 
 size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
-    return team_layout(32 * e, z3, wcap_pts, wcap_cells, wcap_rows).total;
+    return team_layout(32 * e, z3, wcap_pts, wcap_cells).total;
 }
 
 #define FICP_TEAM_DISPATCH(FN, ...)                                                                   \

@@ -31,7 +31,7 @@ namespace ficp {
 namespace {
 
 #ifndef FICP_BULK_MINCTAS
-#define FICP_BULK_MINCTAS 4   // resident CTAs per SM the search kernel is compiled for (64 registers per thread)
+#define FICP_BULK_MINCTAS 3   // resident CTAs per SM the search kernel is compiled for (80 registers; 4 CTAs = 64 registers spills: measured slower)
 #endif
 constexpr int kBT = 256;               // threads per CTA = queries per chunk
 constexpr int kTileBytes = 20480;      // staged target records per window (typical window: 3 rows x ~25 cells x 3 points)
@@ -103,15 +103,32 @@ __global__ void __launch_bounds__(128) qplan_kernel(GridView v, const double4* _
     ChunkPlan P;
     P.pad[0] = P.pad[1] = P.pad[2] = 0;
     P.nseg = (cyb - cya + 1 <= kMaxSeg) ? cyb - cya + 1 : 0;
+    // first record of every further row inside the chunk (records are in cell order: rows ascend) - binary search
+    long long lo_of[kMaxSeg + 1];
+    lo_of[0] = base;
+    for (int sgi = 1; sgi <= kMaxSeg; ++sgi) {
+        lo_of[sgi] = last + 1;
+        if (sgi >= P.nseg) continue;
+        long long lo = lo_of[sgi - 1], hi = last + 1;   // first record with row >= cya + sgi
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            const int cym = clamp_cell((qrec[mid].y - g.y0) * g.inv_h, g.gh);
+            if (cym >= cya + sgi) hi = mid; else lo = mid + 1;
+        }
+        lo_of[sgi] = lo;
+    }
     for (int sgi = 0; sgi < kMaxSeg; ++sgi) {
         SegPlan& S = P.seg[sgi];
         S = SegPlan{};
         if (sgi >= P.nseg) continue;
         const int y = cya + sgi;
-        const int xa = (y == cya) ? cxa : 0, xb = (y == cyb) ? cxb : g.gw - 1;   // cell run of the chunk inside row y
+        S.y = y; S.ok = 1; S.ww1 = 1;
+        if (lo_of[sgi + 1] <= lo_of[sgi]) continue;       // no query of the chunk in this row: empty window
+        const int xa = clamp_cell((qrec[lo_of[sgi]].x - g.x0) * g.inv_h, g.gw);          // cell run of the chunk inside row y
+        const int xb = clamp_cell((qrec[lo_of[sgi + 1] - 1].x - g.x0) * g.inv_h, g.gw);
         const int wx0 = (xa > 0) ? xa - 1 : 0, wx1 = (xb < g.gw - 1) ? xb + 1 : g.gw - 1;
         const int wy0 = (y > 0) ? y - 1 : 0, wy1 = (y < g.gh - 1) ? y + 1 : g.gh - 1;
-        S.y = y; S.wx0 = wx0; S.ww1 = wx1 - wx0 + 2; S.wy0 = wy0; S.wh = wy1 - wy0 + 1;
+        S.wx0 = wx0; S.ww1 = wx1 - wx0 + 2; S.wy0 = wy0; S.wh = wy1 - wy0 + 1;
         long long total = 0;
         for (int r = 0; r < S.wh; ++r) {
             const unsigned* row = v.cell_start + (size_t)(wy0 + r) * g.gw;
@@ -349,9 +366,13 @@ __global__ void __launch_bounds__(128) nn_ring_finish_kernel(GridView v, const B
 
 }  // namespace
 
+// Planner (measured on B200, profiles/r02_nn_bulk_probe_*.jsonl): the bulk kernel pays where a query meets many
+// candidates - indexes built with >= ~4.5 points per cell (the ICP density for XYZ) - and the batch is large and dense
+// enough for its windows (at least half as many queries as cells).  On sparse grids (bulk-query density, 1.5 - 3 points per
+// cell) the thread-per-query kernel is as fast or faster: both are bound by instruction issue / the FP64 pipe there.
 bool nn_bulk_applies(const GridView& v, long long n) {
     const long long nc = (long long)v.g.gw * v.g.gh;
-    return n >= kBulkMinQueries && n <= 0x7FFFFFFFLL && 2 * n >= nc;
+    return n >= kBulkMinQueries && n <= 0x7FFFFFFFLL && 2 * n >= nc && (double)v.m >= 4.5 * (double)nc;
 }
 
 int launch_nn_query_bulk(const GridView& v, bool z3, const double* d_q, long long n, int ld, int* d_idx, double* d_dist,

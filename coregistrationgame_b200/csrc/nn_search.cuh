@@ -550,10 +550,20 @@ FICP_HD bool nn_search_block3(const Acc& acc, const GridGeom& g, double qx, doub
 }
 
 // Unseeded form for bulk queries (nn_bulk.cu): the query's OWN cell is scored first, so that the pruning of the other
-// eight cells has a bound to work with; then the surviving cells of the 3x3 block are streamed as one flat candidate
-// list (the own cell comes by again - three candidates of ~twenty).  The winner is kept with a plain `<`; an exact tie
-// with a different point raises a flag and only then (rare) the stream is looked at again with the
-// lowest-original-index rule.  Same result as nn_search_block3: exact minimum over the block, ties to the lowest index.
+// eight cells has a bound to work with; then the surviving cells of the 3x3 block follow as at most four runs of
+// consecutive cells (every point is visited once).  The winner is kept with a plain `<`; an exact tie between two points
+// raises a flag and only then (rare) the candidates are looked at again with the lowest-original-index rule.  Same result as nn_search_block3: exact minimum over the block, ties to the lowest index.
+template <bool Z3, class Acc>
+FICP_HD void nn_scan_run_flag(const Acc& acc, int s, int e, double qx, double qy, double qz, double& best, int& bestpos, bool& tie) {
+#pragma unroll 2
+    for (int j = s; j < e; ++j) {
+        const double d = nn_dist2<Z3>(acc, j, qx, qy, qz);
+        tie = tie || (d == best);        // an exact tie between two different points (no point is visited twice)
+        const bool lt = d < best;
+        best = lt ? d : best;
+        bestpos = lt ? j : bestpos;
+    }
+}
 template <bool Z3, class Acc>
 FICP_HD void nn_search_block3_unseeded(const Acc& acc, const GridGeom& g, double qx, double qy, double qz, int cx, int cy,
                                        double& best, int& bestpos) {
@@ -562,26 +572,19 @@ FICP_HD void nn_search_block3_unseeded(const Acc& acc, const GridGeom& g, double
     best = kInf;
     bestpos = -1;
     bool tie = false;
-    {
-        int s0, e0;
-        acc.seg(cy, cx, cx, s0, e0);
-        for (int j = s0; j < e0; ++j) {
-            const double d = nn_dist2<Z3>(acc, j, qx, qy, qz);
-            tie = tie || (d == best);
-            const bool lt = d < best;
-            best = lt ? d : best;
-            bestpos = lt ? j : bestpos;
-        }
-    }
+    int s0, e0;
+    acc.seg(cy, cx, cx, s0, e0);
+    nn_scan_run_flag<Z3>(acc, s0, e0, qx, qy, qz, best, bestpos, tie);
     double gx[3], gy[3];
     nn_block3_gaps(g, qx, qy, cx, cy, gx, gy);
     const double bound = best;
-    int s[3], n[3];
+    // the other eight cells as (at most) four runs of consecutive cells: row below, left and right neighbour, row above
+    int rs[4], re[4];
 #pragma unroll
-    for (int ry = 0; ry < 3; ++ry) {
+    for (int k = 0; k < 4; ++k) { rs[k] = 0; re[k] = 0; }
+#pragma unroll
+    for (int ry = 0; ry < 3; ry += 2) {
         const int y = cy - 1 + ry;
-        s[ry] = 0;
-        n[ry] = 0;
         if (y < yl || y > yh) continue;
         int xa = cx + 2, xb = cx - 2;
 #pragma unroll
@@ -592,34 +595,17 @@ FICP_HD void nn_search_block3_unseeded(const Acc& acc, const GridGeom& g, double
                 xb = x;
             }
         }
-        if (xa <= xb) {
-            int e;
-            acc.seg(y, xa, xb, s[ry], e);
-            n[ry] = e - s[ry];
-        }
+        if (xa <= xb) acc.seg(y, xa, xb, rs[ry ? 3 : 0], re[ry ? 3 : 0]);
     }
-    const int n01 = n[0] + n[1], total = n01 + n[2];
-    const int o1 = s[1] - n[0], o2 = s[2] - n01;
-    for (int t = 0; t < total; t += 2) {
-        const int t1 = (t + 1 < total) ? t + 1 : t;
-        const int j0 = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
-        const int j1 = t1 + ((t1 < n[0]) ? s[0] : (t1 < n01) ? o1 : o2);
-        const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
-        const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
-        tie = tie || (da == best && j0 != bestpos);
-        const bool la = da < best;
-        best = la ? da : best;
-        bestpos = la ? j0 : bestpos;
-        tie = tie || (db == best && j1 != bestpos);
-        const bool lb = db < best;
-        best = lb ? db : best;
-        bestpos = lb ? j1 : bestpos;
-    }
-    if (tie) {
-        for (int t = 0; t < total; ++t) {
-            const int j = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
-            nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
-        }
+    if (cx - 1 >= xl && gx[0] + gy[1] <= bound) acc.seg(cy, cx - 1, cx - 1, rs[1], re[1]);
+    if (cx + 1 <= xh && gx[2] + gy[1] <= bound) acc.seg(cy, cx + 1, cx + 1, rs[2], re[2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nn_scan_run_flag<Z3>(acc, rs[k], re[k], qx, qy, qz, best, bestpos, tie);
+    if (tie) {   // rare: second look with the lowest-original-index rule
+        for (int j = s0; j < e0; ++j) nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            for (int j = rs[k]; j < re[k]; ++j) nn_eval<Z3>(acc, j, qx, qy, qz, best, bestpos);
     }
 }
 

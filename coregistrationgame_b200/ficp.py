@@ -57,7 +57,12 @@ class FractionalICP:
     def _target_index(self, target):
         """Grid index over `target`, cached for self.target (built once, not once per pass)."""
         if target is self.target:
-            key = (id(target), target.shape)
+            # keyed on the CONTENT of the matched columns (xor + wrapping sum of the float64 bit patterns: two passes over
+            # the array, ~5 ms per 1e6 points), so an in-place edit of self.target between calls rebuilds the grid - the
+            # reference rebuilds its kd-tree from the current contents on every call (ficp.py:69)
+            bits = self._xyz_or_xy(target).view(np.uint64)
+            key = (id(target), target.shape, int(np.bitwise_xor.reduce(bits, axis=None)) if bits.size else 0,
+                   int(bits.sum(dtype=np.uint64)) if bits.size else 0)
             if self._index is None or self._index_key != key:
                 if self._index is not None:
                     self._index.close()
@@ -158,6 +163,9 @@ class FractionalICP:
             return self.source  # ficp.py:66-68,76-77,125-126: nothing to match, nothing moves
         if not np.isfinite(self.source[:, :self.match_dims]).all():
             raise ValueError("'x' must be finite, check for nan or inf values")
+        if n > _STEPWISE_MAX_N:
+            raise NotImplementedError(f"plots above {_STEPWISE_MAX_N} rows are not supported by the stage kernels "
+                                      f"(got {n}); split the plot")
         if n > _KERNEL_MAX_N:
             for lam in lambdas:
                 self.lambda_val = lam

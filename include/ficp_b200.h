@@ -182,7 +182,8 @@ FICP_API int ficp_batch_run(ficp_batch* b, void* stream);  /* enqueue only */
  * with want_final_xy and n_hyp_local == 1), stats [8]: passes, global-path queries, windows disabled,
  * fix-up rounds, queries, queries that needed a search (the others passed the skip test: their previous
  * neighbour was proved to still be the nearest), searched queries that the 3x3 block of cells did not settle
- * (finished by the ring loop or on the global grid). */
+ * (finished by the ring loop or on the global grid), passes whose trim order the CTA-per-ICP kernel rebuilt with its
+ * block sort (the others reused / repaired the previous pass's order; 0 for the warp-per-ICP kernel). */
 FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_t* best_keys, double* final_xy,
                        uint64_t* stats, void* stream);
 /* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then

@@ -87,7 +87,7 @@ def test_nn_query_bulk_kernel_bit_exact(gpu, dims):
         ref_idx, ref_d2 = orc.nn_assign_bruteforce(q[sel], tgt, dims)
         np.testing.assert_array_equal(idx_b[sel], ref_idx)
         np.testing.assert_array_equal(dist_b[sel], np.sqrt(ref_d2))
-        idx_a, dist_a = ti.query(q)                             # auto picks the bulk kernel here
+        idx_a, dist_a = ti.query(q)                             # auto: bulk kernel on the dense (ICP) grid, thread kernel otherwise
         np.testing.assert_array_equal(idx_a, idx_b)
         ti.close()
 
@@ -389,3 +389,18 @@ def test_mixed_dims_fall_back_to_xy(gpu):
     out = icp.run()
     assert out.shape == src.shape and icp.lambda_val == 1.3
     np.testing.assert_array_equal(out[:, 2], src[:, 2])
+
+
+def test_target_edited_in_place_rebuilds_the_index(gpu):
+    """the cached grid index is keyed on the CONTENT of the matched columns - the reference rebuilds its
+    kd-tree from the current `target` on every call (ficp.py:69), so an in-place edit between calls must be seen."""
+    from coregistrationgame_b200 import FractionalICP
+    tgt, src = _scene(3000, 60, seed=2, dims=3)
+    icp = FractionalICP(src, tgt)
+    m1, d1 = icp.find_correspondences(icp.source, icp.target)
+    icp.target[:, :2] += 7.5                                   # same object, same shape, new contents
+    m2, d2 = icp.find_correspondences(icp.source, icp.target)
+    ref_idx, ref_d2 = orc.nn_assign_bruteforce(icp.source, icp.target, 3)
+    np.testing.assert_array_equal(m2, icp.target[ref_idx])
+    np.testing.assert_array_equal(d2, np.sqrt(ref_d2))
+    assert not np.array_equal(d1, d2)

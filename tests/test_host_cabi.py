@@ -72,6 +72,15 @@ def test_constructor_and_degenerate_inputs_without_gpu():
     assert t.frmsd(0.5, 0, src, src) == float("inf")
 
 
+def test_oversized_plot_is_refused_before_any_work():
+    """plots above the stage kernels' 8192-row limit raise up front (no NN pass first)."""
+    from coregistrationgame_b200 import FractionalICP
+    rng = np.random.default_rng(0)
+    icp = FractionalICP(rng.normal(size=(8193, 2)), rng.normal(size=(50, 2)))
+    with pytest.raises(NotImplementedError, match="8192"):
+        icp.run()
+
+
 def test_host_helpers_match_oracle():
     from coregistrationgame_b200 import batch
     np.testing.assert_array_equal(batch.hypothesis_table(16, (0, 1), batch.translation_lattice(3, 2.5)),

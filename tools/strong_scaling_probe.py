@@ -49,7 +49,7 @@ for w in [int(x) for x in args.worlds.split(",")]:
         print(json.dumps({"world": w, "kernel": name, "ms_median": float(np.median(ms)), "ms_min": float(min(ms)),
                           "passes": out["stats"]["passes"], "icps": int(b.n_hyp_local), "longest": int(row["passes"].max()),
                           "hyp_iter_per_s": out["stats"]["passes"] / (np.median(ms) * 1e-3), "bit_identical_to_w1_warp": same,
-                          "searched": out["stats"]["searched_queries"], "fixups": out["stats"]["fixup_rounds"],
+                          "searched": out["stats"]["searched_queries"], "fixups": out["stats"]["fixup_rounds"], "order_rebuilds": out["stats"].get("order_rebuilds"),
                           "launch": {k: b.info[k] for k in ("cta_per_icp", "warps_per_cta", "ctas", "ctas_per_sm", "team_warps", "helpers", "smem_bytes")}}), flush=True)
         b.close()
 ti.close()

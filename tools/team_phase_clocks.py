@@ -12,7 +12,8 @@ from coregistrationgame_b200.batch import hypothesis_table, translation_lattice
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cps = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 names = ["start/stage", "skip test+list", "search", "deferred", "order check+repair", "block sort", "scan", "arg-min",
-         "stage logic+fit prep", "fit sums", "solve+bcast", "results", "tail"]
+         "fit prep", "f ‖ fit sums (warp 0)", "solve+barrier+logic", "results", "tail",
+         "search: up to the merged group result", "skip test: test itself", "-"]
 lib = _lib.load()
 fn = lib.ficp_debug_phase_clocks
 fn.argtypes = [C.POINTER(C.c_uint64), C.c_int]
@@ -31,7 +32,7 @@ e0.record(stream); b.run(stream); e1.record(stream)
 torch.cuda.synchronize()
 fn(buf, 0)
 st = b.results(per_hypothesis=False)["stats"]
-clk = np.array(list(buf)[:13], dtype=np.float64)
+clk = np.array(list(buf)[:16], dtype=np.float64)
 tot = clk.sum()
 out = {"world": world, "ms": e0.elapsed_time(e1), "passes": st["passes"], "ctas": b.info["ctas"], "ctas_per_sm": b.info["ctas_per_sm"],
        "cycles_per_pass_per_cta": tot / st["passes"],
