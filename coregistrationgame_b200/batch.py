@@ -48,6 +48,24 @@ def translation_lattice(n_side, pitch):
 IDENTITY_HYPOTHESIS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
 
 
+def plot_centres(src, offsets):
+    """Centre of every plot = ``rows[:, :2].mean(axis=0)`` of its rows (what the oracle and the reference-side callers
+    compute), for ten thousand plots without ten thousand numpy calls: plots of equal size are reduced together through
+    a (plots, n, ld) view - the same additions in the same order, bit for bit (pinned by tests/test_host_cabi.py)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    sizes = np.diff(offsets)
+    out = np.empty((sizes.shape[0], 2), dtype=np.float64)
+    if sizes.shape[0] and (sizes == sizes[0]).all():
+        n = int(sizes[0])
+        out[...] = src.reshape(sizes.shape[0], n, src.shape[1])[:, :, :2].mean(axis=1)
+        return out
+    for n in np.unique(sizes):
+        who = np.nonzero(sizes == n)[0]
+        rows = offsets[who][:, None] + np.arange(int(n))[None, :]
+        out[who] = src[rows][:, :, :2].mean(axis=1)
+    return out
+
+
 def frmsd_weights(n, lam):
     """w[k-1] = 1/((k/n)**lam) with Python-float semantics - the very expression of ficp.py:60,81,
     so the table is bit-identical to what the reference multiplies with."""
@@ -167,7 +185,7 @@ class IcpBatch:
         self.hyp = np.ascontiguousarray(IDENTITY_HYPOTHESIS if hyp_table is None else
                                         np.asarray(hyp_table, dtype=np.float64).reshape(-1, 6))
         if centres is None:
-            centres = np.array([s[:, :2].mean(axis=0) for s in srcs])
+            centres = plot_centres(self.src, self.offsets)
         self.centres = np.ascontiguousarray(np.asarray(centres, dtype=np.float64).reshape(self.n_plots, 2))
         self.n_stages = int(n_stages)
         lam2 = STAGE2_LAMBDA[self.match_dims] if stage2_lambda is None else stage2_lambda
@@ -182,10 +200,11 @@ class IcpBatch:
             offs.append(offs[-1] + self.n_stages * n)
         self.weights = np.ascontiguousarray(np.concatenate(tabs))
         self.weight_offsets = np.array(offs, dtype=np.int64)
-        self.plot_tab = np.array([tab_of[int(n)] for n in self.sizes], dtype=np.int32)
+        self.plot_tab = np.searchsorted(np.array(uniq, dtype=np.int64), self.sizes).astype(np.int32)
         self.fixed_k = None
         if fixed_frac is not None:
-            self.fixed_k = np.array([fixed_fraction_k(int(n), fixed_frac) for n in self.sizes], dtype=np.int32)
+            k_of = {n: fixed_fraction_k(n, fixed_frac) for n in uniq}
+            self.fixed_k = np.array([k_of[int(n)] for n in self.sizes], dtype=np.int32)
         self.hyp_begin, self.hyp_stride = int(hyp_shard[0]), int(hyp_shard[1])
         prm = _lib.BatchParams(self.n_stages, int(max_iterations), int(bool(allow_reflection)), int(min_k),
                                float(threshold), float(window_margin), int(warps_per_cta), int(ctas_per_sm),

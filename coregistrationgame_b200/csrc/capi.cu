@@ -539,7 +539,9 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // batch smaller than that is bounded by the serial chain of its longest ICP, and the CTA-per-ICP kernel (icp_team.cu:
     // every phase of a pass cooperative across 32 e threads) runs that chain several times faster.  Plots of <= 32
     // trees (e == 1) are one warp either way.  Auto: below kCtaAutoIcpsPerSm ICPs per SM (measured, profiles/r02_summary.md).
-    constexpr long long kCtaAutoIcpsPerSm = 8;
+    // One start pose per plot (config 4) leaves the warp-per-ICP kernel one warp per CTA: the CTA-per-ICP kernel is ahead a
+    // little further there (measured at 8.4 ICPs per SM: 40.7 vs 37.6 M hyp-iter/s, profiles/r02_bench_c4_*.json).
+    const long long kCtaAutoIcpsPerSm = (n_hyp_local == 1) ? 12 : 8;
     const bool cta_mode = (e >= 2) && (prm->cta_per_icp == 2 || (prm->cta_per_icp == 0 && prm->team_warps == 0 && prm->no_helpers == 0 &&
                                                                  prm->warps_per_cta == 0 && n_icps_all <= kCtaAutoIcpsPerSm * sms));
     // Elastic kernel: warps without an ICP of their own help the ICPs in flight in their CTA.  It pays while the

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .batch import IcpBatch, TargetIndex, compose_world_transforms, decode_best_keys
+from .batch import IcpBatch, TargetIndex, compose_world_transforms, decode_best_keys, plot_centres
 
 PACK_WORDS = 12          # int64 words per plot record: key, 10 words of ficp_hyp_result, passes of the rank
 
@@ -111,8 +111,10 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
             # ---- fewer hypotheses than ranks (e.g. one start pose per plot): shard the PLOTS, gather the rows
             mine = plot_shard(n_plots, rank, world)
             centres_all = kw.pop("centres", None)
-            if centres_all is None:
-                centres_all = np.array([np.asarray(s, dtype=np.float64)[:, :2].mean(axis=0) for s in sources])
+            if centres_all is None:     # every rank composes the world transforms of ALL plots: centres of all of them
+                stacked = [np.asarray(s, dtype=np.float64) for s in sources]
+                offs = np.concatenate([[0], np.cumsum([a.shape[0] for a in stacked])]).astype(np.int64)
+                centres_all = plot_centres(np.ascontiguousarray(np.vstack(stacked)), offs)
             centres = np.asarray(centres_all, dtype=np.float64).reshape(n_plots, 2)
             n_rows = (n_plots + world - 1) // world
             packed = torch.zeros((n_rows, PACK_WORDS), dtype=torch.int64, device=dev)

@@ -81,6 +81,22 @@ def test_oversized_plot_is_refused_before_any_work():
         icp.run()
 
 
+def test_plot_centres_vectorised_is_bit_identical():
+    """batch.plot_centres reduces plots of equal size together; it must return the bits of the per-plot
+    `rows[:, :2].mean(axis=0)` the oracle (and any reference-side caller) computes - start poses depend on them."""
+    from coregistrationgame_b200.batch import plot_centres
+    rng = np.random.default_rng(1)
+    for ld in (2, 3, 5):
+        sizes = np.r_[rng.integers(1, 40, 30), [63, 64, 65, 127, 128, 129, 150, 150, 150, 255, 256, 257, 500, 512, 513, 1000, 1024]]
+        for same in (False, True):
+            sz = np.full(40, 150) if same else sizes
+            srcs = [rng.normal(size=(int(n), ld)) * 1000 + 6.4e6 for n in sz]
+            src = np.ascontiguousarray(np.vstack(srcs))
+            off = np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
+            want = np.array([a[:, :2].mean(axis=0) for a in srcs])
+            np.testing.assert_array_equal(plot_centres(src, off), want)
+
+
 def test_host_helpers_match_oracle():
     from coregistrationgame_b200 import batch
     np.testing.assert_array_equal(batch.hypothesis_table(16, (0, 1), batch.translation_lattice(3, 2.5)),
