@@ -638,7 +638,7 @@ def run_b200(args):
                 "config": {"workload": name, "plots_per_gpu": args.plots_per_gpu, "plots": n_plots,
                            "icps_per_gpu_per_step": (args.plots_per_gpu if by_plots else args.plots_per_gpu * hyp.shape[0]),
                            "hyp_iterations_per_step": passes_all, "parallelism": (f"plots round-robin over {world} GPU(s)" if by_plots else f"hypotheses round-robin over {world} GPU(s)"),
-                           "exchange": "device-side pack + ONE all_gather of 96 B per plot (dist.exchange_best), inside the timed step",
+                           "exchange": "device-side pack + ONE all_gather of 112 B per plot (dist.exchange_best), inside the timed step",
                            "l2": "flushed between timed steps (256 MB write)", "launch": batch.info,
                            "device": props},
                 "nn_queries_per_s": value * args.trees,

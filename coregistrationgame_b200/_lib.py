@@ -136,6 +136,9 @@ def check(rc, what=""):
     raise FicpError(f"{what}: {msg} (status {rc})")
 
 
+PACK_WORDS = 14   # FICP_PACK_WORDS: 8-byte words per plot record of ficp_batch_pack_best_device / ficp_batch_best
+
+
 def ptr(a):
     """void* of a C-contiguous numpy array (or None)."""
     if a is None:

@@ -61,6 +61,7 @@ void dev_free(void* p, cudaStream_t stream) {
 }
 
 static_assert(sizeof(ficp_hyp_result) == sizeof(HypResult), "ABI struct mismatch");
+static_assert(FICP_PACK_WORDS == kPackWords, "ABI constant mismatch");
 
 // RAII device buffer for the host-buffer convenience calls
 // (allocated and released on the stream the call works on: stream-ordered, so an early error return never frees
@@ -763,8 +764,8 @@ int ficp_batch_copy_best_keys_device(ficp_batch* bh, void* dst_dev, void* stream
 int ficp_batch_pack_best_device(ficp_batch* bh, void* dst_dev, void* stream) {
     if (!bh || !dst_dev) { set_error("ficp_batch_pack_best_device: null pointer"); return kErrInvalid; }
     Batch* b = reinterpret_cast<Batch*>(bh);
-    const int rc = launch_pack_best(b->d_best, b->d_results, b->n_plots, b->n_hyp_local, b->params.hyp_begin, b->params.hyp_stride,
-                                    b->d_stats, reinterpret_cast<unsigned long long*>(dst_dev), (cudaStream_t)stream);
+    const int rc = launch_pack_best(b->d_best, b->d_results, b->d_plots, b->n_plots, b->n_hyp_local, b->params.hyp_begin,
+                                    b->params.hyp_stride, b->d_stats, reinterpret_cast<unsigned long long*>(dst_dev), (cudaStream_t)stream);
     b->used.record((cudaStream_t)stream);
     return rc;
 }
@@ -775,11 +776,11 @@ int ficp_batch_best(ficp_batch* bh, uint64_t* packed_out, uint64_t* stats, void*
     cudaStream_t s = (cudaStream_t)stream;
     DevBuf<unsigned long long> tmp(s);
     int rc;
-    if ((rc = tmp.alloc((size_t)b->n_plots * 12))) return rc;
-    if ((rc = launch_pack_best(b->d_best, b->d_results, b->n_plots, b->n_hyp_local, b->params.hyp_begin, b->params.hyp_stride,
-                               b->d_stats, tmp.p, s)))
+    if ((rc = tmp.alloc((size_t)b->n_plots * kPackWords))) return rc;
+    if ((rc = launch_pack_best(b->d_best, b->d_results, b->d_plots, b->n_plots, b->n_hyp_local, b->params.hyp_begin,
+                               b->params.hyp_stride, b->d_stats, tmp.p, s)))
         return rc;
-    FICP_CUDA(cudaMemcpyAsync(packed_out, tmp.p, sizeof(uint64_t) * 12 * (size_t)b->n_plots, cudaMemcpyDeviceToHost, s));
+    FICP_CUDA(cudaMemcpyAsync(packed_out, tmp.p, sizeof(uint64_t) * kPackWords * (size_t)b->n_plots, cudaMemcpyDeviceToHost, s));
     if (stats) FICP_CUDA(cudaMemcpyAsync(stats, b->d_stats, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, s));
     FICP_CUDA(cudaStreamSynchronize(s));
     return kOk;

@@ -175,7 +175,9 @@ int icp_max_warps(int e);
 size_t icp_smem_bytes(int e, bool z3, int slots, int wcap_pts, int wcap_cells, int wcap_rows);
 int icp_max_ctas_per_sm(int e, bool z3, int warps, bool elastic, size_t smem, int* out);
 int launch_icp(const IcpParams& p, const IcpLaunch& l, cudaStream_t stream);
-int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, int n_plots, int n_hyp_local, int hyp_begin,
-                     int hyp_stride, const unsigned long long* d_stats, unsigned long long* d_dst, cudaStream_t stream);
+constexpr int kPackWords = 14;   // 8-byte words per plot record of the exchange (== FICP_PACK_WORDS of the C ABI)
+int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, const PlotMeta* d_plots, int n_plots,
+                     int n_hyp_local, int hyp_begin, int hyp_stride, const unsigned long long* d_stats,
+                     unsigned long long* d_dst, cudaStream_t stream);
 
 }  // namespace ficp

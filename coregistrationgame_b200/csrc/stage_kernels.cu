@@ -204,39 +204,48 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ a
     if (threadIdx.x == 0) *out = s;
 }
 
-// Per-plot best registration of a finished batch, packed for the multi-GPU exchange (dist.py): 12 words per plot:
+// Per-plot best registration of a finished batch, packed for the multi-GPU exchange (dist.py): kPackWords words per plot:
 // [0] the packed key (fp32 score bits << 32 | hypothesis id), [1..10] the 80-byte result row of that hypothesis,
-// [11] the hypothesis-iterations this GPU ran in the launch.  One all_gather of these records is the whole exchange.
+// [11] the hypothesis-iterations this GPU ran in the launch, [12..13] the translation of the WORLD-frame transform
+// b = c - M centre (final = M p + b), evaluated like batch.compose_world_transforms (elementwise, no FMA) so that a
+// receiver needs no plot centres.  One all_gather of these records is the whole exchange.
 __global__ void __launch_bounds__(256) pack_best_kernel(const unsigned long long* __restrict__ best,
-                                                        const HypResult* __restrict__ results, int n_plots, int n_hyp_local,
-                                                        int hyp_begin, int hyp_stride,
+                                                        const HypResult* __restrict__ results, const PlotMeta* __restrict__ plots,
+                                                        int n_plots, int n_hyp_local, int hyp_begin, int hyp_stride,
                                                         const unsigned long long* __restrict__ stats,
                                                         unsigned long long* __restrict__ dst) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = t / 12, w = t - p * 12;
+    const int p = t / kPackWords, w = t - p * kPackWords;
     if (p >= n_plots) return;
     const unsigned long long key = best[p];
+    long long j = ((long long)(unsigned)(key & 0xFFFFFFFFull) - hyp_begin) / hyp_stride;
+    if (j < 0 || j >= n_hyp_local) j = 0;
+    const HypResult* row = results + (size_t)p * n_hyp_local + j;
     unsigned long long v;
     if (w == 0) {
         v = key;
     } else if (w == 11) {
         v = stats[0];
+    } else if (w >= 12) {
+        const double c0 = plots[p].cinx, c1 = plots[p].ciny;
+        const double bw = (w == 12) ? __dsub_rn(row->cx, __dadd_rn(__dmul_rn(row->m00, c0), __dmul_rn(row->m01, c1)))
+                                    : __dsub_rn(row->cy, __dadd_rn(__dmul_rn(row->m10, c0), __dmul_rn(row->m11, c1)));
+        v = (unsigned long long)__double_as_longlong(bw);
     } else {
-        long long j = ((long long)(unsigned)(key & 0xFFFFFFFFull) - hyp_begin) / hyp_stride;
-        if (j < 0 || j >= n_hyp_local) j = 0;
-        v = reinterpret_cast<const unsigned long long*>(results + (size_t)p * n_hyp_local + j)[w - 1];
+        v = reinterpret_cast<const unsigned long long*>(row)[w - 1];
     }
     dst[t] = v;
 }
 
 }  // namespace
 
-int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, int n_plots, int n_hyp_local, int hyp_begin,
-                     int hyp_stride, const unsigned long long* d_stats, unsigned long long* d_dst, cudaStream_t stream) {
+int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, const PlotMeta* d_plots, int n_plots,
+                     int n_hyp_local, int hyp_begin, int hyp_stride, const unsigned long long* d_stats,
+                     unsigned long long* d_dst, cudaStream_t stream) {
     static_assert(sizeof(HypResult) == 80, "pack_best_kernel copies ten 8-byte words per row");
     if (n_plots <= 0) return kOk;
-    const int n = n_plots * 12;
-    pack_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_best, d_results, n_plots, n_hyp_local, hyp_begin, hyp_stride, d_stats, d_dst);
+    const int n = n_plots * kPackWords;
+    pack_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_best, d_results, d_plots, n_plots, n_hyp_local, hyp_begin, hyp_stride, d_stats, d_dst);
     FICP_CUDA(cudaGetLastError());
     return kOk;
 }

@@ -7,7 +7,7 @@ for 1e7 points) and runs the persistent kernel on its share with no data-path co
 
 The exchange is ONE collective on device memory: every rank packs, per plot, its best key
 ``(fp32 score bits << 32) | hypothesis id``, the 80-byte result row of that hypothesis and its pass
-count (``ficp_batch_pack_best_device``, 96 bytes per plot) and the records are all-gathered; the
+count (``ficp_batch_pack_best_device``, 112 bytes per plot) and the records are all-gathered; the
 winner of a plot is the record with the smallest key (ties in score resolve to the lowest
 hypothesis id, exactly like the single-GPU ``atomicMin``).  Nothing is read back to the host before
 the exchange; the result leaves the device once, as ``world x n_plots x 96`` bytes.  The payload
@@ -19,9 +19,9 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .batch import IcpBatch, TargetIndex, compose_world_transforms, decode_best_keys, plot_centres
+from .batch import IcpBatch, TargetIndex, decode_best_keys, world_transforms
 
-PACK_WORDS = 12          # int64 words per plot record: key, 10 words of ficp_hyp_result, passes of the rank
+PACK_WORDS = _lib.PACK_WORDS   # int64 words per plot record: key, 10 words of ficp_hyp_result, passes of the rank, world-frame translation (2)
 
 
 def shard_of(rank, world):
@@ -78,7 +78,7 @@ def select_best(gathered, by_plots=False, n_plots=None):
         sel = g[win, np.arange(n_rows)]
     best_key = sel[:, 0].astype(np.uint64)
     rows = np.ascontiguousarray(sel[:, 1:11]).view(_lib.HYP_RESULT_DTYPE).reshape(-1)
-    return best_key, rows, passes
+    return best_key, rows, passes, np.ascontiguousarray(sel[:, 12:14]).view(np.float64)
 
 
 def register_batch_distributed(sources, target, hyp_table, index=None, group=None, device=None, **kw):
@@ -105,20 +105,15 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
         if not by_plots:
             # ---- shard the hypotheses of every plot; winner = smallest key among the gathered records
             batch = IcpBatch(index, sources, hyp_table, hyp_shard=shard_of(rank, world), **kw)
-            centres = batch.centres
             packed = torch.empty((n_plots, PACK_WORDS), dtype=torch.int64, device=dev)
         else:
             # ---- fewer hypotheses than ranks (e.g. one start pose per plot): shard the PLOTS, gather the rows
             mine = plot_shard(n_plots, rank, world)
             centres_all = kw.pop("centres", None)
-            if centres_all is None:     # every rank composes the world transforms of ALL plots: centres of all of them
-                stacked = [np.asarray(s, dtype=np.float64) for s in sources]
-                offs = np.concatenate([[0], np.cumsum([a.shape[0] for a in stacked])]).astype(np.int64)
-                centres_all = plot_centres(np.ascontiguousarray(np.vstack(stacked)), offs)
-            centres = np.asarray(centres_all, dtype=np.float64).reshape(n_plots, 2)
+            centres_mine = None if centres_all is None else np.asarray(centres_all, dtype=np.float64).reshape(n_plots, 2)[mine]
             n_rows = (n_plots + world - 1) // world
             packed = torch.zeros((n_rows, PACK_WORDS), dtype=torch.int64, device=dev)
-            batch = IcpBatch(index, [sources[p] for p in mine], hyp_table, centres=centres[mine], **kw) if len(mine) else None
+            batch = IcpBatch(index, [sources[p] for p in mine], hyp_table, centres=centres_mine, **kw) if len(mine) else None
         try:
             if batch is not None:
                 batch.run(stream)
@@ -127,15 +122,15 @@ def register_batch_distributed(sources, target, hyp_table, index=None, group=Non
             else:
                 gathered = gather_packed(packed, group)
                 h2d = 0
-            g = gathered.cpu().numpy()                       # the one read-back: world x rows x 96 bytes
+            g = gathered.cpu().numpy()                       # the one read-back: world x rows x 112 bytes
         finally:
             if batch is not None:
                 batch.close()
-        gk, rows, passes = select_best(g, by_plots=by_plots, n_plots=n_plots)
+        gk, rows, passes, b = select_best(g, by_plots=by_plots, n_plots=n_plots)
         res = decode_best_keys(gk)
         res["best_key"] = gk
         res["best_row"] = rows
-        res["best_transform"] = compose_world_transforms(rows, centres)
+        res["best_transform"] = world_transforms(rows, b)
         res["k"] = rows["k"].astype(np.int64)
         res["rmse"], res["frmsd"] = rows["rmse"].copy(), rows["frmsd"].copy()
         res["passes_local"] = int(passes[rank])

@@ -189,13 +189,15 @@ FICP_API int ficp_batch_results(ficp_batch* b, ficp_hyp_result* results, uint64_
 /* device-to-device copy of the per-plot best keys into caller memory (e.g. a torch tensor that is then
  * all-reduced with MIN over NCCL). */
 FICP_API int ficp_batch_copy_best_keys_device(ficp_batch* b, void* dst_dev, void* stream);
-/* enqueue only: packs this GPU's best registration per plot into caller DEVICE memory, 12 x 8 bytes per plot:
+/* enqueue only: packs this GPU's best registration per plot into caller DEVICE memory, FICP_PACK_WORDS x 8 bytes per plot:
  * word 0 the packed key, words 1..10 the ficp_hyp_result row (80 bytes) of that hypothesis, word 11 the
- * hypothesis-iterations this GPU ran.  One NCCL all_gather of these records is the whole multi-GPU exchange
+ * hypothesis-iterations this GPU ran, words 12..13 the translation b of the world-frame transform final = M p + b
+ * (b = c - M centre, doubles).  One NCCL all_gather of these records is the whole multi-GPU exchange
  * (coregistrationgame_b200/dist.py); the winner per plot is the record with the smallest key. */
+#define FICP_PACK_WORDS 14
 FICP_API int ficp_batch_pack_best_device(ficp_batch* b, void* dst_dev, void* stream);
-/* waits for `stream` and returns ONLY the best registration per plot (host buffers): packed_out[n_plots * 12] in the layout
- * of ficp_batch_pack_best_device (key, 80-byte result row, hypothesis-iterations), stats[8] as in ficp_batch_results.
+/* waits for `stream` and returns ONLY the best registration per plot (host buffers): packed_out[n_plots * FICP_PACK_WORDS]
+ * in the layout of ficp_batch_pack_best_device, stats[8] as in ficp_batch_results.
  * The per-hypothesis table (80 B x plots x hypotheses) stays on the device: what app.py:658-661 needs is the winner. */
 FICP_API int ficp_batch_best(ficp_batch* b, uint64_t* packed_out, uint64_t* stats, void* stream);
 /* per-pass trace of a batch created with trace_passes > 0 (waits for `stream`).  For ICP c = plot * n_hyp_local + j and

@@ -52,7 +52,7 @@ def _worker(rank, world, port, n_plots, n_hyp, q):
         ks = np.array([orc.pack_best_key(score[p, h], h) for h in mine], dtype=np.uint64)
         keys[p] = np.int64(ks.min())
     g = gather_packed(torch.from_numpy(_pack(keys, rank, n_plots, 1000 + rank)))       # the ONE collective of the path
-    gk, rows, passes = select_best(g.numpy())
+    gk, rows, passes, _b = select_best(g.numpy())
     q.put((rank, gk.copy(), rows.copy(), passes.copy(), score))
     dist.barrier()
     dist.destroy_process_group()
@@ -93,7 +93,7 @@ def _gather_worker(rank, world, port, n_plots, q):
     n_rows = (n_plots + world - 1) // world
     packed = np.zeros((n_rows, PACK_WORDS), dtype=np.int64)
     packed[:len(mine)] = _pack(np.array([orc.pack_best_key(0.5 + p, 0) for p in mine], dtype=np.uint64).astype(np.int64), rank, len(mine), 50 + rank)
-    gk, rows, passes = select_best(gather_packed(torch.from_numpy(packed)).numpy(), by_plots=True, n_plots=n_plots)
+    gk, rows, passes, _b = select_best(gather_packed(torch.from_numpy(packed)).numpy(), by_plots=True, n_plots=n_plots)
     q.put((rank, gk.copy(), rows.copy(), passes.copy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -131,8 +131,9 @@ def test_single_process_passthrough():
     from coregistrationgame_b200.dist import gather_packed, select_best
     keys = np.array([orc.pack_best_key(0.25, 3), orc.pack_best_key(1.5, 0)], dtype=np.uint64).astype(np.int64)
     g = gather_packed(torch.from_numpy(_pack(keys, 0, 2, 9)))
-    assert tuple(g.shape) == (1, 2, 12)
-    gk, rows, passes = select_best(g.numpy())
+    from coregistrationgame_b200.dist import PACK_WORDS
+    assert tuple(g.shape) == (1, 2, PACK_WORDS)
+    gk, rows, passes, _b = select_best(g.numpy())
     np.testing.assert_array_equal(gk.astype(np.int64), keys)
     np.testing.assert_array_equal(rows["cx"], [3, 0])
     assert passes.tolist() == [9]

@@ -580,3 +580,17 @@ def test_randomised_parity_soak(gpu):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "15", "11"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "0 mismatching cases" in out.stdout
+
+
+def test_packed_world_translation_matches_host_composition(gpu):
+    """The winners' records carry the world-frame translation b = c - M centre, evaluated on the device in the arithmetic
+    of batch.compose_world_transforms: the two routes (winners only / per-hypothesis table) return identical transforms."""
+    from coregistrationgame_b200 import register_batch
+    tgt, plots, _ = orc.synthetic_scene(40000, 120, seed=17, dims=3, n_plots=6, hidden_pose=True)
+    tgt = tgt + [420000.0, 6483000.0, 0.0]
+    plots = [p + [420000.0, 6483000.0, 0.0] for p in plots]
+    hyp = orc.hypothesis_table(8, flips=(0, 1), translations=orc.translation_lattice(2, 2.5))
+    a = register_batch(plots, tgt, hyp, per_hypothesis=False)
+    b = register_batch(plots, tgt, hyp, per_hypothesis=True)
+    np.testing.assert_array_equal(a["best_key"], b["best_key"])
+    np.testing.assert_array_equal(a["best_transform"], b["best_transform"])
