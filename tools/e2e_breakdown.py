@@ -57,5 +57,48 @@ if rank == 0:
     print(json.dumps({"world": world, "plots": n_plots, "build_ms_device": index.info()["build_ms"] if False else None,
                       "ms_mean_over_ranks": dict(zip(names, rows.mean(0).round(3).tolist())),
                       "ms_max_over_ranks": dict(zip(names, rows.max(0).round(3).tolist()))}))
-if world > 1:
-    dist.destroy_process_group()
+
+# ---- part 2: the public call itself, as bench.py's e2e leg drives it (no synchronisation between the parts), with wall-clock
+# timers around its pieces: where does a step of register_batch_distributed go when the ranks run free?
+if os.environ.get("FICP_E2E_PART2", "1") == "1":
+    import coregistrationgame_b200.dist as D
+    import coregistrationgame_b200.batch as B
+    if world > 1:
+        pass
+    T = {"index_create": 0.0, "index_close": 0.0, "batch_create": 0.0, "batch_close": 0.0, "run_enqueue": 0.0, "exchange+cpu": 0.0}
+    def wrap(cls, name, key):
+        orig = getattr(cls, name)
+        def f(*a, **k):
+            t0 = time.perf_counter(); r = orig(*a, **k); T[key] += time.perf_counter() - t0; return r
+        setattr(cls, name, f)
+    wrap(B.TargetIndex, "__init__", "index_create"); wrap(B.TargetIndex, "close", "index_close")
+    wrap(B.IcpBatch, "__init__", "batch_create"); wrap(B.IcpBatch, "close", "batch_close"); wrap(B.IcpBatch, "run", "run_enqueue")
+    orig_ex = D.exchange_best
+    def ex(*a, **k):
+        t0 = time.perf_counter(); r = orig_ex(*a, **k).cpu(); T["exchange+cpu"] += time.perf_counter() - t0; return r
+    D.exchange_best = ex
+    for mode in ("free", "sync_each_step"):
+        for k in T: T[k] = 0.0
+        D.register_batch_distributed(h_plots, h_tgt, h_hyp) if world > 1 else B.register_batch(h_plots, h_tgt, h_hyp, per_hypothesis=False)
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        for k in T: T[k] = 0.0
+        t0 = time.perf_counter()
+        for _ in range(5):
+            D.register_batch_distributed(h_plots, h_tgt, h_hyp) if world > 1 else B.register_batch(h_plots, h_tgt, h_hyp, per_hypothesis=False)
+            if mode == "sync_each_step":
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        tot = (time.perf_counter() - t0) / 5 * 1e3
+        v = torch.tensor([tot] + [T[k] / 5 * 1e3 for k in T], dtype=torch.float64, device=dev)
+        if world > 1:
+            allv = [torch.empty_like(v) for _ in range(world)]; dist.all_gather(allv, v)
+        else:
+            allv = [v]
+        if rank == 0:
+            rows = np.array([a.cpu().numpy() for a in allv])
+            print(json.dumps({"world": world, "mode": mode, "ms_per_step_max": round(float(rows[:, 0].max()), 3),
+                              "mean_over_ranks": dict(zip(["step"] + list(T), rows.mean(0).round(3).tolist())),
+                              "max_over_ranks": dict(zip(["step"] + list(T), rows.max(0).round(3).tolist()))}))
+    if world > 1:
+        dist.destroy_process_group()
