@@ -404,6 +404,19 @@ __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const doubl
     for (int r = 0; r < E; ++r) dd[r] = sd2[key[r] & C::kIdxMask];
 
     // ---- exact fix-up: points whose quantised codes collide are re-ordered by the true (d2, index) ----
+    // The code is a monotone function of d2, so the sorted keys are already in exact order wherever neighbouring codes
+    // differ; only runs of EQUAL codes can be out of order.  Most passes have none: one integer compare per neighbour pair
+    // decides, and the fix-up (5 KB of straight-line fp64 compare-exchanges - instruction fetch is this kernel's top
+    // stall) is skipped.
+    bool collide = false;
+#pragma unroll
+    for (int r = 0; r + 1 < E; ++r)      // (padding slots all carry the key 0xFFFFFFFF: not a collision)
+        collide = collide || (((key[r] ^ key[r + 1]) >> C::kIdxBits) == 0u && key[r + 1] != 0xFFFFFFFFu);
+    {
+        const unsigned nk0 = __shfl_down_sync(kFull, key[0], 1);
+        collide = collide || (lane < 31 && ((key[E - 1] ^ nk0) >> C::kIdxBits) == 0u && nk0 != 0xFFFFFFFFu);
+    }
+    if (__any_sync(kFull, collide))
     for (;;) {
         bool sw = false;
 #pragma unroll
@@ -474,7 +487,8 @@ __device__ __forceinline__ PassOut icp_trim_phase(const PlotCtx& pc, const doubl
 #pragma unroll
         for (int r = 0; r < E; ++r) {
             const int p = lane * E + r;
-            if (p < n) gbest = fmin(gbest, s[r] * s_g[r * 32 + lane]);
+            const double gr = s[r] * s_g[r * 32 + lane];
+            if (p < n && gr < gbest) gbest = gr;     // no NaN handling needed: a NaN (0 * inf of a padded slot) never wins
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gbest = fmin(gbest, __shfl_xor_sync(kFull, gbest, o));
