@@ -594,3 +594,28 @@ def test_packed_world_translation_matches_host_composition(gpu):
     b = register_batch(plots, tgt, hyp, per_hypothesis=True)
     np.testing.assert_array_equal(a["best_key"], b["best_key"])
     np.testing.assert_array_equal(a["best_transform"], b["best_transform"])
+
+
+def test_planner_picks_the_kernel_shape_by_batch_size(gpu):
+    """Auto launch shape (capi.cu): CTA-per-ICP below 8 ICPs per SM (12 when every plot has one start pose: the
+    warp-per-ICP kernel would run one warp per CTA), warp-per-ICP above; plots of <= 32 trees are one warp either way."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex, _lib
+    sms = _lib.device_props()["sms"]
+    tgt, plots, _ = orc.synthetic_scene(60000, 40, seed=5, dims=3, n_plots=13 * sms + 7, hidden_pose=False)
+    ti = TargetIndex(tgt)
+    ident = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
+    hyp = orc.hypothesis_table(8, flips=(0, 1))
+    cases = [(plots[:11 * sms], ident, 1), (plots, ident, 0), (plots[:sms // 4], hyp, 1), (plots[:sms], hyp, 0)]
+    rows = []
+    for ps, h, want in cases:
+        b = IcpBatch(ti, ps, h, min_k=0)
+        assert b.info["cta_per_icp"] == want, (len(ps), h.shape[0], b.info)
+        rows.append(b.run().results())
+        b.close()
+    # the same plots give the same rows whichever kernel the planner picked
+    n0 = 11 * sms
+    assert _rows_equal_except_flags(rows[0]["hyp"], rows[1]["hyp"][:n0])
+    small = IcpBatch(ti, [p[:30] for p in plots[:5]], hyp, min_k=0)
+    assert small.info["cta_per_icp"] == 0 and small.info["elems_per_lane"] == 1
+    small.close()
+    ti.close()
