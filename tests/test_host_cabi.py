@@ -4,6 +4,7 @@ No compute call is made here (there is no GPU in the build container and no CPU 
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -136,3 +137,12 @@ def test_nn_search_host_check(tmp_path, flags):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-2000:]
     assert "mismatches=0" in out.stdout
+
+
+def test_bench_cli_parses_without_a_gpu():
+    """`bench.py --help` must render (a stray '%' in a help string once broke argparse) and `--impl reference` must be
+    importable on a box without CUDA (the reference arm never touches the GPU)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-800:]
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload"):
+        assert flag in out.stdout
