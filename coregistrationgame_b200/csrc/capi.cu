@@ -567,7 +567,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // per-ICP state (distances, neighbours, search list, trim order, slack: 18 B per tree) must leave room for a window
     while (!cta_mode && slots_per_cta > 1 && icp_smem_bytes(e, z3, slots_per_cta, 0, 0, wcap_rows) + 16384 > (size_t)smem_optin) --slots_per_cta;
     warps = slots_per_cta * team;
-    if (cta_mode) { warps = e; team = e; slots_per_cta = 1; }
+    if (cta_mode) { warps = icp_team_threads(e) / 32; team = warps; slots_per_cta = 1; }
     auto smem_of = [&](int wp, int wc) -> size_t {
         return cta_mode ? icp_team_smem_bytes(e, z3, wp, wc, wcap_rows) : icp_smem_bytes(e, z3, slots_per_cta, wp, wc, wcap_rows);
     };
@@ -584,7 +584,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     };
     // a window with a modest margin (one ring of cells + a few metres of drift) must fit for the worst plot
     int want_ctas_per_sm = prm->ctas_per_sm > 0 ? prm->ctas_per_sm
-                           : cta_mode ? std::max(1, std::min(16, 32 / warps))   // 64 registers per thread: 1024 threads per SM
+                           : cta_mode ? std::max(1, std::min(16, 32 / e))       // as many CTAs as the kernel's register budget allows (occupancy query below)
                                       : std::max(1, std::min(8, 16 / warps));
     if (prm->ctas_per_sm <= 0) {  // fewer resident CTAs when that is what it takes for the windows to fit on-chip
         auto modest_fits = [&](int ctas) -> bool {

@@ -170,6 +170,7 @@ struct IcpLaunch {
 // CTA-per-ICP kernel (icp_team.cu): T = 32 e threads work on one ICP
 size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows);
 int icp_team_max_ctas_per_sm(int e, bool z3, size_t smem, int* out);
+int icp_team_threads(int e);   // threads of its CTA for plots of 32 e tree slots (one or two trees per thread)
 int launch_icp_team(const IcpParams& p, int e, bool z3, int ctas, size_t smem, cudaStream_t stream);
 int icp_max_warps(int e);
 size_t icp_smem_bytes(int e, bool z3, int slots, int wcap_pts, int wcap_cells, int wcap_rows);

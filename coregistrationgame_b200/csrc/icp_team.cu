@@ -52,7 +52,7 @@ struct TeamLayout {
     size_t s_u, s_z, s_g, sd2, snn, ssl, list, dlist, slist, sidx, kbuf, sdd, tmp, misc, rowoff, rowdelta, rowg, w_xy, w_z, w_cell, total;
 };
 __host__ __device__ constexpr size_t team_up16(size_t b) { return (b + 15) & ~size_t(15); }
-__host__ __device__ inline TeamLayout team_layout(int t, bool z3, int wcap_pts, int wcap_cells) {
+__host__ __device__ inline TeamLayout team_layout(int t /* tree slots = 32 e */, bool z3, int wcap_pts, int wcap_cells) {
     TeamLayout L{};
     size_t o = 0;
     L.s_u = o; o += team_up16((size_t)t * 16);
@@ -96,31 +96,53 @@ struct TeamMisc {
 };
 static_assert(sizeof(TeamMisc) <= 1792, "TeamMisc must fit its reservation");
 
-// Block bitonic sort, one 32-bit key per thread, ascending in thread order.  Strides below 32 exchange through
+// Block bitonic sort of NP = T * TPT 32-bit keys (TPT per thread), ascending in position order.  Strides below 32 exchange through
 // shuffles; larger strides through two alternating shared-memory buffers (one barrier per step).  Fully unrolled:
 // directions and buffers are compile-time, a step is shuffle + predicated min/max.
-template <int T>
-__device__ __forceinline__ unsigned block_sort32(unsigned key, unsigned* buf, int tid) {
+template <int T, int TPT>
+__device__ __forceinline__ void block_sort32(unsigned (&key)[TPT], unsigned* buf, int tid) {
+    // element p = tid + kk * T lives in key[kk] of thread tid; strides >= T pair two slots of the same thread
+    constexpr int NP = T * TPT;
     int flip = 0;
 #pragma unroll
-    for (int k = 2; k <= T; k <<= 1) {
+    for (int k = 2; k <= NP; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            unsigned other;
-            if (j >= 32) {
-                unsigned* b = buf + flip * T;
-                b[tid] = key;
+            if (j >= T) {
+                const int dj = j / T;
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) {
+                    if ((kk & dj) == 0) {
+                        const bool asc = (((tid + kk * T) & k) == 0);   // (p & NP) == 0: the last phase ascends
+                        const unsigned lo = min(key[kk], key[kk | dj]), hi = max(key[kk], key[kk | dj]);
+                        key[kk] = asc ? lo : hi;
+                        key[kk | dj] = asc ? hi : lo;
+                    }
+                }
+            } else if (j >= 32) {
+                unsigned* b = buf + flip * NP;
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) b[tid + kk * T] = key[kk];
                 __syncthreads();
-                other = b[tid ^ j];
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) {
+                    const int p = tid + kk * T;
+                    const unsigned other = b[p ^ j];
+                    const bool takemin = (((p & j) == 0) == ((p & k) == 0));
+                    key[kk] = takemin ? min(key[kk], other) : max(key[kk], other);
+                }
                 flip ^= 1;
             } else {
-                other = __shfl_xor_sync(kFull, key, j);
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) {
+                    const int p = tid + kk * T;
+                    const unsigned other = __shfl_xor_sync(kFull, key[kk], j);
+                    const bool takemin = (((p & j) == 0) == ((p & k) == 0));
+                    key[kk] = takemin ? min(key[kk], other) : max(key[kk], other);
+                }
             }
-            const bool takemin = (((tid & j) == 0) == ((tid & k) == 0));   // (tid & T) == 0: the last phase ascends
-            key = takemin ? min(key, other) : max(key, other);
         }
     }
-    return key;
 }
 
 // Odd-even transposition rounds on the (d2, tree index) pairs in trim order until a round swaps nothing (-> true) or
@@ -134,18 +156,23 @@ __device__ __forceinline__ unsigned block_sort32(unsigned key, unsigned* buf, in
 #endif
 constexpr int kRepairMaxInversions = FICP_REPAIR_INV;   // adjacent inversions above which the order is rebuilt by the block sort
 constexpr int kRepairMaxRounds = FICP_REPAIR_ROUNDS;
-template <int T, int E>
+template <int T, int TPT, int E>
 __device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* sidx, int tid, int max_rounds) {
+    constexpr int NP = T * TPT;
     for (int round = 0; round < max_rounds; ++round) {
         bool sw = false;
 #pragma unroll 1
         for (int par = 0; par < 2; ++par) {
-            if ((tid & 1) == par && tid + 1 < T) {
-                const double a = sdd[PAD(tid)], b = sdd[PAD(tid + 1)];
-                const unsigned short ia = sidx[tid], ib = sidx[tid + 1];
-                if (key_greater(a, ia, b, ib)) {
-                    sdd[PAD(tid)] = b; sdd[PAD(tid + 1)] = a; sidx[tid] = ib; sidx[tid + 1] = ia;
-                    sw = true;
+#pragma unroll
+            for (int kk = 0; kk < TPT; ++kk) {
+                const int p = tid + kk * T;
+                if ((p & 1) == par && p + 1 < NP) {
+                    const double a = sdd[PAD(p)], b = sdd[PAD(p + 1)];
+                    const unsigned short ia = sidx[p], ib = sidx[p + 1];
+                    if (key_greater(a, ia, b, ib)) {
+                        sdd[PAD(p)] = b; sdd[PAD(p + 1)] = a; sidx[p] = ib; sidx[p + 1] = ia;
+                        sw = true;
+                    }
                 }
             }
             __syncthreads();
@@ -175,18 +202,23 @@ __device__ __forceinline__ double warp_min_of(const double* red, int nw, int lan
     return v;
 }
 
-#ifndef FICP_TEAM_REGS
-#define FICP_TEAM_REGS 64      // registers per thread the kernel is compiled for: 1024 threads resident per SM
+// T threads work on one ICP of NP = T * TPT tree slots (TPT trees per thread: slot tid + kk * T).  TPT = 1 is the
+// original shape (one tree per thread, 64 registers); TPT = 2 halves the threads of the two big size classes, so that
+// the kernel can be compiled for 128 registers (no spills: 17.7 k instead of 28 k cycles per pass) and
+// still keep two CTAs of the 512-slot class on an SM.
+#ifndef FICP_TEAM_TPT
+#define FICP_TEAM_TPT 2        // trees per thread for the size classes of 512 and 1024 slots
 #endif
-template <bool Z3, int T>
-__global__ void __launch_bounds__(T, (65536 / FICP_TEAM_REGS / T) > 0 ? (65536 / FICP_TEAM_REGS / T) : 1)
+template <bool Z3, int T, int TPT>
+__global__ void __launch_bounds__(T, (65536 / (TPT == 1 ? 64 : 128) / T) > 0 ? (65536 / (TPT == 1 ? 64 : 128) / T) : 1)
 icp_team_kernel(const __grid_constant__ IcpParams P) {
-    constexpr int E = T / 32;
+    constexpr int NP = T * TPT;        // tree slots (NPAD of the launch)
+    constexpr int E = NP / 32;         // elements per lane in the canonical (one-warp) association
     constexpr int NW = T / 32;
-    constexpr int IB = (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;   // bits of a tree index
+    constexpr int IB = (NP == 64) ? 6 : (NP == 128) ? 7 : (NP == 256) ? 8 : (NP == 512) ? 9 : 10;   // bits of a tree index
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TeamLayout L = team_layout(T, Z3, P.wcap_pts, P.wcap_cells);
+    const TeamLayout L = team_layout(NP, Z3, P.wcap_pts, P.wcap_cells);
     double2* s_u = reinterpret_cast<double2*>(smem + L.s_u);
     double* s_z = reinterpret_cast<double*>(smem + L.s_z);
     double* s_g = reinterpret_cast<double*>(smem + L.s_g);
@@ -206,7 +238,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     unsigned* kbuf = reinterpret_cast<unsigned*>(smem + L.kbuf);
     double* sdd = reinterpret_cast<double*>(smem + L.sdd);
     double* f_ux = reinterpret_cast<double*>(smem + L.kbuf);          // fit terms alias the (dead) sort buffers
-    double* f_uy = reinterpret_cast<double*>(smem + L.kbuf) + T;
+    double* f_uy = reinterpret_cast<double*>(smem + L.kbuf) + NP;
     double* f_vx = reinterpret_cast<double*>(smem + L.sdd);
     double* f_vy = reinterpret_cast<double*>(smem + L.tmp);
     double* spart = reinterpret_cast<double*>(smem + L.tmp);
@@ -233,10 +265,12 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
 
         if (plot != staged_plot) {
             // ---- stage the plot: source rows, weight tables, window of grid cells (as in icp_persistent.cu) ----
-            s_u[tid] = (tid < pm.n) ? P.src_u[pm.off + tid] : make_double2(0.0, 0.0);
-            if (Z3) s_z[tid] = (tid < pm.n) ? P.src_z[pm.off + tid] : 0.0;
-            const double* tab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;
-            for (int i = tid; i < P.n_stages * T; i += T) s_g[i] = tab[(size_t)(i / T) * 2 * T + (i % T)];
+            for (int i = tid; i < NP; i += T) {
+                s_u[i] = (i < pm.n) ? P.src_u[pm.off + i] : make_double2(0.0, 0.0);
+                if (Z3) s_z[i] = (i < pm.n) ? P.src_z[pm.off + i] : 0.0;
+            }
+            const double* tab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NP;
+            for (int i = tid; i < P.n_stages * NP; i += T) s_g[i] = tab[(size_t)(i / NP) * 2 * NP + (i % NP)];
             const int ww = pm.wx1 - pm.wx0, wh = pm.wy1 - pm.wy0;
             bool ok = (ww > 0 && wh > 0 && (long long)ww * wh <= P.wcap_cells && wh <= P.wcap_rows && G_.m > 0);
             if (ok) {
@@ -285,7 +319,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
         }
         const bool win_ok = (M->win_ok != 0);
         const int fixed_k = pm.fixed_k;
-        const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * T;  // [stage][0]=g [stage][1]=c
+        const double* g_ctab = P.tabs + (size_t)pm.tab * P.n_stages * 2 * NP;  // [stage][0]=g [stage][1]=c
         const int n = pm.n;
 
         // ---- one ICP: start pose of hypothesis h (the expression of icp_persistent.cu / oracle.pre_transform)
@@ -304,16 +338,18 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             M->cnt[0] = M->cnt[1] = M->cnt[2] = M->cnt[3] = 0u;
         }
         int passes = 0;
-        if (tid >= n) { sd2[tid] = kInf; snn[tid] = -1; }   // padding never changes
-        sidx[tid] = (unsigned short)tid;                     // no previous trim order yet
+#pragma unroll
+        for (int kk = 0; kk < TPT; ++kk) {
+            const int i = tid + kk * T;
+            if (i >= n) { sd2[i] = kInf; snn[i] = -1; }   // padding never changes
+            sidx[i] = (unsigned short)i;                  // no previous trim order yet
+        }
         PassOut po{0, kInf, 0.0, -1.0, -1};
-        // position of this thread in trim order: chunk (= lane of the one-warp kernel) and element inside it
-        const int lp = tid / E, r = tid - lp * E;
         PHASE(0);
 
         for (int st = 0; st < P.n_stages; ++st) {
-            const double* sg = s_g + (size_t)st * T;
-            const double* gc = g_ctab + ((size_t)st * 2 + 1) * T;
+            const double* sg = s_g + (size_t)st * NP;
+            const double* gc = g_ctab + ((size_t)st * 2 + 1) * NP;
             double cur = 0.0;
             int it = 0;
             bool first = true;
@@ -325,15 +361,20 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 if (have_prev) {
                     const WindowAcc Wt = team_window(tp, M->win, G_);
                     const PlotCtx pct{s_u, s_z, n, fixed_k, 0.0, 0.0};
-                    const int need = nn_test_round<Z3>(Wt, pct, ld_pose(M->pose[pb]), ld_pose(M->pose[pb] + 6), sd2, snn, ssl, warp, lane);
+                    const Pose pose_t = ld_pose(M->pose[pb]), dpose_t = ld_pose(M->pose[pb] + 6);
+#pragma unroll 1
+                    for (int e = warp; e < E; e += NW) {
+                        const int need = nn_test_round<Z3>(Wt, pct, pose_t, dpose_t, sd2, snn, ssl, e, lane);
+                        const unsigned m = __ballot_sync(kFull, need >= 0);
+                        int base = 0;
+                        if (lane == 0 && m) base = atomicAdd(&M->nlist, __popc(m));
+                        base = __shfl_sync(kFull, base, 0);
+                        if (need >= 0) list[base + __popc(m & lt_mask)] = (unsigned short)need;
+                    }
                     PHASE(14);
-                    const unsigned m = __ballot_sync(kFull, need >= 0);
-                    int base = 0;
-                    if (lane == 0 && m) base = atomicAdd(&M->nlist, __popc(m));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (need >= 0) list[base + __popc(m & lt_mask)] = (unsigned short)need;
                 } else {
-                    list[tid] = (unsigned short)tid;
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) list[tid + kk * T] = (unsigned short)(tid + kk * T);
                 }
                 __syncthreads();
                 PHASE(1);
@@ -345,14 +386,15 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 int G = 1;
                 if (win_ok) while (G < 16 && n_list * G * 2 <= T) G <<= 1;
                 if (G == 1) {
-                    const int defer = (warp * 32 < n_list)
-                                          ? nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, list, warp, n_list, lane, have_prev)
-                                          : -1;
-                    const unsigned m = __ballot_sync(kFull, defer >= 0);
-                    int base = 0;
-                    if (lane == 0 && m) base = atomicAdd(&M->ndef, __popc(m));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (defer >= 0) dlist[base + __popc(m & lt_mask)] = (unsigned short)defer;
+#pragma unroll 1
+                    for (int e = warp; e * 32 < n_list; e += NW) {
+                        const int defer = nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, list, e, n_list, lane, have_prev);
+                        const unsigned m = __ballot_sync(kFull, defer >= 0);
+                        int base = 0;
+                        if (lane == 0 && m) base = atomicAdd(&M->ndef, __popc(m));
+                        base = __shfl_sync(kFull, base, 0);
+                        if (defer >= 0) dlist[base + __popc(m & lt_mask)] = (unsigned short)defer;
+                    }
                 } else {
                     const int slot = tid / G, sub = tid - slot * G;     // G divides 32: a group never straddles warps
                     const bool active = slot < n_list;
@@ -392,10 +434,10 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     if (ser >= 0) slist[base + __popc(m & lt_mask)] = (unsigned short)ser;
                     __syncthreads();
                     const int n_ser = M->nser;
-                    if (n_ser > 0) {    // possible exact ties: the one-lane search applies the lowest-original-index rule
-                        const int d2nd = (warp * 32 < n_ser)
-                                             ? nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, slist, warp, n_ser, lane, have_prev)
-                                             : -1;
+                    // possible exact ties: the one-lane search applies the lowest-original-index rule
+#pragma unroll 1
+                    for (int e = warp; e * 32 < n_ser; e += NW) {
+                        const int d2nd = nn_round<Z3, false>(G_, W, win_ok, pc, pose, sd2, snn, ssl, slist, e, n_ser, lane, have_prev);
                         const unsigned m2 = __ballot_sync(kFull, d2nd >= 0);
                         int b2 = 0;
                         if (lane == 0 && m2) b2 = atomicAdd(&M->ndef, __popc(m2));
@@ -418,38 +460,65 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 // the PREVIOUS pass's order is tried first: verified against the new distances, repaired by a few
                 // odd-even transposition rounds when only a handful of neighbours swapped, and only otherwise rebuilt by
                 // the block sort.  The order is a total order, so every route ends in the same permutation.
-                const double my_d2 = sd2[tid];
-                int sidx_t = sidx[tid];
-                double dd = sd2[sidx_t];
-                sdd[PAD(tid)] = dd;
+                // Thread tid owns tree slots AND trim-order positions tid + kk * T.
+                double my_d2[TPT], dd[TPT];
+                int sidx_t[TPT];
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) {
+                    const int p = tid + kk * T;
+                    my_d2[kk] = sd2[p];
+                    sidx_t[kk] = sidx[p];
+                    dd[kk] = sd2[sidx_t[kk]];
+                    sdd[PAD(p)] = dd[kk];
+                }
                 __syncthreads();
                 bool sorted;
                 {
-                    bool inv = false;
-                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[PAD(tid + 1)], (unsigned)sidx[tid + 1]);
-                    const int ninv = __syncthreads_count(inv);
+                    int ninv = 0;
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int p = tid + kk * T;
+                        bool inv = false;
+                        if (p + 1 < NP) inv = key_greater(dd[kk], (unsigned)sidx_t[kk], sdd[PAD(p + 1)], (unsigned)sidx[p + 1]);
+                        ninv += __syncthreads_count(inv);
+                    }
                     sorted = (ninv == 0);
-                    if (!sorted && ninv <= kRepairMaxInversions) sorted = team_repair_order<T, E>(sdd, sidx, tid, kRepairMaxRounds);
+                    if (!sorted && ninv <= kRepairMaxInversions) sorted = team_repair_order<T, TPT, E>(sdd, sidx, tid, kRepairMaxRounds);
                 }
                 PHASE(4);
                 if (!sorted) {
                     if (tid == 0) ++M->cnt[3];
                     // packed key: monotone (32 - IB)-bit code of d2 (float bits, rounded down) | tree index; the exact
                     // order is verified afterwards and repaired where quantised codes collide
-                    const unsigned fb = __float_as_uint(__double2float_rd(my_d2));
-                    unsigned key = ((fb >> (IB - 1)) << IB) | (unsigned)tid;
-                    key = block_sort32<T>(key, kbuf, tid);
-                    sidx_t = (int)(key & ((1u << IB) - 1u));
-                    dd = sd2[sidx_t];
+                    unsigned key[TPT];
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const unsigned fb = __float_as_uint(__double2float_rd(my_d2[kk]));
+                        key[kk] = ((fb >> (IB - 1)) << IB) | (unsigned)(tid + kk * T);
+                    }
+                    block_sort32<T, TPT>(key, kbuf, tid);
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        sidx_t[kk] = (int)(key[kk] & ((1u << IB) - 1u));
+                        dd[kk] = sd2[sidx_t[kk]];
+                    }
                     __syncthreads();    // the verification above may still be reading the old order
-                    sdd[PAD(tid)] = dd;
-                    sidx[tid] = (unsigned short)sidx_t;
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int p = tid + kk * T;
+                        sdd[PAD(p)] = dd[kk];
+                        sidx[p] = (unsigned short)sidx_t[kk];
+                    }
                     __syncthreads();
                     bool inv = false;
-                    if (tid + 1 < T) inv = key_greater(dd, (unsigned)sidx_t, sdd[PAD(tid + 1)], (unsigned)sidx[tid + 1]);
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int p = tid + kk * T;
+                        if (p + 1 < NP) inv = inv || key_greater(dd[kk], (unsigned)sidx_t[kk], sdd[PAD(p + 1)], (unsigned)sidx[p + 1]);
+                    }
                     if (__syncthreads_or(inv)) {
                         if (tid == 0) ++M->cnt[0];
-                        (void)team_repair_order<T, E>(sdd, sidx, tid, 1 << 30);
+                        (void)team_repair_order<T, TPT, E>(sdd, sidx, tid, 1 << 30);
                     }
                 }
                 PHASE(5);
@@ -479,8 +548,12 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 __syncthreads();
                 PHASE(6);
-                sidx_t = sidx[tid];
-                const double S = __dadd_rn(M->sexcl[lp], spart[PAD(tid)]);
+                double S[TPT];
+#pragma unroll
+                for (int kk = 0; kk < TPT; ++kk) {
+                    const int p = tid + kk * T;
+                    S[kk] = __dadd_rn(M->sexcl[p / E], spart[PAD(p)]);
+                }
 
                 // subset size: first strict minimum of FRMSD(k) = c_k sqrt(S_k / k)  (ficp.py:80-85).
                 // The filter G(k) = S_k (c_k^2 / k) leaves the k within rounding distance of the minimum - almost always
@@ -491,32 +564,49 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 double fstar = kInf, rstar = 0.0;
                 if (fixed_k > 0) {
                     kstar = fixed_k;
-                    if (tid == kstar - 1) M->sk = S;
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk)
+                        if (tid + kk * T == kstar - 1) M->sk = S[kk];
                     f_pending = true;
                     __syncthreads();   // every S has been read: the fit terms below reuse the scan's buffers
                 } else {
-                    const double g = (tid < n) ? __dmul_rn(S, sg[r * 32 + lp]) : kInf;
-                    double gb = g;
+                    double g[TPT];
+                    double gb = kInf;
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int p = tid + kk * T, lp = p / E, r = p - lp * E;
+                        g[kk] = (p < n) ? __dmul_rn(S[kk], sg[r * 32 + lp]) : kInf;
+                        gb = fmin(gb, g[kk]);
+                    }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) gb = fmin(gb, __shfl_xor_sync(kFull, gb, o));
                     if (lane == 0) M->red_a[warp] = gb;
                     __syncthreads();
                     const double gbest = warp_min_of(M->red_a, NW, lane);
                     const double gthr = gbest * (1.0 + 1e-12);
-                    const bool cand = (tid < n && g <= gthr);
-                    if (cand) { M->red_k[0] = tid + 1; M->sk = S; }     // meaningful when there is exactly one
-                    const int ncand = __syncthreads_count(cand);
+                    int ncand = 0;
+                    bool cand[TPT];
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int p = tid + kk * T;
+                        cand[kk] = (p < n && g[kk] <= gthr);
+                        if (cand[kk]) { M->red_k[0] = p + 1; M->sk = S[kk]; }     // meaningful when there is exactly one
+                        ncand += __syncthreads_count(cand[kk]);
+                    }
                     if (ncand == 1) {
                         kstar = M->red_k[0];
                         f_pending = true;
                     } else {
                         int kb = INT_MAX;
-                        if (cand) {
-                            const int k = tid + 1;
-                            const double rm = sqrt(S / (double)k);
-                            fstar = __dmul_rn(__ldg(gc + r * 32 + lp), rm);
-                            kb = k;
-                            rstar = rm;
+#pragma unroll
+                        for (int kk = 0; kk < TPT; ++kk) {
+                            if (cand[kk]) {
+                                const int p = tid + kk * T, lp = p / E, r = p - lp * E;
+                                const int k = p + 1;
+                                const double rm = sqrt(S[kk] / (double)k);
+                                const double f = __dmul_rn(__ldg(gc + r * 32 + lp), rm);
+                                if (f < fstar || (f == fstar && k < kb)) { fstar = f; kb = k; rstar = rm; }
+                            }
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
@@ -555,22 +645,27 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
 
                 // ================= rigid fit (ficp.py:89-110), started BEFORE the stage logic below has the FRMSD value: the
                 // fit needs only the trimmed subset.  It is skipped when no outcome of the convergence test could use it.
-                // Every thread prepares its tree's term; warp 0 adds them in the order of the one-warp kernel - lane l adds
+                // Every thread prepares its trees' terms; warp 0 adds them in the order of the one-warp kernel - lane l adds
                 // the trees l, l + 32, ... in turn, then an xor butterfly over the 32 lanes - and solves; the last warp
                 // computes FRMSD / RMSE of the pass meanwhile.
                 const bool fit_useful = kstar > 0 && (first ? (it < P.max_iter) : (it + 1 < P.max_iter));
                 double ax = 0.0, ay = 0.0;
                 if (fit_useful) {
-                    const Pose pose = ld_pose(M->pose[pb]);
-                    fit_shift(pose, M->ub[0], M->ub[1], ax, ay);
-                    const bool inl = tid < n && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx));
-                    finl[tid] = inl ? 1 : 0;
-                    if (inl) {
-                        double qx, qy, ux, uy, vx, vy;
-                        pose_apply(pose, s_u[tid], qx, qy);
-                        const double2 t = corr_xy(G_, team_window(tp, M->win, G_), snn[tid]);
-                        fit_uv(qx, qy, t.x, t.y, ax, ay, ux, uy, vx, vy);
-                        f_ux[tid] = ux; f_uy[tid] = uy; f_vx[tid] = vx; f_vy[tid] = vy;
+                    const Pose pose_f = ld_pose(M->pose[pb]);
+                    fit_shift(pose_f, M->ub[0], M->ub[1], ax, ay);
+                    const WindowAcc Wf = team_window(tp, M->win, G_);
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int i = tid + kk * T;
+                        const bool inl = i < n && (my_d2[kk] < po.thr || (my_d2[kk] == po.thr && i <= po.thr_idx));
+                        finl[i] = inl ? 1 : 0;
+                        if (inl) {
+                            double qx, qy, ux, uy, vx, vy;
+                            pose_apply(pose_f, s_u[i], qx, qy);
+                            const double2 t = corr_xy(G_, Wf, snn[i]);
+                            fit_uv(qx, qy, t.x, t.y, ax, ay, ux, uy, vx, vy);
+                            f_ux[i] = ux; f_uy[i] = uy; f_vx[i] = vx; f_vy[i] = vy;
+                        }
                     }
                 }
                 __syncthreads();     // fit terms, M->sk
@@ -601,15 +696,22 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 __syncthreads();
                 if (f_pending) { po.f = M->fk[0]; po.rmse = M->fk[1]; }
-                if (P.trace_cap > 0 && passes < P.trace_cap && tid < n) {
+                if (P.trace_cap > 0 && passes < P.trace_cap) {
                     // per-pass trace (tests only): original target row, squared distance, membership in the trimmed subset
                     const size_t rec = (size_t)c * P.trace_cap + passes, base = rec * P.trace_stride;
-                    const int code = snn[tid];
-                    int orig = -1;
-                    if (code != -1) orig = grid_orig(G_, (code < 0) ? (code & 0x7FFFFFFF) : team_window(tp, M->win, G_).global_pos(code & 0xFFFF));
-                    P.tr_idx[base + tid] = orig;
-                    P.tr_d2[base + tid] = my_d2;
-                    P.tr_in[base + tid] = (po.k > 0 && (my_d2 < po.thr || (my_d2 == po.thr && tid <= po.thr_idx))) ? 1 : 0;
+                    const WindowAcc Wr = team_window(tp, M->win, G_);
+#pragma unroll
+                    for (int kk = 0; kk < TPT; ++kk) {
+                        const int i = tid + kk * T;
+                        if (i < n) {
+                            const int code = snn[i];
+                            int orig = -1;
+                            if (code != -1) orig = grid_orig(G_, (code < 0) ? (code & 0x7FFFFFFF) : Wr.global_pos(code & 0xFFFF));
+                            P.tr_idx[base + i] = orig;
+                            P.tr_d2[base + i] = my_d2[kk];
+                            P.tr_in[base + i] = (po.k > 0 && (my_d2[kk] < po.thr || (my_d2[kk] == po.thr && i <= po.thr_idx))) ? 1 : 0;
+                        }
+                    }
                     if (tid == 0) { P.tr_k[rec] = po.k; P.tr_f[rec] = po.f; }
                 }
                 ++passes;
@@ -657,11 +759,18 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
             M->acc[3] += M->cnt[1]; M->acc[4] += M->cnt[2]; M->acc[5] += M->cnt[3];
             if (ng) atomicAdd(P.stats + 1, (unsigned long long)ng);
         }
-        if (P.final_xy && P.n_hyp_local == 1 && tid < n) {
-            double qx, qy;
-            pose_apply(ld_pose(M->pose[pb]), s_u[tid], qx, qy);
-            P.final_xy[(pm.off + tid) * 2] = qx;
-            P.final_xy[(pm.off + tid) * 2 + 1] = qy;
+        if (P.final_xy && P.n_hyp_local == 1) {
+            const Pose pose_r = ld_pose(M->pose[pb]);
+#pragma unroll
+            for (int kk = 0; kk < TPT; ++kk) {
+                const int i = tid + kk * T;
+                if (i < n) {
+                    double qx, qy;
+                    pose_apply(pose_r, s_u[i], qx, qy);
+                    P.final_xy[(pm.off + i) * 2] = qx;
+                    P.final_xy[(pm.off + i) * 2 + 1] = qy;
+                }
+            }
         }
     }
     PHASE(12);
@@ -676,17 +785,17 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
     }
 }
 
-template <bool Z3, int T>
+template <bool Z3, int T, int TPT>
 int team_launch_one(const IcpParams& p, int ctas, size_t smem, cudaStream_t stream) {
-    auto kern = icp_team_kernel<Z3, T>;
+    auto kern = icp_team_kernel<Z3, T, TPT>;
     FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, T, smem, stream>>>(p);
     FICP_CUDA(cudaGetLastError());
     return kOk;
 }
-template <bool Z3, int T>
+template <bool Z3, int T, int TPT>
 int team_occupancy_one(size_t smem, int* out) {
-    auto kern = icp_team_kernel<Z3, T>;
+    auto kern = icp_team_kernel<Z3, T, TPT>;
     FICP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, T, smem));
     return kOk;
@@ -703,17 +812,21 @@ extern "C" __attribute__((visibility("default"))) int ficp_debug_phase_clocks(un
 #endif
 
 size_t icp_team_smem_bytes(int e, bool z3, int wcap_pts, int wcap_cells, int wcap_rows) {
+    (void)wcap_rows;
     return team_layout(32 * e, z3, wcap_pts, wcap_cells).total;
 }
 
-#define FICP_TEAM_DISPATCH(FN, ...)                                                                   \
-    switch (e) {                                                                                      \
-        case 2: return z3 ? FN<true, 64>(__VA_ARGS__) : FN<false, 64>(__VA_ARGS__);                   \
-        case 4: return z3 ? FN<true, 128>(__VA_ARGS__) : FN<false, 128>(__VA_ARGS__);                 \
-        case 8: return z3 ? FN<true, 256>(__VA_ARGS__) : FN<false, 256>(__VA_ARGS__);                 \
-        case 16: return z3 ? FN<true, 512>(__VA_ARGS__) : FN<false, 512>(__VA_ARGS__);                \
-        case 32: return z3 ? FN<true, 1024>(__VA_ARGS__) : FN<false, 1024>(__VA_ARGS__);              \
-        default: set_error("icp_team: unsupported elements-per-lane"); return kErrInvalid;            \
+// threads of the CTA that works on a plot of 32 e tree slots
+int icp_team_threads(int e) { return (e >= 16) ? 32 * e / FICP_TEAM_TPT : 32 * e; }
+
+#define FICP_TEAM_DISPATCH(FN, ...)                                                                                         \
+    switch (e) {                                                                                                            \
+        case 2: return z3 ? FN<true, 64, 1>(__VA_ARGS__) : FN<false, 64, 1>(__VA_ARGS__);                                   \
+        case 4: return z3 ? FN<true, 128, 1>(__VA_ARGS__) : FN<false, 128, 1>(__VA_ARGS__);                                 \
+        case 8: return z3 ? FN<true, 256, 1>(__VA_ARGS__) : FN<false, 256, 1>(__VA_ARGS__);                                 \
+        case 16: return z3 ? FN<true, 512 / FICP_TEAM_TPT, FICP_TEAM_TPT>(__VA_ARGS__) : FN<false, 512 / FICP_TEAM_TPT, FICP_TEAM_TPT>(__VA_ARGS__);   \
+        case 32: return z3 ? FN<true, 1024 / FICP_TEAM_TPT, FICP_TEAM_TPT>(__VA_ARGS__) : FN<false, 1024 / FICP_TEAM_TPT, FICP_TEAM_TPT>(__VA_ARGS__); \
+        default: set_error("icp_team: unsupported elements-per-lane"); return kErrInvalid;                                  \
     }
 
 int icp_team_max_ctas_per_sm(int e, bool z3, size_t smem, int* out) { FICP_TEAM_DISPATCH(team_occupancy_one, smem, out) }

@@ -324,7 +324,7 @@ def test_cta_per_icp_is_bit_identical(gpu, n, dims):
         b = IcpBatch(ti, [plots[0], plots[1], small], hyp, **kw)
         assert b.info["cta_per_icp"] == int(kw["cta_per_icp"])
         if kw["cta_per_icp"]:
-            assert b.info["warps_per_cta"] == b.info["elems_per_lane"]
+            assert b.info["warps_per_cta"] in (b.info["elems_per_lane"], b.info["elems_per_lane"] // 2)   # one or two trees per thread
         outs.append(b.run().results())
         b.close()
     for o in outs[1:4]:

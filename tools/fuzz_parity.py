@@ -111,7 +111,11 @@ def check(src, tgt, hyp, kw, launch):
         err = np.abs(got - ref["aligned"][h][:, :2]).max()
         if err > 1e-6:
             msgs.append(f"hyp {h}: positions differ by {err:.3g}")
-        if np.isfinite(ref["score"][h]) and abs(rows["frmsd"][h] - ref["score"][h]) > 1e-6 * max(1.0, ref["score"][h]):
+        # FRMSD = (N/k)^lambda * rmse magnifies a position difference: a pass that ends with k = 1 of 300 trees turns the
+        # 2.4e-9 m (3 ulp of a UTM northing) by which two implementations' poses differ into 4e-6 of score (seed 31 case 1016)
+        kf = max(int(ref["k"][h]), 1)
+        amp = (len(src) / kf) ** 1.3 * 8.0 * 2.3e-16 * float(np.abs(tgt[:, :2]).max())   # stage-2 lambda <= 1.3
+        if np.isfinite(ref["score"][h]) and abs(rows["frmsd"][h] - ref["score"][h]) > max(1e-6 * max(1.0, ref["score"][h]), amp):
             msgs.append(f"hyp {h}: frmsd {rows['frmsd'][h]} vs {ref['score'][h]}")
     if real.all() and out["best_key"][0] != ref["best_key"]:
         # two hypotheses that converged to the same pose can swap places at the fp32 rounding of the score
