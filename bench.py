@@ -271,11 +271,12 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------------- CUDA arm
 def kernel_source_hash():
-    """sha256 (16 hex) of the sources of the persistent kernels: ncu-derived figures in profiles/traffic.json are only used
-    when they were captured on exactly this code."""
+    """sha256 (16 hex) of the sources the warp-per-ICP persistent kernel is compiled from: ncu-derived figures in
+    profiles/traffic.json (all of that kernel) are only used when they were captured on exactly this code.  (icp_team.cu, the
+    CTA-per-ICP kernel, is a separate translation unit and does not enter the default bench line's dominant kernel.)"""
     import hashlib
     h = hashlib.sha256()
-    for f in ("icp_persistent.cu", "icp_team.cu", "icp_shared.cuh", "nn_search.cuh", "ficp_common.cuh"):
+    for f in ("icp_persistent.cu", "icp_shared.cuh", "nn_search.cuh", "ficp_common.cuh"):
         h.update(open(os.path.join(ROOT, "coregistrationgame_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -285,7 +286,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from coregistrationgame_b200 import IcpBatch, TargetIndex, _lib, register_batch
-    from coregistrationgame_b200.dist import PACK_WORDS, exchange_best, register_batch_distributed, shard_of
+    from coregistrationgame_b200.dist import PACK_WORDS, exchange_best, register_batch_distributed, shard_of, shard_plan
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -298,7 +299,9 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     n_plots = args.plots_per_gpu * world
     tgt, plots, hyp, name = workload(args, n_plots)
-    by_plots = hyp.shape[0] < world or args.workload == "c4"     # one pose per plot: shard the plots, not the poses
+    one_pose = hyp.shape[0] < world or args.workload == "c4"     # one start pose per plot (config 4)
+    # the same cut register_batch_distributed takes (dist.shard_plan): whole plots per rank when that balances
+    by_plots = one_pose or (world > 1 and shard_plan([len(p) for p in plots], hyp.shape[0], world) == "plots")
     props = _lib.device_props()
     cta = {"auto": None, "on": True, "off": False}[args.cta]
     helpers = {'auto': None, 'on': True, 'off': False}[args.helpers]
@@ -312,7 +315,7 @@ def run_b200(args):
     tinfo = index.info()
     if by_plots:
         mine = list(range(rank, n_plots, world))
-        batch = IcpBatch(index, [plots[p] for p in mine], hyp, min_k=0, **bkw)
+        batch = IcpBatch(index, [plots[p] for p in mine], hyp, **({"min_k": 0} if one_pose else {}), **bkw)
         n_rows = (n_plots + world - 1) // world
     else:
         batch = IcpBatch(index, plots, hyp, hyp_shard=shard_of(rank, world), **bkw)
@@ -375,7 +378,7 @@ def run_b200(args):
     ekw = dict(warps_per_cta=args.warps, ctas_per_sm=args.ctas_per_sm, cta_per_icp=cta)
     if args.fixed_frac > 0:
         ekw["fixed_frac"] = args.fixed_frac
-    if by_plots:
+    if one_pose:
         ekw["min_k"] = 0
 
     def e2e_step():
@@ -465,7 +468,7 @@ def run_b200(args):
         return res
 
     single = None
-    if not by_plots and not args.no_single_stand:
+    if not one_pose and not args.no_single_stand:
         ms_n, p_n, info_n = time_single(shard_of(rank, world), True)
         sms_ = torch.tensor([ms_n], dtype=torch.float64, device=dev)
         sp_ = torch.tensor([p_n], dtype=torch.float64, device=dev)
@@ -638,7 +641,7 @@ def run_b200(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": name, "plots_per_gpu": args.plots_per_gpu, "plots": n_plots,
-                           "icps_per_gpu_per_step": (args.plots_per_gpu if by_plots else args.plots_per_gpu * hyp.shape[0]),
+                           "icps_per_gpu_per_step": (args.plots_per_gpu if one_pose else args.plots_per_gpu * hyp.shape[0]),
                            "hyp_iterations_per_step": passes_all, "parallelism": (f"plots round-robin over {world} GPU(s)" if by_plots else f"hypotheses round-robin over {world} GPU(s)"),
                            "exchange": "device-side pack + ONE all_gather of 112 B per plot (dist.exchange_best), inside the timed step",
                            "l2": "flushed between timed steps (256 MB write)", "launch": batch.info,

@@ -325,7 +325,7 @@ int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* cor
     if (frmsd_out) *frmsd_out = HUGE_VAL;
     if (n <= 0) return kOk;
     if (!dist_host) { set_error("ficp_select_fraction: null distances"); return kErrInvalid; }
-    if (n > kSelectMaxN) { set_error("ficp_select_fraction: more than 8192 points per plot are not supported"); return kErrTooLarge; }
+    if (n > kSelectLargeMaxN) { set_error("ficp_select_fraction: more than 2^24 points per plot are not supported"); return kErrTooLarge; }
     const bool want_k = (src_host != nullptr);
     if (want_k && (!corr_host || !weights_host || ld_s < md || ld_c < md || (md != 2 && md != 3))) {
         set_error("ficp_select_fraction: bad source/correspondence arguments");

@@ -87,8 +87,10 @@ int launch_radial_crop(const GridView& v, double cx, double cy, double dist, uns
 int launch_match_remove(const GridView& v, bool z3, const double* d_trees, const long long* d_offsets, int n_plots,
                         int ld, const double* d_thr, long long* d_out, int* d_scratch, cudaStream_t stream);
 int measure_l2_read_gbs(size_t bytes, int iters, double* gbs);
-// Sort by (dist, index) + FRMSD prefix scan + first-minimum k (auto) or fixed k.  n <= kSelectMaxN.
+// Sort by (dist, index) + FRMSD prefix scan + first-minimum k (auto) or fixed k.  One CTA in shared memory up to
+// kSelectMaxN rows, a chain of launches over global scratch above (up to kSelectLargeMaxN).
 constexpr int kSelectMaxN = 8192;
+constexpr int kSelectLargeMaxN = 1 << 24;
 int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, int ld_c, const double* d_dist,
                            int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,
                            double* d_frmsd_out, int* d_order_out, cudaStream_t stream);

@@ -140,6 +140,126 @@ __global__ void __launch_bounds__(1024) select_fraction_kernel(const double* __r
     }
 }
 
+// ---- select_fraction for plots above kSelectMaxN rows: the same three steps over GLOBAL scratch arrays ----------------
+// (the reference accepts any N, ficp.py:73-86; np.argsort + np.cumsum there).  Sort: bitonic network on (distance, index)
+// pairs - phases / steps whose partners lie within one tile of kSfTile elements run in shared memory (one launch for all
+// phases k <= kSfTile, one per later phase), the wider steps are one grid-wide compare-exchange launch each
+// (45 launches for 2^20 rows).  Scan + first strict minimum: one CTA, every thread a contiguous chunk, as above.
+constexpr int kSfTile = 4096;
+
+__device__ __forceinline__ void sf_cex(double& ka, int& ia, double& kb, int& ib, bool asc) {
+    const bool gt = (ka > kb) || (ka == kb && ia > ib);
+    if (gt == asc) {
+        const double tk = ka; ka = kb; kb = tk;
+        const int ti = ia; ia = ib; ib = ti;
+    }
+}
+
+__global__ void __launch_bounds__(256) sf_init_kernel(const double* __restrict__ dist, int n, int npad, double* __restrict__ key,
+                                                      int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    key[i] = (i < n) ? dist[i] : kInf;
+    idx[i] = i;
+}
+
+// Steps j = j_hi, j_hi/2, ..., 1 of the phases k = k_lo, 2 k_lo, ..., k_hi inside tiles of kSfTile elements (j_hi < kSfTile;
+// for k_lo < k_hi every phase starts at j = k/2, i.e. k_hi <= kSfTile).
+__global__ void __launch_bounds__(1024) sf_tile_kernel(double* __restrict__ key, int* __restrict__ idx, int k_lo, int k_hi, int j_hi) {
+    __shared__ double sk[kSfTile];
+    __shared__ int si[kSfTile];
+    const int base = blockIdx.x * kSfTile, tid = threadIdx.x;
+    for (int i = tid; i < kSfTile; i += 1024) { sk[i] = key[base + i]; si[i] = idx[base + i]; }
+    __syncthreads();
+    for (int k = k_lo; k <= k_hi; k <<= 1) {
+        for (int j = (k_lo == k_hi) ? j_hi : (k >> 1); j > 0; j >>= 1) {
+            for (int t = tid; t < kSfTile / 2; t += 1024) {
+                const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+                sf_cex(sk[i], si[i], sk[l], si[l], ((base + i) & k) == 0);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < kSfTile; i += 1024) { key[base + i] = sk[i]; idx[base + i] = si[i]; }
+}
+
+// One step (k, j) with j >= kSfTile: partners are j apart in global memory.
+__global__ void __launch_bounds__(256) sf_step_kernel(double* __restrict__ key, int* __restrict__ idx, int npad, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (npad >> 1)) return;
+    const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+    double ka = key[i], kb = key[l];
+    int ia = idx[i], ib = idx[l];
+    const bool gt = (ka > kb) || (ka == kb && ia > ib);
+    if (gt == ((i & k) == 0)) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
+}
+
+__global__ void __launch_bounds__(256) sf_residual_kernel(const double* __restrict__ src, int ld_s, const double* __restrict__ corr,
+                                                          int ld_c, const int* __restrict__ idx, int n, int md,
+                                                          double* __restrict__ pre, int* __restrict__ order_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = idx[i];
+    if (order_out) order_out[i] = r;
+    if (src) pre[i] = sqdiff(src + (size_t)r * ld_s, corr + (size_t)r * ld_c, md);
+}
+
+__global__ void __launch_bounds__(1024) sf_scan_min_kernel(const double* __restrict__ pre, int n, const double* __restrict__ w,
+                                                           int fixed_k, long long* __restrict__ k_out, double* __restrict__ f_out) {
+    __shared__ double red[32];
+    __shared__ double red_f[32];
+    __shared__ int red_k[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int chunk = (n + nt - 1) / nt;
+    const int b0 = tid * chunk;
+    double loc = 0.0;
+    for (int j = 0; j < chunk; ++j)
+        if (b0 + j < n) loc += pre[b0 + j];
+    double inc = loc;
+    const int l = tid & 31, wq = tid >> 5, nw = (nt + 31) >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, inc, o);
+        if (l >= o) inc += t;
+    }
+    if (l == 31) red[wq] = inc;
+    __syncthreads();
+    double base = 0.0;
+    for (int i = 0; i < wq && i < nw; ++i) base += red[i];
+    double run = base + inc - loc;
+    double fbest = kInf;
+    int kbest = 0;
+    for (int j = 0; j < chunk; ++j) {
+        const int i = b0 + j;
+        if (i < n) {
+            run += pre[i];
+            const int k = i + 1;
+            const double f = w[i] * sqrt(run / (double)k);
+            if (fixed_k > 0) {
+                if (k == fixed_k) { fbest = f; kbest = k; }
+            } else if (f < fbest) {  // first strict minimum (ficp.py:84)
+                fbest = f;
+                kbest = k;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double of = __shfl_xor_sync(kFull, fbest, o);
+        const int ok = __shfl_xor_sync(kFull, kbest, o);
+        if (ok != 0 && (kbest == 0 || of < fbest || (of == fbest && ok < kbest))) { fbest = of; kbest = ok; }
+    }
+    if (l == 0) { red_f[wq] = fbest; red_k[wq] = kbest; }
+    __syncthreads();
+    if (tid == 0) {
+        double f = kInf; int k = 0;
+        for (int i = 0; i < nw; ++i)
+            if (red_k[i] != 0 && (k == 0 || red_f[i] < f || (red_f[i] == f && red_k[i] < k))) { f = red_f[i]; k = red_k[i]; }
+        *k_out = k;
+        *f_out = (k == 0) ? kInf : f;
+    }
+}
+
 // ---- rigid 2-D fit -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fit_rigid2d_kernel(const double* __restrict__ src, int ld_s,
                                                           const double* __restrict__ tgt, int ld_t,
@@ -254,12 +374,37 @@ int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, 
                            int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,
                            double* d_frmsd_out, int* d_order_out, cudaStream_t stream) {
     if (n <= 0) return kOk;
-    if (n > kSelectMaxN) {
-        set_error("select_fraction: more than 8192 points per plot are not supported");
+    if (n > kSelectLargeMaxN) {
+        set_error("select_fraction: more than 2^24 points per plot are not supported");
         return kErrTooLarge;
     }
     int npad = 2;
     while (npad < n) npad <<= 1;
+    if (n > kSelectMaxN) {
+        // global-scratch path: (distance, index) pairs padded to a power of two, residuals in trim order
+        double *key = nullptr, *pre = nullptr;
+        int* idx = nullptr;
+        cudaError_t e;
+        if ((e = dev_alloc_t(&key, (size_t)npad, stream)) != cudaSuccess || (e = dev_alloc_t(&idx, (size_t)npad, stream)) != cudaSuccess ||
+            (e = dev_alloc_t(&pre, (size_t)n, stream)) != cudaSuccess) {
+            dev_free(key, stream); dev_free(idx, stream); dev_free(pre, stream);
+            return cuda_fail(e, "select_fraction scratch", __FILE__, __LINE__);
+        }
+        auto done = [&](int rc) { dev_free(key, stream); dev_free(idx, stream); dev_free(pre, stream); return rc; };
+        sf_init_kernel<<<(npad + 255) / 256, 256, 0, stream>>>(d_dist, n, npad, key, idx);
+        const int tiles = npad / kSfTile;   // npad >= 16384
+        sf_tile_kernel<<<tiles, 1024, 0, stream>>>(key, idx, 2, kSfTile, 0);
+        for (int k = 2 * kSfTile; k <= npad; k <<= 1) {
+            int j = k >> 1;
+            for (; j >= kSfTile; j >>= 1) sf_step_kernel<<<((npad >> 1) + 255) / 256, 256, 0, stream>>>(key, idx, npad, k, j);
+            sf_tile_kernel<<<tiles, 1024, 0, stream>>>(key, idx, k, k, j);
+        }
+        sf_residual_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_src, ld_s, d_corr, ld_c, idx, n, md, pre, d_order_out);
+        if (d_src) sf_scan_min_kernel<<<1, 1024, 0, stream>>>(pre, n, d_weights, fixed_k, d_k_out, d_frmsd_out);
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return done(cuda_fail(le, "select_fraction (large)", __FILE__, __LINE__));
+        return done(kOk);
+    }
     const size_t smem = (size_t)npad * (2 * sizeof(double) + sizeof(int));
     // per launch, not once per process: the attribute is per device (ficp_set_device may have moved us)
     FICP_CUDA(cudaFuncSetAttribute(select_fraction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

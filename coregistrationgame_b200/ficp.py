@@ -22,7 +22,7 @@ from . import _lib
 from .batch import IDENTITY_HYPOTHESIS, STAGE2_LAMBDA, IcpBatch, TargetIndex, frmsd_weights
 
 _KERNEL_MAX_N = 1024      # persistent kernel: trees per plot
-_STEPWISE_MAX_N = 8192    # stage kernels
+_STEPWISE_MAX_N = 1 << 24  # stage kernels (one CTA in shared memory up to 8192 rows, global-scratch sort / scan above)
 
 
 class FractionalICP:

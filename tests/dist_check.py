@@ -42,6 +42,17 @@ def main():
     np.testing.assert_array_equal(d2["best_transform"], s2["best_transform"])
     np.testing.assert_array_equal(d2["k"], s2["best_row"]["k"])
     assert d2["passes_global"] == s2["stats"]["passes"]
+    # a batch of stands (one per rank and more): sharded over PLOTS with every hypothesis on the owner (dist.shard_plan)
+    from coregistrationgame_b200.dist import shard_plan
+    tgt3, plots3, _ = orc.synthetic_scene(200000, 120, seed=11, dims=3, n_plots=2 * world, hidden_pose=True)
+    assert shard_plan([len(p) for p in plots3], hyp.shape[0], world) == "plots"
+    d3 = register_batch_distributed(plots3, tgt3, hyp)
+    s3 = register_batch(plots3, tgt3, hyp)
+    np.testing.assert_array_equal(d3["best_key"], s3["best_key"])
+    np.testing.assert_array_equal(d3["best_hyp"], s3["best_hyp"])
+    np.testing.assert_array_equal(d3["best_transform"], s3["best_transform"])
+    np.testing.assert_array_equal(d3["k"], s3["best_row"]["k"])
+    assert d3["passes_global"] == s3["stats"]["passes"], (d3["passes_global"], s3["stats"]["passes"])
     dist.barrier()
     if rank == 0:
         print(f"dist_check ok: world={world} plots={len(plots)} hyps={hyp.shape[0]} winners={d['best_hyp'].tolist()} "

@@ -137,3 +137,17 @@ def test_single_process_passthrough():
     np.testing.assert_array_equal(gk.astype(np.int64), keys)
     np.testing.assert_array_equal(rows["cx"], [3, 0])
     assert passes.tolist() == [9]
+
+
+def test_shard_plan_picks_the_balanced_axis():
+    """dist.shard_plan: whole plots per rank for a batch of stands, hypotheses for ONE stand, plots when there are fewer
+    start poses than ranks; the same decision on every rank (pure function of sizes)."""
+    from coregistrationgame_b200.dist import shard_plan
+    assert shard_plan([500] * 128, 4096, 8) == "plots"          # the bench's weak-scaling batch (16 stands per GPU)
+    assert shard_plan([500] * 16, 4096, 1) == "plots"           # one rank: everything is its own
+    assert shard_plan([500], 4096, 8) == "hypotheses"           # the literal config 3: one stand, strong scaling
+    assert shard_plan([500] * 5, 64, 2) == "hypotheses"         # 3 + 2 plots would be 1.2x unbalanced, 32 + 32 poses are not
+    assert shard_plan([150] * 10000, 1, 8) == "plots"           # config 4: one start pose per plot
+    assert shard_plan([150] * 3, 1, 8) == "plots"               # nothing else to cut
+    assert shard_plan([1000, 10, 10, 10], 64, 2) == "hypotheses"   # one big stand among small ones: plots would be 1010 : 20
+    assert shard_plan([250] * 8, 7, 4) == "plots"               # 7 poses over 4 ranks = 8/7 unbalanced; plots are even

@@ -269,6 +269,73 @@ def test_select_fraction_matches_oracle(gpu, n, lam):
     assert val == pytest.approx(val_ref, rel=1e-13)
 
 
+@pytest.mark.parametrize("n", [8193, 20000, 70001])
+@pytest.mark.parametrize("lam", [3.0, 0.95])
+def test_select_fraction_large_plots(gpu, n, lam):
+    """Plots above the one-CTA kernel's 8192 rows (the reference accepts any N, ficp.py:73-86): global-scratch bitonic sort +
+    scan.  The trim order is exact (array_equal with the stable (distance, index) order, ties included); k is the first
+    strict minimum of the oracle's cumsum FRMSD curve unless that minimum is within summation rounding of another k."""
+    from ficp import FractionalICP
+    rng = np.random.default_rng(n)
+    src = rng.normal(size=(n, 3)) * 50
+    corr = src + rng.normal(size=(n, 3)) * rng.choice([0.05, 0.5, 5.0], size=(n, 1))
+    src[3], corr[3] = src[7], corr[7]
+    src[n - 1], corr[n - 1] = src[11], corr[11]      # exact ties far apart in index
+    icp = FractionalICP(src, corr, lambda_val=lam)
+    d2 = orc.sqdist_canonical(src, corr)
+    dist = np.sqrt(d2)
+    order = orc.stable_order(dist)
+    np.testing.assert_array_equal(icp.get_n_first_elements(n, dist), order)
+    frac, k = icp.find_optimal_fraction(corr, dist)
+    k_ref, val_ref, _ = orc.select_fraction_cumsum(d2, lam, order)
+    s = np.cumsum(d2[order])
+    vals = orc.frmsd_weights(n, lam) * np.sqrt(s / np.arange(1, n + 1))
+    assert k == k_ref or abs(vals[k - 1] - val_ref) <= 1e-12 * val_ref, (k, k_ref, vals[k - 1], val_ref)
+    assert frac == k / n
+    # fixed-size trimming reads the k-th element of the same order
+    lib_k, lib_f = ctypes_select_fixed(src, corr, dist, n // 2, lam)
+    assert lib_k == n // 2
+    assert lib_f == pytest.approx(vals[n // 2 - 1], rel=1e-12)
+
+
+def ctypes_select_fixed(src, corr, dist, fixed_k, lam):
+    import ctypes as C
+    from coregistrationgame_b200 import _lib
+    from coregistrationgame_b200.ficp import frmsd_weights
+    n = len(src)
+    w = frmsd_weights(n, lam)
+    k, val = C.c_int64(0), C.c_double(0.0)
+    d = np.ascontiguousarray(dist, dtype=np.float64)
+    s3, c3 = np.ascontiguousarray(src), np.ascontiguousarray(corr)
+    _lib.check(_lib.load().ficp_select_fraction(_lib.ptr(s3), 3, _lib.ptr(c3), 3, _lib.ptr(d), n, 3, _lib.ptr(w), fixed_k,
+                                                C.byref(k), C.byref(val), None), "ficp_select_fraction")
+    return int(k.value), float(val.value)
+
+
+def test_run_on_a_plot_above_the_persistent_kernels_limit(gpu):
+    """A 12 000-tree plot (above the persistent kernel's 1024 and the one-CTA trim kernel's 8192): the host-stepped path
+    over the stage kernels recovers the hidden pose like the oracle's run on the same data."""
+    from ficp import FractionalICP
+    rng = np.random.default_rng(5)
+    m, n = 60000, 12000
+    tgt = np.column_stack([rng.uniform(0, 800, m), rng.uniform(0, 800, m), rng.uniform(5, 35, m)])
+    pick = rng.choice(m, n, replace=False)
+    src = tgt[pick] + np.column_stack([rng.normal(0, 0.05, (n, 2)), rng.normal(0, 0.3, n)])
+    th = np.deg2rad(0.2)
+    r = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    c = src[:, :2].mean(0)
+    moved = src.copy()
+    moved[:, :2] = (src[:, :2] - c) @ r.T + c + np.array([0.3, -0.2])
+    icp = FractionalICP(moved, tgt, max_iterations=30)
+    out = icp.run()
+    tr = orc.RunTrace(light=True)
+    ref = orc.ficp_run(moved, tgt, max_iterations=30, trace=tr)
+    assert icp.n_passes_ == tr.passes
+    np.testing.assert_allclose(out[:, :2], ref[:, :2], atol=1e-6)
+    assert np.abs(out[:, :2] - src[:, :2]).max() < 0.05
+    np.testing.assert_array_equal(out[:, 2], moved[:, 2])
+
+
 def test_select_fraction_zero_and_tied_distances(gpu):
     from ficp import FractionalICP
     src = np.arange(40, dtype=float).reshape(20, 2)

@@ -74,12 +74,12 @@ def test_constructor_and_degenerate_inputs_without_gpu():
 
 
 def test_oversized_plot_is_refused_before_any_work():
-    """plots above the stage kernels' 8192-row limit raise up front (no NN pass first)."""
-    from coregistrationgame_b200 import FractionalICP
-    rng = np.random.default_rng(0)
-    icp = FractionalICP(rng.normal(size=(8193, 2)), rng.normal(size=(50, 2)))
-    with pytest.raises(NotImplementedError, match="8192"):
-        icp.run()
+    """plots above the stage kernels' row limit (2^24 since round 2; 8192 before) raise up front - no NN pass
+    first.  Checked on the limit constant: allocating 2^24 + 1 rows here would only test numpy."""
+    from coregistrationgame_b200 import ficp as shim
+    assert shim._STEPWISE_MAX_N == 1 << 24 and shim._KERNEL_MAX_N == 1024
+    src = open(shim.__file__).read()
+    assert src.index("if n > _STEPWISE_MAX_N") < src.index("if n > _KERNEL_MAX_N") < src.index("IcpBatch(index")
 
 
 def test_plot_centres_vectorised_is_bit_identical():
