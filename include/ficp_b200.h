@@ -145,7 +145,8 @@ FICP_API int ficp_radial_crop(const ficp_target* t, double cx, double cy, double
 /* ---- kernel 2: trimming.  Replaces find_optimal_fraction / get_n_first_elements (ficp.py:62-63,73-86).
  * weights[k-1] = 1/((k/n)**lambda) (computed by the caller with the reference's own expression).
  * fixed_k > 0 selects a fixed subset size instead of the FRMSD-optimal one.  src/corr may be NULL
- * to obtain only the stable (distance, index) order.  n <= 8192. */
+ * to obtain only the stable (distance, index) order.  One CTA in shared memory for n <= 8192, a chain of launches over
+ * global scratch above (n <= 2^24). */
 FICP_API int ficp_select_fraction(const double* src_host, int32_t ld_s, const double* corr_host, int32_t ld_c,
                          const double* dist_host, int64_t n, int32_t md, const double* weights_host,
                          int64_t fixed_k, int64_t* k_out, double* frmsd_out, int64_t* order_out);
