@@ -566,8 +566,17 @@ def run_b200(args):
                                     "bound": "instruction issue / FP64 pipe, not bandwidth: ~25-55 fp64 candidates per query (DESIGN.md 4.2)",
                                     "cell_m": qindex.info()["cell"]}
         qindex.close()
-        extra["grid_build"] = {"points": int(tinfo["m"]), "ms": tinfo["build_ms"],
-                               "alg_GBps": tinfo["m"] * GRID_BYTES_PER_POINT / (tinfo["build_ms"] * 1e-3) / 1e9,
+        # grid build of the bench target: device time of its launch chain (CUDA events inside ficp_target_create), median of
+        # five warm builds - the build that made `index` above was the process's first launches (module load, pool growth)
+        gb = []
+        for _ in range(6):
+            t2 = TargetIndex(tgt, pts_per_cell=(args.pts_per_cell or None))
+            gb.append(t2.info()["build_ms"])
+            t2.close()
+        gb_ms = sorted(gb[1:])[2]
+        extra["grid_build"] = {"points": int(tinfo["m"]), "ms": gb_ms, "ms_first_build_of_the_process": tinfo["build_ms"],
+                               "alg_GBps": tinfo["m"] * GRID_BYTES_PER_POINT / (gb_ms * 1e-3) / 1e9,
+                               "timing": "CUDA events around the build's launch chain, median of 5 warm builds",
                                "grid": [tinfo["grid_w"], tinfo["grid_h"]], "cell_m": tinfo["cell"]}
 
     # ---- roofline of the dominant kernel (the persistent ICP kernel), SURVEY 8(d): the working set (cell-sorted target,
