@@ -65,6 +65,12 @@ SIGNATURES = {
     "ficp_fit_rigid2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_vp]),
     "ficp_apply_xy": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),
     "ficp_sumsq": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, P(c_f64)]),
+    "ficp_stepper_create": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, P(c_vp)]),
+    "ficp_stepper_set_weights": (c_i32, [c_vp, c_vp]),
+    "ficp_stepper_pass": (c_i32, [c_vp, c_i64, P(c_i64), P(c_f64)]),
+    "ficp_stepper_fit_apply": (c_i32, [c_vp, c_i32, c_vp]),
+    "ficp_stepper_read_xy": (c_i32, [c_vp, c_vp]),
+    "ficp_stepper_destroy": (None, [c_vp]),
     "ficp_batch_create": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp,
                                   c_vp, c_i32, c_vp, P(BatchParams), c_i32, c_vp, P(c_vp)]),
     "ficp_batch_get_info": (c_i32, [c_vp, P(BatchInfo)]),

@@ -408,6 +408,123 @@ int ficp_sumsq(const double* a_host, int32_t ld_a, const double* b_host, int32_t
     return kOk;
 }
 
+// ------------------------------------------------------------------------------------------ stepper
+// Device-resident state of ONE plot above the persistent kernels' 1024-tree limit: the host drives the loop of
+// ficp.py:122-147 pass by pass (it owns the convergence test, in the reference's own expressions), the arrays stay here.
+// Every step runs exactly the stage kernels the host-buffer entry points above run, on the same values in the same order -
+// same bits, without their six host round trips per pass.
+struct Stepper {
+    const Target* t = nullptr;
+    long long n = 0, m = 0;
+    int md = 2;
+    long long k_last = 0;
+    double *d_src = nullptr, *d_src2 = nullptr, *d_corr = nullptr, *d_dist = nullptr, *d_w = nullptr;
+    double *d_f = nullptr, *d_sum = nullptr, *d_T = nullptr;
+    int *d_idx = nullptr, *d_order = nullptr, *d_inv = nullptr;   // d_inv: grid position of every original target row
+    long long* d_k = nullptr;
+    ~Stepper() {
+        cudaDeviceSynchronize();
+        void* all[] = {d_inv, d_src, d_src2, d_corr, d_dist, d_w, d_f, d_sum, d_T, d_idx, d_order, d_k};
+        for (void* q : all) dev_free(q, 0);
+    }
+};
+
+int ficp_stepper_create(const ficp_target* th, const double* src_host, int64_t n, int32_t ld_s, int32_t md, ficp_stepper** out) {
+    if (out) *out = nullptr;
+    if (!th || !src_host || !out) { set_error("ficp_stepper_create: null pointer"); return kErrInvalid; }
+    const Target* t = reinterpret_cast<const Target*>(th);
+    if ((md != 2 && md != 3) || ld_s < md || n <= 0 || n > kSelectLargeMaxN || t->m <= 0 || t->m > 0x7FFFFFFFLL) {
+        set_error("ficp_stepper_create: bad shape (need md in {2, 3} columns, 1 <= n <= 2^24, a non-empty target)");
+        return kErrInvalid;
+    }
+    if ((md == 3) != (t->has_z != 0)) { set_error("ficp_stepper_create: the index must be built on the md matched columns"); return kErrInvalid; }
+    Stepper* S = new Stepper();
+    S->t = t; S->n = n; S->m = t->m; S->md = md;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](auto** q, size_t count) { if (e == cudaSuccess) e = dev_alloc_t(q, count, 0); };
+    A(&S->d_inv, (size_t)t->m); A(&S->d_src, (size_t)n * md); A(&S->d_src2, (size_t)n * md); A(&S->d_corr, (size_t)n * md);
+    A(&S->d_dist, (size_t)n); A(&S->d_w, (size_t)n); A(&S->d_f, 1); A(&S->d_sum, 1); A(&S->d_T, 9);
+    A(&S->d_idx, (size_t)n); A(&S->d_order, (size_t)n); A(&S->d_k, 1);
+    if (e == cudaSuccess) {
+        if (ld_s == md) {
+            e = cudaMemcpy(S->d_src, src_host, sizeof(double) * (size_t)n * md, cudaMemcpyHostToDevice);
+        } else {   // pack the matched columns first: a strided copy of short rows is one transfer per row
+            std::vector<double> packed((size_t)n * md);
+            for (int64_t i = 0; i < n; ++i)
+                for (int c = 0; c < md; ++c) packed[(size_t)i * md + c] = src_host[(size_t)i * ld_s + c];
+            e = cudaMemcpy(S->d_src, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) { delete S; return cuda_fail(e, "ficp_stepper_create", __FILE__, __LINE__); }
+    const int rc = launch_inverse_perm(t->view, S->d_inv, 0);
+    t->used.record(0);
+    if (rc) { delete S; return rc; }
+    *out = reinterpret_cast<ficp_stepper*>(S);
+    return kOk;
+}
+
+int ficp_stepper_set_weights(ficp_stepper* sh, const double* weights_host) {
+    if (!sh || !weights_host) { set_error("ficp_stepper_set_weights: null pointer"); return kErrInvalid; }
+    Stepper* S = reinterpret_cast<Stepper*>(sh);
+    FICP_CUDA(cudaMemcpy(S->d_w, weights_host, sizeof(double) * S->n, cudaMemcpyHostToDevice));
+    return kOk;
+}
+
+// One pass (ficp.py:133-135 / :123-124): nearest neighbours of the current positions, their rows, the trim order and the
+// FRMSD-optimal k (or fixed_k), and the sum of squared residuals over the first k rows of that order.
+int ficp_stepper_pass(ficp_stepper* sh, int64_t fixed_k, int64_t* k_out, double* sumsq_out) {
+    if (!sh || !k_out || !sumsq_out) { set_error("ficp_stepper_pass: null pointer"); return kErrInvalid; }
+    Stepper* S = reinterpret_cast<Stepper*>(sh);
+    *k_out = 0; *sumsq_out = 0.0;
+    if (fixed_k < 0 || fixed_k > S->n) { set_error("ficp_stepper_pass: fixed_k out of range"); return kErrInvalid; }
+    const bool z3 = S->md == 3;
+    int rc = nn_bulk_applies(S->t->view, S->n)
+                 ? launch_nn_query_bulk(S->t->view, z3, S->d_src, S->n, S->md, S->d_idx, S->d_dist, nullptr, nullptr, 0)
+                 : launch_nn_query(S->t->view, z3, S->d_src, S->n, S->md, S->d_idx, S->d_dist, nullptr, 0);
+    S->t->used.record(0);
+    if (rc) return rc;
+    if ((rc = launch_gather_grid_rows(S->t->view, z3, S->d_inv, S->d_idx, S->n, S->d_corr, 0))) return rc;
+    if ((rc = launch_select_fraction(S->d_src, S->md, S->d_corr, S->md, S->d_dist, (int)S->n, S->md, S->d_w, (int)fixed_k, S->d_k,
+                                     S->d_f, S->d_order, 0))) return rc;
+    long long k = 0;
+    FICP_CUDA(cudaMemcpy(&k, S->d_k, sizeof k, cudaMemcpyDeviceToHost));
+    S->k_last = k;
+    *k_out = k;
+    if (k > 0) {
+        if ((rc = launch_sumsq(S->d_src, S->md, S->d_corr, S->md, S->d_order, (int)k, S->md, S->d_sum, 0))) return rc;
+        FICP_CUDA(cudaMemcpy(sumsq_out, S->d_sum, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return kOk;
+}
+
+// Fit on the trimmed rows of the last pass and move the plot (ficp.py:137-139); T9 = the step's 3x3 transform.
+int ficp_stepper_fit_apply(ficp_stepper* sh, int32_t allow_reflection, double* T9) {
+    if (!sh || !T9) { set_error("ficp_stepper_fit_apply: null pointer"); return kErrInvalid; }
+    Stepper* S = reinterpret_cast<Stepper*>(sh);
+    if (S->k_last <= 0) { set_error("ficp_stepper_fit_apply: the last pass kept no rows"); return kErrInvalid; }
+    int rc;
+    if ((rc = launch_fit_rigid2d(S->d_src, S->md, S->d_corr, S->md, S->d_order, (int)S->k_last, allow_reflection, S->d_T, 0))) return rc;
+    if ((rc = launch_apply_xy(S->d_src, S->d_src2, S->n, S->md, S->d_T, 0))) return rc;
+    std::swap(S->d_src, S->d_src2);
+    FICP_CUDA(cudaMemcpy(T9, S->d_T, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+int ficp_stepper_read_xy(ficp_stepper* sh, double* xy_out) {
+    if (!sh || !xy_out) { set_error("ficp_stepper_read_xy: null pointer"); return kErrInvalid; }
+    Stepper* S = reinterpret_cast<Stepper*>(sh);
+    if (S->md == 2) {
+        FICP_CUDA(cudaMemcpy(xy_out, S->d_src, sizeof(double) * 2 * (size_t)S->n, cudaMemcpyDeviceToHost));
+        return kOk;
+    }
+    std::vector<double> rows((size_t)S->n * S->md);
+    FICP_CUDA(cudaMemcpy(rows.data(), S->d_src, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < S->n; ++i) { xy_out[2 * i] = rows[(size_t)i * S->md]; xy_out[2 * i + 1] = rows[(size_t)i * S->md + 1]; }
+    return kOk;
+}
+
+void ficp_stepper_destroy(ficp_stepper* sh) { delete reinterpret_cast<Stepper*>(sh); }
+
 // ------------------------------------------------------------------------------------------ batch
 int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld, int32_t use_z,
                       const int64_t* plot_offsets, int64_t n_plots, const double* centres, const double* hyp,

@@ -94,6 +94,9 @@ constexpr int kSelectLargeMaxN = 1 << 24;
 int launch_select_fraction(const double* d_src, int ld_s, const double* d_corr, int ld_c, const double* d_dist,
                            int n, int md, const double* d_weights, int fixed_k, long long* d_k_out,
                            double* d_frmsd_out, int* d_order_out, cudaStream_t stream);
+int launch_inverse_perm(const GridView& v, int* d_inv, cudaStream_t stream);
+int launch_gather_grid_rows(const GridView& v, bool z3, const int* d_inv, const int* d_idx, long long n, double* d_out,
+                            cudaStream_t stream);
 int launch_fit_rigid2d(const double* d_src, int ld_s, const double* d_tgt, int ld_t, const int* d_sel, int k,
                        int allow_reflection, double* d_T9, cudaStream_t stream);
 int launch_apply_xy(const double* d_in, double* d_out, long long n, int ld, const double* d_T9, cudaStream_t stream);

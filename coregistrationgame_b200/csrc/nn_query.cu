@@ -33,6 +33,25 @@ __global__ void __launch_bounds__(128) nn_query_kernel(GridView v, const double*
     if (d2out) d2out[i] = (pos >= 0) ? best : __longlong_as_double(0x7FF8000000000000LL);
 }
 
+// position of every original target row in the cell-sorted grid (the stepper gathers `target[idx]` from the grid's own
+// copies of the coordinates - the same bits - instead of keeping a second copy of the target on the device)
+__global__ void __launch_bounds__(256) inverse_perm_kernel(GridView v, int* __restrict__ inv) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p < v.m) inv[grid_orig(v, p)] = (int)p;
+}
+template <bool Z3>
+__global__ void __launch_bounds__(256) gather_grid_rows_kernel(GridView v, const int* __restrict__ inv, const int* __restrict__ idx,
+                                                               long long n, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = inv[idx[i]];
+    const double2 xy = grid_xy(v, p);
+    constexpr int md = Z3 ? 3 : 2;
+    out[i * md] = xy.x;
+    out[i * md + 1] = xy.y;
+    if (Z3) out[i * md + 2] = grid_z(v, p);
+}
+
 // Greedy match-and-remove (replaces CHMPlot.remove_matches, chm_plot.py:223-285): the plot's
 // trees are visited IN ORDER; each takes its nearest remaining CHM point and removes it when the distance is below
 // the tree's threshold.  The order dependence makes it sequential per plot: one thread per plot, plots in parallel.
@@ -115,6 +134,23 @@ int measure_l2_read_gbs(size_t bytes, int iters, double* gbs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
     *gbs = (double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
+    return kOk;
+}
+
+int launch_inverse_perm(const GridView& v, int* d_inv, cudaStream_t stream) {
+    if (v.m <= 0) return kOk;
+    inverse_perm_kernel<<<(unsigned)((v.m + 255) / 256), 256, 0, stream>>>(v, d_inv);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
+int launch_gather_grid_rows(const GridView& v, bool z3, const int* d_inv, const int* d_idx, long long n, double* d_out,
+                            cudaStream_t stream) {
+    if (n <= 0) return kOk;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (z3) gather_grid_rows_kernel<true><<<nb, 256, 0, stream>>>(v, d_inv, d_idx, n, d_out);
+    else gather_grid_rows_kernel<false><<<nb, 256, 0, stream>>>(v, d_inv, d_idx, n, d_out);
+    FICP_CUDA(cudaGetLastError());
     return kOk;
 }
 

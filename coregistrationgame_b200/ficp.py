@@ -167,10 +167,7 @@ class FractionalICP:
             raise NotImplementedError(f"plots above {_STEPWISE_MAX_N} rows are not supported by the stage kernels "
                                       f"(got {n}); split the plot")
         if n > _KERNEL_MAX_N:
-            for lam in lambdas:
-                self.lambda_val = lam
-                self._iterate_stepwise()
-            return self.source
+            return self._run_stages_resident(lambdas)
         index, _ = self._target_index(self.target)
         batch = IcpBatch(index, [self.source], IDENTITY_HYPOTHESIS, centres=np.zeros((1, 2)),
                          lambda_val=lambdas[0], stage2_lambda=(lambdas[1] if len(lambdas) > 1 else None),
@@ -189,6 +186,55 @@ class FractionalICP:
         self.transform_ = step @ self.transform_
         self.frmsd_, self.rmse_, self.k_ = float(row["frmsd"]), float(row["rmse"]), int(row["k"])
         self.n_passes_ += int(row["passes"])
+        return self.source
+
+    def _run_stages_resident(self, lambdas):
+        """Plots above the persistent kernels' 1024-tree limit: the loop of ficp.py:122-147 driven from here pass by pass
+        (the convergence test stays in the reference's own expressions) over arrays that stay on the device
+        (``ficp_stepper_*``).  Same stage kernels on the same values as `_iterate_stepwise` - same bits - without its six
+        host round trips per pass."""
+        lib = _lib.load()
+        _lib.require_device()
+        n, md = len(self.source), self.match_dims
+        index, _ = self._target_index(self.target)
+        src = self._xyz_or_xy(self.source)
+        h = C.c_void_p()
+        _lib.check(lib.ficp_stepper_create(index.handle, _lib.ptr(src), n, md, md, C.byref(h)), "ficp_stepper_create")
+        k, ss = C.c_int64(0), C.c_double(0.0)
+        t9 = np.empty(9, dtype=np.float64)
+
+        def one_pass():
+            _lib.check(lib.ficp_stepper_pass(h, 0, C.byref(k), C.byref(ss)), "ficp_stepper_pass")
+            self.n_passes_ += 1
+            if k.value == 0:
+                return 0, float("inf")
+            frac = k.value / n
+            rmse = np.sqrt(ss.value / k.value)                       # the expressions of frmsd(), ficp.py:54-60
+            self.rmse_ = float(rmse)
+            return int(k.value), (1.0 / (frac ** self.lambda_val)) * rmse
+        try:
+            for lam in lambdas:
+                self.lambda_val = lam
+                w = frmsd_weights(n, lam)
+                _lib.check(lib.ficp_stepper_set_weights(h, _lib.ptr(w)), "ficp_stepper_set_weights")
+                kk, score = one_pass()
+                if kk == 0:
+                    continue
+                for _ in range(self.max_iterations):
+                    _lib.check(lib.ficp_stepper_fit_apply(h, int(bool(self.allow_reflection)), _lib.ptr(t9)), "ficp_stepper_fit_apply")
+                    self.transform_ = t9.reshape(3, 3).copy() @ self.transform_
+                    kk, new_score = one_pass()
+                    self.frmsd_, self.k_ = float(new_score), int(kk)
+                    if score - new_score <= self.threshold or kk == 0:
+                        break
+                    score = new_score
+            xy = np.empty((n, 2), dtype=np.float64)
+            _lib.check(lib.ficp_stepper_read_xy(h, _lib.ptr(xy)), "ficp_stepper_read_xy")
+        finally:
+            lib.ficp_stepper_destroy(h)
+        moved = self.source.copy()
+        moved[:, :2] = xy
+        self.source = moved
         return self.source
 
     def _pass_stepwise(self):

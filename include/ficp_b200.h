@@ -161,6 +161,24 @@ FICP_API int ficp_apply_xy(const double* in_host, double* out_host, int64_t n, i
 FICP_API int ficp_sumsq(const double* a_host, int32_t ld_a, const double* b_host, int32_t ld_b, int64_t k, int32_t md,
                double* out);
 
+/* ---- plots above the persistent kernels' 1024-tree limit: the loop of ficp.py:122-147 driven pass by pass from the host
+ * (which keeps the convergence test in the reference's own expressions) over arrays that stay on the device.  Each step
+ * runs the stage kernels above on the same values in the same order as the host-buffer entry points - same bits.
+ *   create        uploads columns 0..md-1 of the plot; `target[idx]` is gathered from the index's own copy of the target
+ *   set_weights   FRMSD weights of the stage (n doubles, 1/((k/n)**lambda), as for ficp_select_fraction)
+ *   pass          NN of the current positions + `target[idx]` + trim order + k (ficp.py:65-86, :123-124); sumsq_out = sum
+ *                 of squared residuals over the k trimmed rows (the sum inside frmsd, ficp.py:58-59); k_out = 0: none kept
+ *   fit_apply     compute_optimal_transform_2d on those rows + apply_transform_2d_xy_only (ficp.py:137-139); T9 = the step
+ *   read_xy       current XY of the plot (n x 2) */
+typedef struct ficp_stepper ficp_stepper;
+FICP_API int ficp_stepper_create(const ficp_target* t, const double* src_host, int64_t n, int32_t ld_s, int32_t md,
+                        ficp_stepper** out);
+FICP_API int ficp_stepper_set_weights(ficp_stepper* s, const double* weights_host);
+FICP_API int ficp_stepper_pass(ficp_stepper* s, int64_t fixed_k, int64_t* k_out, double* sumsq_out);
+FICP_API int ficp_stepper_fit_apply(ficp_stepper* s, int32_t allow_reflection, double* T9);
+FICP_API int ficp_stepper_read_xy(ficp_stepper* s, double* xy_out);
+FICP_API void ficp_stepper_destroy(ficp_stepper* s);
+
 /* ---- kernel 4: persistent batched ICP.  Replaces _iterate()/run() (ficp.py:122-154), batched over
  * plots and start-pose hypotheses.
  *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1])

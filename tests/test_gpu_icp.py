@@ -255,6 +255,30 @@ def test_large_plot_uses_stepwise_path(gpu):
     np.testing.assert_allclose(out, ref, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,dims,extra", [(1500, 2, 0), (3000, 3, 2), (9000, 3, 0)])
+def test_device_resident_stepper_equals_host_stepped_path(gpu, n, dims, extra):
+    """Plots above 1024 trees: run() drives the loop over device-resident arrays (ficp_stepper_*); the host-stepped path over
+    the host-buffer stage entry points (`_iterate_stepwise`) runs the same kernels on the same values - every observable
+    must agree BIT FOR BIT, incl. the extra columns the transform never touches and the passes taken."""
+    from ficp import FractionalICP
+    from coregistrationgame_b200.batch import STAGE2_LAMBDA
+    tgt, plots, _ = orc.synthetic_scene(60000, n, seed=21 + n, dims=dims, hidden_pose=False)
+    src = orc.pre_transform(plots[0], np.r_[orc.hypothesis_matrix(0.7, 0).ravel(), 0.4, -0.3], plots[0][:, :2].mean(0))
+    if extra:
+        src = np.column_stack([src, np.random.default_rng(n).normal(size=(n, extra))])
+    a = FractionalICP(src, tgt, max_iterations=25)
+    out_a = a.run()
+    b = FractionalICP(src, tgt, max_iterations=25)
+    for lam in (3.0, STAGE2_LAMBDA[b.match_dims]):
+        b.lambda_val = lam
+        b._iterate_stepwise()
+    assert a.n_passes_ == b.n_passes_ and a.k_ == b.k_ and a.n_passes_ >= 4
+    np.testing.assert_array_equal(out_a, b.source)
+    np.testing.assert_array_equal(a.transform_, b.transform_)
+    assert a.frmsd_ == b.frmsd_
+    np.testing.assert_array_equal(out_a[:, 2:], src[:, 2:])
+
+
 def test_determinism_bitwise(gpu):
     from coregistrationgame_b200 import register_batch
     tgt, plots, _ = orc.synthetic_scene(30000, 200, seed=3, dims=3, n_plots=4, hidden_pose=True)
