@@ -678,11 +678,24 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                 }
                 if (fit_useful && warp == 0) {
                     FitSums fs = fit_zero();
+#ifndef FICP_TEAM_BRANCHFREE_FIT
+#define FICP_TEAM_BRANCHFREE_FIT 1
+#endif
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         const int i = e * 32 + lane;
+#if FICP_TEAM_BRANCHFREE_FIT
+                        // no branch around the nine additions (the compiler can then keep the next trees' loads in flight): a
+                        // tree outside the subset contributes exact zeros - s + 0.0 and fma(0.0, v, s) return s bit for bit
+                        // (the sums start at +0.0 and x + (-x) rounds to +0.0, so no sum is ever -0.0; v is finite) - and
+                        // its slots, which may hold anything, are never used in arithmetic
+                        const bool in = finl[i] != 0;
+                        const double ux = in ? f_ux[i] : 0.0, uy = in ? f_uy[i] : 0.0, vx = in ? f_vx[i] : 0.0, vy = in ? f_vy[i] : 0.0;
+                        fit_acc(fs, ux, uy, vx, vy);
+#else
                         const double ux = f_ux[i], uy = f_uy[i], vx = f_vx[i], vy = f_vy[i];
                         if (finl[i]) fit_acc(fs, ux, uy, vx, vy);
+#endif
                     }
                     fit_reduce(fs);
                     PHASE(9);
