@@ -397,8 +397,11 @@ def run_b200(args):
         dist.barrier()
     t0 = time.perf_counter()
     e2e_passes = 0
+    e2e_ms_list = []
     for _ in range(e2e_steps):
-        r = e2e_step()
+        ts = time.perf_counter()
+        r = e2e_step()                      # synchronous: the winners are on the host when it returns
+        e2e_ms_list.append((time.perf_counter() - ts) * 1e3)
         e2e_passes += r["passes_global"]
     torch.cuda.synchronize()
     if world > 1:
@@ -657,7 +660,10 @@ def run_b200(args):
                            "device": props},
                 "nn_queries_per_s": value * args.trees,
                 "e2e": {"value": e2e_val, "unit": "hyp-iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "api": "register_batch_distributed" if world > 1 else "register_batch"},
+                        "steps": e2e_steps, "api": "register_batch_distributed" if world > 1 else "register_batch",
+                        "ms_per_step_rank0": [round(x, 3) for x in e2e_ms_list],
+                        "note": "value = all steps' hypothesis-iterations / wall clock of the whole loop (max over ranks); the per-step list "
+                                "(rank 0) shows whether one slow step - a host or PCIe hiccup on the box - moved it"},
                 "e2e_resident_index": e2e_res,
                 "gpu_launches": args.steps * 2,      # per timed step: the persistent ICP kernel + the pack kernel of the exchange
                 "roofline": roofline, "clocks": sampler.summary(),
