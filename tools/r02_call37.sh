@@ -1,7 +1,7 @@
 #!/bin/bash
-# GPU call 37 (1 GPU): CTA-per-ICP kernel, fit sums without the branch (default) vs with it (brfit): probe + bit identity
+# GPU call 37 (1 GPU): CTA-per-ICP kernel A/B of two builds (VARIANTS="a b a b"): probe + bit identity
 mkdir -p gpurun_out
-for v in b200 brfit b200 brfit; do
+for v in ${VARIANTS:-b200 oldsort b200 oldsort}; do
   FICP_B200_LIB=$PWD/coregistrationgame_b200/libficp_$v.so timeout 200 python tools/strong_scaling_probe.py --worlds 1,4,8 --kernels warp,cta --reps 9 > gpurun_out/r02_c37_probe_$v.jsonl 2> gpurun_out/r02_c37_probe.err
   python - $v <<'PY'
 import json, sys
