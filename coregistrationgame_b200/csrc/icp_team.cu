@@ -194,12 +194,27 @@ __device__ __forceinline__ WindowAcc team_window(const TeamPtrs& tp, const int* 
     return WindowAcc{tp.w_xy, tp.w_z, tp.w_cell, tp.rowoff, tp.rowdelta, G.orig, G.rec, wx0, wy0, wx1, wy1, wx1 - wx0, wy1 - wy0};
 }
 
-// min / lexicographic arg-min over the NW per-warp partials in shared memory, by every warp for itself (5 shuffles)
-__device__ __forceinline__ double warp_min_of(const double* red, int nw, int lane) {
-    double v = (lane < nw) ? red[lane] : kInf;
+// Minimum over the warp of a value that is >= +0 and not NaN (+inf allowed): such doubles order like their bit patterns,
+// so two integer warp reductions (REDUX: high words, then low words among the lanes holding the smallest high word) replace
+// five shuffle + fmin steps.  The minimum is order-free: same bits as the butterfly.
+#ifndef FICP_TEAM_REDUX_MIN
+#define FICP_TEAM_REDUX_MIN 1
+#endif
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+#if FICP_TEAM_REDUX_MIN
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const unsigned ml = __reduce_min_sync(kFull, (hi == mh) ? lo : 0xFFFFFFFFu);
+    return __hiloint2double((int)mh, (int)ml);
+#else
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
     return v;
+#endif
+}
+// min over the NW per-warp partials in shared memory, by every warp for itself
+__device__ __forceinline__ double warp_min_of(const double* red, int nw, int lane) {
+    return warp_min_nonneg((lane < nw) ? red[lane] : kInf);
 }
 
 // T threads work on one ICP of NP = T * TPT tree slots (TPT trees per thread: slot tid + kk * T).  TPT = 1 is the
@@ -578,8 +593,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                         g[kk] = (p < n) ? __dmul_rn(S[kk], sg[r * 32 + lp]) : kInf;
                         gb = fmin(gb, g[kk]);
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) gb = fmin(gb, __shfl_xor_sync(kFull, gb, o));
+                    gb = warp_min_nonneg(gb);   // S_k >= 0 and the weights are positive: never negative, never NaN
                     if (lane == 0) M->red_a[warp] = gb;
                     __syncthreads();
                     const double gbest = warp_min_of(M->red_a, NW, lane);
