@@ -182,6 +182,68 @@ __device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* s
     return false;
 }
 
+// Skip test of one round (icp_shared.cuh: nn_test_round - the warp kernel's form, same arithmetic per tree), without a
+// branch: every lane evaluates the test on a safe operand (a tree slot past the plot, or one whose code cannot be tested,
+// reads the plot's first source row instead of a window point) and only the stores are predicated.  Straight-line code lets
+// the compiler overlap the dependent chains of the TWO rounds a warp has (FICP_TEAM_TPT = 2) instead of walking them one
+// after the other - each is ~150 instructions at one issue per ~5 cycles.
+#ifndef FICP_TEAM_BRANCHFREE_TEST
+#define FICP_TEAM_BRANCHFREE_TEST 1
+#endif
+template <bool Z3>
+__device__ __forceinline__ int team_test_round(const WindowAcc& W, const PlotCtx& pc, const Pose& P, const Pose& D,
+                                               double* __restrict__ sd2, int* __restrict__ snn, __half* __restrict__ ssl, int e,
+                                               int lane) {
+    const int i = e * 32 + lane;
+    const bool live = i < pc.n;
+    const int ii = live ? i : 0;
+    const int code = snn[ii];
+    const float s0 = __half2float(ssl[ii]);
+    const bool test = live && code >= 0 && s0 > 0.f;
+    const double2 u = pc.s_u[ii];
+    const double ex = D.m00 * u.x + D.m01 * u.y + D.cx;
+    const double ey = D.m10 * u.x + D.m11 * u.y + D.cy;
+    const double pad = 1e-14 * ((fabs(P.cx) + fabs(P.cy)) + (fabs(u.x) + fabs(u.y)));
+    const float move = __fadd_ru(__fsqrt_ru(__double2float_ru(ex * ex + ey * ey)), __double2float_ru(pad));
+    const float s1 = __fmul_rd(__fsub_rd(s0, move), 0.99999904632568359375f);
+    const __half sh = __float2half_rd(fmaxf(s1, 0.f));
+    const float s = __half2float(sh);
+    double qx, qy;
+    pose_apply(P, u, qx, qy);
+    const double qz = Z3 ? pc.s_z[ii] : 0.0;
+    const int p1 = code & 0xFFFF, p2 = code >> 16;
+    // operands of the two candidate distances: window points when the test applies, else the (always present) source row 0
+    const double2* a1 = test ? (W.xy + p1) : pc.s_u;
+    const double2* a2 = test ? (W.xy + p2) : pc.s_u;
+    const double2 t1 = *a1, t2 = *a2;
+    double z1 = 0.0, z2 = 0.0;
+    if (Z3) {
+        const double* b1 = test ? (W.z + p1) : pc.s_z;
+        const double* b2 = test ? (W.z + p2) : pc.s_z;
+        z1 = *b1; z2 = *b2;
+    }
+    double d1, dr;
+    {
+        const double dx = dsub(qx, t1.x), dy = dsub(qy, t1.y);
+        d1 = dadd(dmul(dx, dx), dmul(dy, dy));
+        if (Z3) { const double dz = dsub(qz, z1); d1 = dadd(d1, dmul(dz, dz)); }
+    }
+    {
+        const double dx = dsub(qx, t2.x), dy = dsub(qy, t2.y);
+        dr = dadd(dmul(dx, dx), dmul(dy, dy));
+        if (Z3) { const double dz = dsub(qz, z2); dr = dadd(dr, dmul(dz, dz)); }
+    }
+    const bool swap = dr < d1;
+    const double dmin = swap ? dr : d1;
+    const bool settled = test && dmin < (double)s * (double)s && (p2 == p1 || d1 != dr);
+    if (test) ssl[i] = sh;
+    if (settled) {
+        sd2[i] = dmin;
+        if (swap) snn[i] = p2 | (p1 << 16);
+    }
+    return (live && !settled) ? i : -1;
+}
+
 // The pose is CTA-uniform state: it lives in shared memory (TeamMisc::pose) and is read where a phase needs it - held in
 // registers across the whole pass it cost every thread 24 registers, and the kernel is compiled for 64.
 __device__ __forceinline__ Pose ld_pose(const double* p) { return Pose{p[0], p[1], p[2], p[3], p[4], p[5]}; }
@@ -377,6 +439,20 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     const WindowAcc Wt = team_window(tp, M->win, G_);
                     const PlotCtx pct{s_u, s_z, n, fixed_k, 0.0, 0.0};
                     const Pose pose_t = ld_pose(M->pose[pb]), dpose_t = ld_pose(M->pose[pb] + 6);
+#if FICP_TEAM_BRANCHFREE_TEST
+                    if (E == 2 * NW) {
+                        // both rounds of the warp side by side, one reservation in the search list for the two
+                        const int need0 = team_test_round<Z3>(Wt, pct, pose_t, dpose_t, sd2, snn, ssl, warp, lane);
+                        const int need1 = team_test_round<Z3>(Wt, pct, pose_t, dpose_t, sd2, snn, ssl, warp + NW, lane);
+                        const unsigned m0 = __ballot_sync(kFull, need0 >= 0), m1 = __ballot_sync(kFull, need1 >= 0);
+                        const int c0 = __popc(m0);
+                        int base = 0;
+                        if (lane == 0 && (m0 | m1)) base = atomicAdd(&M->nlist, c0 + __popc(m1));
+                        base = __shfl_sync(kFull, base, 0);
+                        if (need0 >= 0) list[base + __popc(m0 & lt_mask)] = (unsigned short)need0;
+                        if (need1 >= 0) list[base + c0 + __popc(m1 & lt_mask)] = (unsigned short)need1;
+                    } else
+#endif
 #pragma unroll 1
                     for (int e = warp; e < E; e += NW) {
                         const int need = nn_test_round<Z3>(Wt, pct, pose_t, dpose_t, sd2, snn, ssl, e, lane);
