@@ -182,6 +182,112 @@ __device__ __forceinline__ bool team_repair_order(double* sdd, unsigned short* s
     return false;
 }
 
+// Group search (icp_shared.cuh: nn_search_group - same candidates, same folds in the same order, same result), arranged for
+// the latency of ONE search, which is what a pass of this kernel waits for: the column runs of the three rows are worked out
+// first and their row-table lookups issued together on safe operands (no branch around each), and the candidate loop scores
+// two candidates per iteration (two independent load / distance chains in flight; the odd tail repeats its last candidate,
+// which the top-3 bookkeeping ignores).
+#ifndef FICP_TEAM_FAST_GROUP
+#define FICP_TEAM_FAST_GROUP 1
+#endif
+template <bool Z3>
+__device__ __forceinline__ int team_search_group(const WindowAcc& acc, const GridGeom& g, bool active, double qx, double qy,
+                                                 double qz, int prev, int G, int sub, double& best, int& bestpos, int& cx,
+                                                 int& cy, int& lb_hi, int& pos2) {
+#if !FICP_TEAM_FAST_GROUP
+    return nn_search_group<Z3>(acc, g, active, qx, qy, qz, prev, G, sub, best, bestpos, cx, cy, lb_hi, pos2);
+#else
+    int status = 0, lb = kHiInf;
+    best = kInf; bestpos = -1; pos2 = -1; cx = 0; cy = 0;
+    lb_hi = kHiInf;
+    if (__ballot_sync(kFull, active) == 0u) return 0;   // a warp without a query has nothing to merge either
+    Top3 top = top3_empty();
+    if (active) {
+        cx = clamp_cell((qx - g.x0) * g.inv_h, g.gw);
+        cy = clamp_cell((qy - g.y0) * g.inv_h, g.gh);
+        const int xl = (cx > 0) ? cx - 1 : 0, xh = (cx < g.gw - 1) ? cx + 1 : g.gw - 1;
+        const int yl = (cy > 0) ? cy - 1 : 0, yh = (cy < g.gh - 1) ? cy + 1 : g.gh - 1;
+        if (!acc.covers(xl, xh, yl, yh)) {
+            status = 1;
+        } else {
+            const double seed_d2 = (prev >= 0) ? nn_dist2<Z3>(acc, prev, qx, qy, qz) : kInf;
+            double gx[3], gy[3];
+            nn_block3_gaps(g, qx, qy, cx, cy, gx, gy);
+            const double bound = seed_d2 * FICP_PRUNE_PAD;
+            int xa[3], xb[3];
+            bool has[3];
+#pragma unroll
+            for (int ry = 0; ry < 3; ++ry) {
+                const int y = cy - 1 + ry;
+                const bool rowok = (y >= yl && y <= yh);
+                xa[ry] = cx + 2;
+                xb[ry] = cx - 2;
+#pragma unroll
+                for (int rx = 0; rx < 3; ++rx) {
+                    const int x = cx - 1 + rx;
+                    if (rowok && x >= xl && x <= xh) {
+                        const double gap2 = gx[rx] + gy[ry];
+                        if (gap2 <= bound) {
+                            if (x < xa[ry]) xa[ry] = x;
+                            xb[ry] = x;
+                        } else {
+                            const int c = d_hi(gap2);
+                            lb = (c < lb) ? c : lb;
+                        }
+                    }
+                }
+                has[ry] = rowok && xa[ry] <= xb[ry];
+            }
+            int s[3], n[3];
+            bool seed_in = false;
+#pragma unroll
+            for (int ry = 0; ry < 3; ++ry) {
+                // a row without a run looks up the query's own cell (always inside the window) and counts nothing
+                int s0, e0;
+                acc.seg(has[ry] ? cy - 1 + ry : cy, has[ry] ? xa[ry] : cx, has[ry] ? xb[ry] : cx, s0, e0);
+                s[ry] = has[ry] ? s0 : 0;
+                n[ry] = has[ry] ? e0 - s0 : 0;
+                seed_in = seed_in || (has[ry] && prev >= s0 && prev < e0);
+            }
+            if (prev >= 0 && !seed_in && sub == 0) nn_fold_track_notie(prev, seed_d2, best, bestpos, top);
+            const int n01 = n[0] + n[1], total = n01 + n[2];
+            const int o1 = s[1] - n[0], o2 = s[2] - n01;
+            for (int t = sub; t < total; t += 2 * G) {
+                const int t1 = (t + G < total) ? t + G : t;
+                const int j0 = t + ((t < n[0]) ? s[0] : (t < n01) ? o1 : o2);
+                const int j1 = t1 + ((t1 < n[0]) ? s[0] : (t1 < n01) ? o1 : o2);
+                const double da = nn_dist2<Z3>(acc, j0, qx, qy, qz);
+                const double db = nn_dist2<Z3>(acc, j1, qx, qy, qz);
+                nn_fold_track_notie(j0, da, best, bestpos, top);
+                nn_fold_track_notie(j1, db, best, bestpos, top);
+            }
+        }
+    }
+    __syncwarp();
+    for (int o = 1; o < G; o <<= 1) {
+        const double ob = __shfl_xor_sync(kFull, best, o);
+        const int op = __shfl_xor_sync(kFull, bestpos, o);
+        const int oc1 = __shfl_xor_sync(kFull, top.c1, o), oc2 = __shfl_xor_sync(kFull, top.c2, o);
+        const int oc3 = __shfl_xor_sync(kFull, top.c3, o);
+        const int op1 = __shfl_xor_sync(kFull, top.p1, o), op2 = __shfl_xor_sync(kFull, top.p2, o);
+        const bool lt = ob < best;
+        best = lt ? ob : best;
+        bestpos = lt ? op : bestpos;
+        top3_insert(top, oc1, op1);
+        top3_insert(top, oc2, op2);
+        top3_insert(top, oc3, -1);   // can only land in the third slot (oc3 >= oc2 >= what slot 2 now holds)
+    }
+    if (active && status == 0) {
+        const int cb = d_hi(best);
+        if (bestpos >= 0 && top.c1 == cb && (top.p1 != bestpos || top.c2 == cb)) status = 2;
+        const int c = top3_finish(top, bestpos, pos2);
+        lb = (c < lb) ? c : lb;
+    }
+    lb_hi = lb;
+    return status;
+#endif
+}
+
 // Skip test of one round (icp_shared.cuh: nn_test_round - the warp kernel's form, same arithmetic per tree), without a
 // branch: every lane evaluates the test on a safe operand (a tree slot past the plot, or one whose code cannot be tested,
 // reads the plot's first source row instead of a window point) and only the stores are predicated.  Straight-line code lets
@@ -499,7 +605,7 @@ icp_team_kernel(const __grid_constant__ IcpParams P) {
                     }
                     double best;
                     int pos, cx, cy, lb_hi, pos2;
-                    const int status = nn_search_group<Z3>(W, G_.g, active, qx, qy, qz, prev, G, sub, best, pos, cx, cy, lb_hi, pos2);
+                    const int status = team_search_group<Z3>(W, G_.g, active, qx, qy, qz, prev, G, sub, best, pos, cx, cy, lb_hi, pos2);
                     PHASE(13);
                     int defer = -1, ser = -1;
                     if (active && sub == 0) {
