@@ -659,7 +659,9 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // trees (e == 1) are one warp either way.  Auto: below kCtaAutoIcpsPerSm ICPs per SM (measured, profiles/r02_summary.md).
     // One start pose per plot (config 4) leaves the warp-per-ICP kernel one warp per CTA: the CTA-per-ICP kernel is ahead a
     // little further there (measured at 8.4 ICPs per SM: 40.7 vs 37.6 M hyp-iter/s, profiles/r02_bench_c4_*.json).
-    const long long kCtaAutoIcpsPerSm = (n_hyp_local == 1) ? 12 : 8;
+    // (round 2, after the latency work on the CTA kernel: 2048 ICPs = 13.8 per SM 3.06 vs 3.26 ms, 1366 ICPs 2.31 vs 3.18 ms,
+    // 4096 ICPs = 27.7 per SM 5.31 vs 4.63 ms - profiles/r02_strong_scaling_probe_crossover.jsonl)
+    const long long kCtaAutoIcpsPerSm = 14;
     const bool cta_mode = (e >= 2) && (prm->cta_per_icp == 2 || (prm->cta_per_icp == 0 && prm->team_warps == 0 && prm->no_helpers == 0 &&
                                                                  prm->warps_per_cta == 0 && n_icps_all <= kCtaAutoIcpsPerSm * sms));
     // Elastic kernel: warps without an ICP of their own help the ICPs in flight in their CTA.  It pays while the

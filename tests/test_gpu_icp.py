@@ -621,11 +621,11 @@ def test_packed_world_translation_matches_host_composition(gpu):
 
 
 def test_planner_picks_the_kernel_shape_by_batch_size(gpu):
-    """Auto launch shape (capi.cu): CTA-per-ICP below 8 ICPs per SM (12 when every plot has one start pose: the
-    warp-per-ICP kernel would run one warp per CTA), warp-per-ICP above; plots of <= 32 trees are one warp either way."""
+    """Auto launch shape (capi.cu): CTA-per-ICP up to 14 ICPs per SM, warp-per-ICP above; plots of <= 32 trees are one warp
+    either way."""
     from coregistrationgame_b200 import IcpBatch, TargetIndex, _lib
     sms = _lib.device_props()["sms"]
-    tgt, plots, _ = orc.synthetic_scene(60000, 40, seed=5, dims=3, n_plots=13 * sms + 7, hidden_pose=False)
+    tgt, plots, _ = orc.synthetic_scene(60000, 40, seed=5, dims=3, n_plots=15 * sms + 7, hidden_pose=False)
     ti = TargetIndex(tgt)
     ident = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
     hyp = orc.hypothesis_table(8, flips=(0, 1))
