@@ -395,6 +395,13 @@ def run_b200(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # like timeit: no cyclic garbage collection inside the timed loops (with torch imported a full collection walks millions of
+    # objects); collected once before instead.  (The 14-40 ms step that showed up once in ~25 end-to-end steps was not this but
+    # the memory pool growing when a handle's buffers were freed on another stream than they were allocated on - fixed in the
+    # library, ficp_internal.h release_stream; tools/e2e_outlier_probe.py: 118 steps, max 48.6 ms.)
+    import gc
+    gc.collect()
+    gc.disable()
     t0 = time.perf_counter()
     e2e_passes = 0
     e2e_ms_list = []
@@ -439,6 +446,8 @@ def run_b200(args):
             dist.all_reduce(rs, op=dist.ReduceOp.MAX)
         e2e_res = {"value": rp / float(rs.item()), "unit": "hyp-iter/s", "h2d_bytes_per_step": int(rr["h2d_bytes"]),
                    "d2h_bytes_per_step": int(rr["d2h_bytes"]), "what": "register_batch(..., index=resident TargetIndex)"}
+
+    gc.enable()
 
     # ---- the named config taken literally: ONE stand x all its hypotheses, strong-scaled over the ranks
     # (time to register a single stand; the headline above is the throughput of a batch of stands)

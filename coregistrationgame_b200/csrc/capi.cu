@@ -104,9 +104,10 @@ struct Batch {
     int* d_tr_k = nullptr;
     double* d_tr_f = nullptr;
     UseEvent used;  // last enqueued run / copy that touches the buffers below
+    cudaStream_t alloc_stream = nullptr;
     ~Batch() {
         used.wait();  // nothing in flight any more: the release below may be ordered on any stream
-        cudaStream_t s = cudaStreamPerThread;
+        cudaStream_t s = release_stream(alloc_stream);
         dev_free(d_tr_idx, s); dev_free(d_tr_d2, s); dev_free(d_tr_in, s); dev_free(d_tr_k, s); dev_free(d_tr_f, s);
         dev_free(d_src_u, s); dev_free(d_src_z, s); dev_free(d_plots, s); dev_free(d_hyp, s); dev_free(d_tabs, s);
         dev_free(d_results, s); dev_free(d_best, s); dev_free(d_final, s); dev_free(d_counters, s); dev_free(d_stats, s);
@@ -570,6 +571,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
 
     Batch* b = new Batch();
     struct Guard { Batch* b; bool armed = true; ~Guard() { if (armed) delete b; } } guard{b};
+    b->alloc_stream = s;
     b->tgt = t; b->n_plots = (int)n_plots; b->n_hyp = (int)n_hyp; b->n_hyp_local = n_hyp_local;
     b->rows = rows; b->z3 = z3; b->want_final = (want_final_xy != 0) && n_hyp_local == 1;
 

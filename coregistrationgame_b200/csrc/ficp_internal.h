@@ -33,6 +33,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // for it before releasing their buffers (see UseEvent), so destroy-after-enqueue on a non-blocking stream is safe.
 cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream);
 void dev_free(void* p, cudaStream_t stream);
+// Stream on which a handle releases its buffers once nothing is in flight (after UseEvent::wait).  Blocks freed on the stream
+// they were allocated on are reusable by the next allocation at once; freed on another stream the pool can only reuse them
+// opportunistically and now and then grows instead (measured: one end-to-end step in ~25 took 14-40 ms longer inside
+// ficp_target_create).  The legacy default stream - what callers pass unless they bring their own - always exists, so a handle
+// built on it frees on it; a handle built on a caller's stream (which may be gone by then) frees on the per-thread stream.
+inline cudaStream_t release_stream(cudaStream_t alloc_stream) { return alloc_stream == nullptr ? nullptr : cudaStreamPerThread; }
 template <class T>
 inline cudaError_t dev_alloc_t(T** p, size_t count, cudaStream_t stream) {
     return dev_alloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1), stream);
@@ -65,6 +71,7 @@ struct Target {
     float build_ms = 0.f;  // device time of the build kernels (CUDA events)
     long long max_cell_pts = 0;  // heaviest cell (diagnostic: skew of the target)
     mutable UseEvent used;  // last enqueued work that reads the index (queries, ICP batches)
+    cudaStream_t alloc_stream = nullptr;  // stream the buffers were allocated on (see release_stream)
 };
 
 // Builds the grid from row-major points (ld doubles per row; columns 0,1[,2]).  `pts` is a host

@@ -328,10 +328,11 @@ __global__ void __launch_bounds__(kT) heavy_cell_kernel(const BuildState* __rest
 void target_free(Target* t) {
     if (!t) return;
     t->used.wait();  // queries / batches enqueued on any stream have finished reading the index
-    dev_free(t->d_xy, cudaStreamPerThread);
-    dev_free(t->d_rec, cudaStreamPerThread);
-    dev_free(t->d_orig, cudaStreamPerThread);
-    dev_free(t->d_cell_start, cudaStreamPerThread);
+    const cudaStream_t rs = release_stream(t->alloc_stream);
+    dev_free(t->d_xy, rs);
+    dev_free(t->d_rec, rs);
+    dev_free(t->d_orig, rs);
+    dev_free(t->d_cell_start, rs);
     delete t;
 }
 
@@ -348,6 +349,7 @@ int target_build(const double* pts, int on_device, long long m, int ld, int use_
     }
     if (!(pts_per_cell > 0.0)) pts_per_cell = 2.0;
     Target* t = new Target();
+    t->alloc_stream = stream;
     t->m = m;
     t->has_z = use_z ? 1 : 0;
     t->pts_per_cell = pts_per_cell;
