@@ -169,20 +169,32 @@ class IcpBatch:
                  hyp_shard=(0, 1), want_final_xy=False, window_margin=-1.0, warps_per_cta=0, ctas_per_sm=0,
                  disable_window=False, team_warps=0, helpers=None, trace_passes=0, cta_per_icp=None, stream=None):
         lib = _lib.load()
-        if isinstance(sources, np.ndarray) and sources.ndim == 2:
-            sources = [sources]
-        srcs = [np.ascontiguousarray(np.asarray(s, dtype=np.float64)) for s in sources]
-        if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
-            raise ValueError("every plot must be a non-empty 2D array (N, D)")
-        ld = srcs[0].shape[1]
-        if any(s.shape[1] != ld for s in srcs):
-            raise ValueError("all plots must have the same number of columns")
+        if isinstance(sources, tuple) and len(sources) == 2 and isinstance(sources[0], np.ndarray) and sources[0].ndim == 2 \
+                and np.ndim(sources[1]) == 1:
+            # already stacked: (rows, offsets) - plot p owns rows[offsets[p]:offsets[p + 1]].  The form for thousands of plots:
+            # per-plot Python work (a list of 1250 arrays costs ~3 ms to check and stack) is what bounds config 4 end to end
+            rows, offs = sources
+            self.src = np.ascontiguousarray(np.asarray(rows, dtype=np.float64))
+            self.offsets = np.ascontiguousarray(np.asarray(offs, dtype=np.int64))
+            self.sizes = np.diff(self.offsets)
+            if self.offsets.size < 2 or self.offsets[0] != 0 or self.offsets[-1] != self.src.shape[0] or (self.sizes <= 0).any():
+                raise ValueError("offsets must start at 0, end at the number of rows and describe non-empty plots")
+            ld = self.src.shape[1]
+        else:
+            if isinstance(sources, np.ndarray) and sources.ndim == 2:
+                sources = [sources]
+            srcs = [np.ascontiguousarray(np.asarray(s, dtype=np.float64)) for s in sources]
+            if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
+                raise ValueError("every plot must be a non-empty 2D array (N, D)")
+            ld = srcs[0].shape[1]
+            if any(s.shape[1] != ld for s in srcs):
+                raise ValueError("all plots must have the same number of columns")
+            self.sizes = np.array([s.shape[0] for s in srcs], dtype=np.int64)
+            self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+            self.src = np.ascontiguousarray(np.vstack(srcs))
         self.index = index
         self.match_dims = 3 if (ld >= 3 and index.has_z) else 2
-        self.n_plots = len(srcs)
-        self.sizes = np.array([s.shape[0] for s in srcs], dtype=np.int64)
-        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
-        self.src = np.ascontiguousarray(np.vstack(srcs))
+        self.n_plots = int(self.sizes.shape[0])
         self.hyp = np.ascontiguousarray(IDENTITY_HYPOTHESIS if hyp_table is None else
                                         np.asarray(hyp_table, dtype=np.float64).reshape(-1, 6))
         if centres is None:

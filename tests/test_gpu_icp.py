@@ -620,6 +620,26 @@ def test_packed_world_translation_matches_host_composition(gpu):
     np.testing.assert_array_equal(a["best_transform"], b["best_transform"])
 
 
+def test_stacked_input_equals_list_of_plots(gpu):
+    """register_batch((rows, offsets), ...) - the input form for thousands of plots - gives exactly what the list of per-plot
+    arrays gives; malformed offsets are refused."""
+    from coregistrationgame_b200 import register_batch
+    tgt, plots, _ = orc.synthetic_scene(50000, 60, seed=8, dims=3, n_plots=37, hidden_pose=True)
+    plots = [p[: 40 + (i % 3) * 10] for i, p in enumerate(plots)]        # three size classes
+    hyp = orc.hypothesis_table(4, flips=(0, 1))
+    a = register_batch(plots, tgt, hyp)
+    rows = np.vstack(plots)
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in plots])])
+    b = register_batch((rows, offs), tgt, hyp)
+    np.testing.assert_array_equal(a["best_key"], b["best_key"])
+    np.testing.assert_array_equal(a["best_transform"], b["best_transform"])
+    assert _rows_equal_except_flags(a["hyp"], b["hyp"])
+    with pytest.raises(ValueError):
+        register_batch((rows, offs[:-1]), tgt, hyp)
+    with pytest.raises(ValueError):
+        register_batch((rows, np.r_[offs[:3], offs[2:]]), tgt, hyp)
+
+
 def test_planner_picks_the_kernel_shape_by_batch_size(gpu):
     """Auto launch shape (capi.cu): CTA-per-ICP up to 14 ICPs per SM, warp-per-ICP above; plots of <= 32 trees are one warp
     either way."""
