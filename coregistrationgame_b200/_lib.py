@@ -71,6 +71,8 @@ SIGNATURES = {
     "ficp_stepper_fit_apply": (c_i32, [c_vp, c_i32, c_vp]),
     "ficp_stepper_read_xy": (c_i32, [c_vp, c_vp]),
     "ficp_stepper_destroy": (None, [c_vp]),
+    "ficp_plot_centres": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "ficp_plot_geometry": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ficp_batch_create": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp,
                                   c_vp, c_i32, c_vp, P(BatchParams), c_i32, c_vp, P(c_vp)]),
     "ficp_batch_get_info": (c_i32, [c_vp, P(BatchInfo)]),

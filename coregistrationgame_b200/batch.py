@@ -50,20 +50,15 @@ IDENTITY_HYPOTHESIS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
 
 def plot_centres(src, offsets):
     """Centre of every plot = ``rows[:, :2].mean(axis=0)`` of its rows (what the oracle and the reference-side callers
-    compute), for ten thousand plots without ten thousand numpy calls: plots of equal size are reduced together through
-    a (plots, n, ld) view - the same additions in the same order, bit for bit (pinned by tests/test_host_cabi.py)."""
-    offsets = np.asarray(offsets, dtype=np.int64)
-    sizes = np.diff(offsets)
-    out = np.empty((sizes.shape[0], 2), dtype=np.float64)
-    if sizes.shape[0] and (sizes == sizes[0]).all():
-        n = int(sizes[0])
-        # einsum accumulates the rows in order, like `mean(axis=0)` of one plot (the strided `mean(axis=1)` does too, 5x slower)
-        out[...] = np.einsum("pnc->pc", src.reshape(sizes.shape[0], n, src.shape[1])[:, :, :2]) / n
-        return out
-    for n in np.unique(sizes):
-        who = np.nonzero(sizes == n)[0]
-        rows = offsets[who][:, None] + np.arange(int(n))[None, :]
-        out[who] = np.einsum("pnc->pc", src[rows][:, :, :2]) / int(n)
+    compute; `Plot.rotate_plot` / `coordinate_flip` turn about it, trees.py:201-222), for ten thousand plots without ten
+    thousand numpy calls: ``ficp_plot_centres`` adds the rows of a plot in order and divides once - the same additions in
+    the same order, bit for bit (pinned by tests/test_host_cabi.py) - on a few host threads (no device involved)."""
+    src = np.ascontiguousarray(np.asarray(src, dtype=np.float64))
+    offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+    out = np.empty((offsets.shape[0] - 1, 2), dtype=np.float64)
+    if out.shape[0]:
+        _lib.check(_lib.load().ficp_plot_centres(_lib.ptr(src), src.shape[1], _lib.ptr(offsets), out.shape[0], _lib.ptr(out)),
+                   "ficp_plot_centres")
     return out
 
 
@@ -183,15 +178,18 @@ class IcpBatch:
         else:
             if isinstance(sources, np.ndarray) and sources.ndim == 2:
                 sources = [sources]
-            srcs = [np.ascontiguousarray(np.asarray(s, dtype=np.float64)) for s in sources]
+            srcs = list(sources)
+            if not all(type(s) is np.ndarray and s.dtype == np.float64 for s in srcs):
+                srcs = [np.asarray(s, dtype=np.float64) for s in srcs]
             if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
                 raise ValueError("every plot must be a non-empty 2D array (N, D)")
             ld = srcs[0].shape[1]
-            if any(s.shape[1] != ld for s in srcs):
-                raise ValueError("all plots must have the same number of columns")
-            self.sizes = np.array([s.shape[0] for s in srcs], dtype=np.int64)
+            self.sizes = np.fromiter(map(len, srcs), dtype=np.int64, count=len(srcs))
             self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
-            self.src = np.ascontiguousarray(np.vstack(srcs))
+            try:
+                self.src = np.concatenate(srcs, axis=0)     # one C-contiguous copy; checks the column counts itself
+            except ValueError:
+                raise ValueError("all plots must have the same number of columns") from None
         self.index = index
         self.match_dims = 3 if (ld >= 3 and index.has_z) else 2
         self.n_plots = int(self.sizes.shape[0])
@@ -204,7 +202,7 @@ class IcpBatch:
         lam2 = STAGE2_LAMBDA[self.match_dims] if stage2_lambda is None else stage2_lambda
         self.lambdas = [lambda_val, lam2][: self.n_stages]
         # FRMSD weight tables, one per distinct plot size
-        uniq = sorted(set(int(n) for n in self.sizes))
+        uniq = np.unique(self.sizes).tolist()
         tab_of = {n: i for i, n in enumerate(uniq)}
         tabs, offs = [], [0]
         for n in uniq:

@@ -4,11 +4,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/ficp_b200.h"
 #include "ficp_internal.h"
+#include "batch_prep.h"
 
 namespace ficp {
 
@@ -526,6 +528,37 @@ int ficp_stepper_read_xy(ficp_stepper* sh, double* xy_out) {
 
 void ficp_stepper_destroy(ficp_stepper* sh) { delete reinterpret_cast<Stepper*>(sh); }
 
+// ------------------------------------------------------------------------------------------ host-side plot geometry
+static int check_offsets(const char* who, const int64_t* plot_offsets, int64_t n_plots) {
+    if (n_plots <= 0) { set_error(std::string(who) + ": need n_plots >= 1"); return kErrInvalid; }
+    for (int64_t p = 0; p < n_plots; ++p)
+        if (plot_offsets[p + 1] <= plot_offsets[p] || plot_offsets[p] < 0) { set_error(std::string(who) + ": empty plot or unsorted offsets"); return kErrInvalid; }
+    return kOk;
+}
+
+int ficp_plot_centres(const double* src_host, int32_t ld, const int64_t* plot_offsets, int64_t n_plots, double* centres_out) {
+    if (!src_host || !plot_offsets || !centres_out || ld < 2) { set_error("ficp_plot_centres: null pointer or ld < 2"); return kErrInvalid; }
+    if (int rc = check_offsets("ficp_plot_centres", plot_offsets, n_plots)) return rc;
+    plot_centres_host(src_host, ld, plot_offsets, n_plots, centres_out, host_threads_for(plot_offsets[n_plots] - plot_offsets[0]));
+    return kOk;
+}
+
+int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_z, const int64_t* plot_offsets, int64_t n_plots,
+                       const double* centres, double* u_out, double* z_out, double* ubar_out, double* rho_out) {
+    if (!src_host || !plot_offsets || !centres || !u_out || !ubar_out || !rho_out || (use_z && !z_out) || ld < 2 || (use_z && ld < 3)) {
+        set_error("ficp_plot_geometry: null pointer or too few columns");
+        return kErrInvalid;
+    }
+    if (int rc = check_offsets("ficp_plot_geometry", plot_offsets, n_plots)) return rc;
+    if (plot_offsets[0] != 0) { set_error("ficp_plot_geometry: offsets must start at 0"); return kErrInvalid; }
+    if (!plot_geometry_host(src_host, ld, use_z != 0, plot_offsets, n_plots, centres, u_out, z_out, ubar_out, rho_out,
+                            host_threads_for(plot_offsets[n_plots]))) {
+        set_error("source contains non-finite coordinates ('x' must be finite)");
+        return kErrNonFinite;
+    }
+    return kOk;
+}
+
 // ------------------------------------------------------------------------------------------ batch
 int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld, int32_t use_z,
                       const int64_t* plot_offsets, int64_t n_plots, const double* centres, const double* hyp,
@@ -585,9 +618,16 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     }
 
     // ---- per-plot geometry: local coordinates u = p - centre, shift point, footprint of the start poses
+    // (batch_prep.h: a few host threads over the plots - with one ICP per plot this pass is the end-to-end step)
     std::vector<PlotMeta> plots((size_t)n_plots);
-    std::vector<double2> h_u((size_t)rows);
-    std::vector<double> h_z(z3 ? (size_t)rows : 0);
+    std::unique_ptr<double[]> h_u(new double[2 * (size_t)rows]);          // (ux, uy) per row = the device's double2
+    std::unique_ptr<double[]> h_z(z3 ? new double[(size_t)rows] : nullptr);
+    std::unique_ptr<double[]> h_ubar(new double[2 * (size_t)n_plots]), h_rho(new double[(size_t)n_plots]);
+    if (!plot_geometry_host(src_host, ld, z3, plot_offsets, n_plots, centres, h_u.get(), h_z.get(), h_ubar.get(), h_rho.get(),
+                            host_threads_for(rows))) {
+        set_error("source contains non-finite coordinates ('x' must be finite)");
+        return kErrNonFinite;
+    }
     struct Foot { double rho, fx0, fx1, fy0, fy1; };
     std::vector<Foot> foot((size_t)n_plots);
     for (int64_t p = 0; p < n_plots; ++p) {
@@ -599,25 +639,9 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         pm.fixed_k = fixed_k ? fixed_k[p] : 0;
         pm.pad = 0;
         pm.wx0 = pm.wy0 = pm.wx1 = pm.wy1 = 0;
-        double sx = 0, sy = 0;
-        for (int i = 0; i < pm.n; ++i) {
-            const double* r = src_host + (size_t)(pm.off + i) * ld;
-            if (!std::isfinite(r[0]) || !std::isfinite(r[1]) || (z3 && !std::isfinite(r[2]))) {
-                set_error("source contains non-finite coordinates ('x' must be finite)");
-                return kErrNonFinite;
-            }
-            const double ux = r[0] - pm.cinx, uy = r[1] - pm.ciny;  // same single subtraction as the oracle
-            h_u[(size_t)(pm.off + i)] = make_double2(ux, uy);
-            if (z3) h_z[(size_t)(pm.off + i)] = r[2];
-            sx += ux; sy += uy;
-        }
-        pm.ubx = sx / pm.n; pm.uby = sy / pm.n;
+        pm.ubx = h_ubar[2 * (size_t)p]; pm.uby = h_ubar[2 * (size_t)p + 1];
         Foot& f = foot[(size_t)p];
-        f.rho = 0;
-        for (int i = 0; i < pm.n; ++i) {
-            const double2 u = h_u[(size_t)(pm.off + i)];
-            f.rho = std::max(f.rho, std::hypot(u.x - pm.ubx, u.y - pm.uby));
-        }
+        f.rho = h_rho[(size_t)p];
         // footprint of the plot centroid over all start poses: centre_h = M_h ubar + cin + d_h
         if (std::hypot(pm.ubx, pm.uby) <= 1e-9 * (f.rho + 1.0)) {
             f.fx0 = pm.cinx + dxmin; f.fx1 = pm.cinx + dxmax; f.fy0 = pm.ciny + dymin; f.fy1 = pm.ciny + dymax;
@@ -797,8 +821,8 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_k), sizeof(int) * recs, s));
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_f), sizeof(double) * recs, s));
     }
-    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.data(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
-    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.data(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.get(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.get(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * 6 * (size_t)n_hyp, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_tabs, h_tabs.data(), sizeof(double) * h_tabs.size(), cudaMemcpyHostToDevice, s));

@@ -179,6 +179,19 @@ FICP_API int ficp_stepper_fit_apply(ficp_stepper* s, int32_t allow_reflection, d
 FICP_API int ficp_stepper_read_xy(ficp_stepper* s, double* xy_out);
 FICP_API void ficp_stepper_destroy(ficp_stepper* s);
 
+/* ---- host-side plot geometry (no device needed).  What a caller of ficp_batch_create needs for thousands of plots without
+ * thousands of numpy calls; a few host threads over the plots (FICP_HOST_THREADS caps them, 1 = serial).
+ *   ficp_plot_centres    centres_out[2p..2p+1] = mean of columns 0,1 of plot p, rows added in order - the bits of
+ *                        `rows[:, :2].mean(axis=0)`, the point `Plot.rotate_plot` / `coordinate_flip` turn about
+ *                        (trees.py:201-222)
+ *   ficp_plot_geometry   the pass ficp_batch_create itself makes over the rows (exported so that it can be checked without a
+ *                        GPU): u_out [rows*2] = row - centre, z_out [rows] (use_z), ubar_out [n_plots*2] = mean of u,
+ *                        rho_out [n_plots] >= max |u - ubar| (sizes the on-chip window only).  -2 on a non-finite coordinate. */
+FICP_API int ficp_plot_centres(const double* src_host, int32_t ld, const int64_t* plot_offsets, int64_t n_plots,
+                      double* centres_out);
+FICP_API int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_z, const int64_t* plot_offsets, int64_t n_plots,
+                      const double* centres, double* u_out, double* z_out, double* ubar_out, double* rho_out);
+
 /* ---- kernel 4: persistent batched ICP.  Replaces _iterate()/run() (ficp.py:122-154), batched over
  * plots and start-pose hypotheses.
  *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1])

@@ -98,6 +98,58 @@ def test_plot_centres_vectorised_is_bit_identical():
             np.testing.assert_array_equal(plot_centres(src, off), want)
 
 
+def _plot_geometry(src, off, cen, use_z):
+    import ctypes as C
+    from coregistrationgame_b200 import _lib
+    rows, n_plots = src.shape[0], off.shape[0] - 1
+    u, z = np.full((rows, 2), np.nan), np.full(rows, np.nan)
+    ubar, rho = np.full((n_plots, 2), np.nan), np.full(n_plots, np.nan)
+    rc = _lib.load().ficp_plot_geometry(_lib.ptr(src), src.shape[1], int(use_z), _lib.ptr(off), n_plots, _lib.ptr(cen),
+                                        _lib.ptr(u), _lib.ptr(z) if use_z else None, _lib.ptr(ubar), _lib.ptr(rho))
+    return rc, u, z, ubar, rho
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_plot_geometry_pass_of_batch_create(threads, monkeypatch):
+    """The host pass ficp_batch_create makes over the rows (csrc/batch_prep.h; a few threads over the plots): local
+    coordinates are the oracle's single subtraction `row - centre` bit for bit (oracle.pre_transform), the shift point is
+    the in-order mean of them, and the radius covers every tree - with any number of host threads, for ragged plots."""
+    monkeypatch.setenv("FICP_HOST_THREADS", threads)
+    from coregistrationgame_b200.batch import plot_centres
+    rng = np.random.default_rng(int(threads))
+    for ld, use_z, sizes in ((3, True, np.full(1250, 150)), (2, False, rng.integers(1, 300, 900)), (5, True, rng.integers(1, 1025, 400)),
+                             (3, True, np.array([1])), (3, False, np.array([1, 1024, 1, 7]))):
+        srcs = [rng.normal(size=(int(n), ld)) * 300 + np.r_[5.3e5, 6.48e6, np.zeros(ld - 2)] for n in sizes]
+        src = np.ascontiguousarray(np.vstack(srcs))
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        cen = plot_centres(src, off)
+        np.testing.assert_array_equal(cen, np.array([a[:, :2].mean(axis=0) for a in srcs]))
+        rc, u, z, ubar, rho = _plot_geometry(src, off, cen, use_z)
+        assert rc == 0
+        np.testing.assert_array_equal(u, src[:, :2] - np.repeat(cen, sizes, axis=0))
+        if use_z:
+            np.testing.assert_array_equal(z, src[:, 2])
+        for p in (0, len(sizes) // 2, len(sizes) - 1):
+            up = u[off[p]:off[p + 1]]
+            sx = sy = 0.0
+            for a, b in up:
+                sx += a
+                sy += b
+            assert (ubar[p, 0], ubar[p, 1]) == (sx / len(up), sy / len(up))
+        far = np.array([np.hypot(*(u[off[p]:off[p + 1]] - ubar[p]).T).max() for p in range(len(sizes))])
+        assert (rho >= far).all() and (rho <= far * (1 + 1e-14) + 1e-300).all()
+    # a non-finite matched coordinate anywhere -> status -2 ('x' must be finite, ficp.py:70 via scipy); unmatched columns may hold anything
+    src = rng.normal(size=(70000, 4))
+    off = np.arange(0, 70001, 100).astype(np.int64)
+    cen = plot_centres(src, off)
+    src[:, 3] = np.nan
+    assert _plot_geometry(src, off, cen, True)[0] == 0
+    for (r, c), use_z, want in (((69999, 2), True, -2), ((69999, 2), False, 0), ((12345, 0), False, -2), ((40000, 1), True, -2)):
+        bad = src.copy()
+        bad[r, c] = np.inf if c else np.nan
+        assert _plot_geometry(bad, off, cen, use_z)[0] == want
+
+
 def test_host_helpers_match_oracle():
     from coregistrationgame_b200 import batch
     np.testing.assert_array_equal(batch.hypothesis_table(16, (0, 1), batch.translation_lattice(3, 2.5)),
