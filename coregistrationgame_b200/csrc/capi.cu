@@ -62,6 +62,56 @@ void dev_free(void* p, cudaStream_t stream) {
     if (p) cudaFreeAsync(p, stream);
 }
 
+// Page-locked staging blocks for the host->device copies of ficp_batch_create: the rows are written once (u = p - centre)
+// and leave by DMA from where they were written, instead of from pageable memory through the driver's own staging copy.
+// Blocks are kept for the life of the process (a handful: one per concurrent caller) and handed out under a mutex; a block
+// is returned only after the stream that read it has been synchronised.  Above 256 MB, or when pinning fails, the caller
+// gets ordinary heap memory.
+namespace {
+struct StageBlock { void* p; size_t cap; };
+std::mutex g_stage_mu;
+std::vector<StageBlock> g_stage_free;
+}  // namespace
+struct HostStage {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    cudaStream_t pending_on = nullptr;
+    bool pending = false;
+    explicit HostStage(size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        if (bytes <= ((size_t)256 << 20)) {
+            {
+                std::lock_guard<std::mutex> lk(g_stage_mu);
+                for (size_t i = 0; i < g_stage_free.size(); ++i)
+                    if (g_stage_free[i].cap >= bytes) {
+                        p = g_stage_free[i].p; cap = g_stage_free[i].cap; pinned = true;
+                        g_stage_free.erase(g_stage_free.begin() + (long)i);
+                        break;
+                    }
+                if (!p && !g_stage_free.empty()) {   // too small: replace the largest kept block instead of hoarding
+                    cudaFreeHost(g_stage_free.back().p);
+                    g_stage_free.pop_back();
+                }
+            }
+            if (!p) {
+                const size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 20);
+                if (cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess) { cap = want; pinned = true; }
+                else { cudaGetLastError(); p = nullptr; }
+            }
+        }
+        if (!p) { p = ::operator new(bytes); cap = bytes; pinned = false; }
+    }
+    ~HostStage() {
+        if (pending) cudaStreamSynchronize(pending_on);   // an early error return: the copies may still be reading
+        if (!pinned) { ::operator delete(p); return; }
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        g_stage_free.push_back({p, cap});
+    }
+    HostStage(const HostStage&) = delete;
+    HostStage& operator=(const HostStage&) = delete;
+};
+
 static_assert(sizeof(ficp_hyp_result) == sizeof(HypResult), "ABI struct mismatch");
 static_assert(FICP_PACK_WORDS == kPackWords, "ABI constant mismatch");
 
@@ -620,10 +670,12 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // ---- per-plot geometry: local coordinates u = p - centre, shift point, footprint of the start poses
     // (batch_prep.h: a few host threads over the plots - with one ICP per plot this pass is the end-to-end step)
     std::vector<PlotMeta> plots((size_t)n_plots);
-    std::unique_ptr<double[]> h_u(new double[2 * (size_t)rows]);          // (ux, uy) per row = the device's double2
-    std::unique_ptr<double[]> h_z(z3 ? new double[(size_t)rows] : nullptr);
-    std::unique_ptr<double[]> h_ubar(new double[2 * (size_t)n_plots]), h_rho(new double[(size_t)n_plots]);
-    if (!plot_geometry_host(src_host, ld, z3, plot_offsets, n_plots, centres, h_u.get(), h_z.get(), h_ubar.get(), h_rho.get(),
+    HostStage stage(sizeof(double) * ((size_t)rows * (z3 ? 3 : 2) + 3 * (size_t)n_plots));
+    double* const h_u = static_cast<double*>(stage.p);                    // (ux, uy) per row = the device's double2
+    double* const h_z = z3 ? h_u + 2 * (size_t)rows : nullptr;
+    double* const h_ubar = h_u + (size_t)rows * (z3 ? 3 : 2);
+    double* const h_rho = h_ubar + 2 * (size_t)n_plots;
+    if (!plot_geometry_host(src_host, ld, z3, plot_offsets, n_plots, centres, h_u, h_z, h_ubar, h_rho,
                             host_threads_for(rows))) {
         set_error("source contains non-finite coordinates ('x' must be finite)");
         return kErrNonFinite;
@@ -821,12 +873,14 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_k), sizeof(int) * recs, s));
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_f), sizeof(double) * recs, s));
     }
-    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u.get(), sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
-    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z.get(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    stage.pending_on = s; stage.pending = true;
+    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u, sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
+    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z, sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * 6 * (size_t)n_hyp, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_tabs, h_tabs.data(), sizeof(double) * h_tabs.size(), cudaMemcpyHostToDevice, s));
-    FICP_CUDA(cudaStreamSynchronize(s));  // the staging vectors go out of scope below
+    FICP_CUDA(cudaStreamSynchronize(s));  // the staging block and vectors go out of scope below
+    stage.pending = false;
 
     IcpParams& P = b->params;
     P.grid = t->view;
