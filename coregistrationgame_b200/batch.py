@@ -62,6 +62,37 @@ def plot_centres(src, offsets):
     return out
 
 
+def stack_plots(sources):
+    """Plots as ONE C-contiguous float64 array + offsets + sizes (plot p owns ``rows[offsets[p]:offsets[p + 1]]``).
+
+    ``sources``: a list of (N_p, D) arrays, one (N, D) array (a single plot), or - the form for thousands of plots, where
+    the per-plot Python work of a list is what bounds config 4 end to end - a tuple ``(rows, offsets)`` already stacked."""
+    if isinstance(sources, tuple) and len(sources) == 2 and isinstance(sources[0], np.ndarray) and sources[0].ndim == 2 \
+            and np.ndim(sources[1]) == 1:
+        rows, offs = sources
+        src = np.ascontiguousarray(np.asarray(rows, dtype=np.float64))
+        offsets = np.ascontiguousarray(np.asarray(offs, dtype=np.int64))
+        sizes = np.diff(offsets)
+        if offsets.size < 2 or offsets[0] != 0 or offsets[-1] != src.shape[0] or (sizes <= 0).any():
+            raise ValueError("offsets must start at 0, end at the number of rows and describe non-empty plots")
+        return src, offsets, sizes
+    if isinstance(sources, np.ndarray) and sources.ndim == 2:
+        sources = [sources]
+    srcs = list(sources)
+    if not all(type(s) is np.ndarray and s.dtype == np.float64 for s in srcs):
+        srcs = [np.asarray(s, dtype=np.float64) for s in srcs]
+    if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
+        raise ValueError("every plot must be a non-empty 2D array (N, D)")
+    sizes = np.fromiter(map(len, srcs), dtype=np.int64, count=len(srcs))
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    try:
+        # one copy; checks the column counts itself (Fortran-ordered plots give a Fortran-ordered stack: made C after)
+        src = np.ascontiguousarray(np.concatenate(srcs, axis=0))
+    except ValueError:
+        raise ValueError("all plots must have the same number of columns") from None
+    return src, offsets, sizes
+
+
 def frmsd_weights(n, lam):
     """w[k-1] = 1/((k/n)**lam) with Python-float semantics - the very expression of ficp.py:60,81,
     so the table is bit-identical to what the reference multiplies with."""
@@ -164,32 +195,8 @@ class IcpBatch:
                  hyp_shard=(0, 1), want_final_xy=False, window_margin=-1.0, warps_per_cta=0, ctas_per_sm=0,
                  disable_window=False, team_warps=0, helpers=None, trace_passes=0, cta_per_icp=None, stream=None):
         lib = _lib.load()
-        if isinstance(sources, tuple) and len(sources) == 2 and isinstance(sources[0], np.ndarray) and sources[0].ndim == 2 \
-                and np.ndim(sources[1]) == 1:
-            # already stacked: (rows, offsets) - plot p owns rows[offsets[p]:offsets[p + 1]].  The form for thousands of plots:
-            # per-plot Python work (a list of 1250 arrays costs ~3 ms to check and stack) is what bounds config 4 end to end
-            rows, offs = sources
-            self.src = np.ascontiguousarray(np.asarray(rows, dtype=np.float64))
-            self.offsets = np.ascontiguousarray(np.asarray(offs, dtype=np.int64))
-            self.sizes = np.diff(self.offsets)
-            if self.offsets.size < 2 or self.offsets[0] != 0 or self.offsets[-1] != self.src.shape[0] or (self.sizes <= 0).any():
-                raise ValueError("offsets must start at 0, end at the number of rows and describe non-empty plots")
-            ld = self.src.shape[1]
-        else:
-            if isinstance(sources, np.ndarray) and sources.ndim == 2:
-                sources = [sources]
-            srcs = list(sources)
-            if not all(type(s) is np.ndarray and s.dtype == np.float64 for s in srcs):
-                srcs = [np.asarray(s, dtype=np.float64) for s in srcs]
-            if not srcs or any(s.ndim != 2 or s.shape[0] == 0 for s in srcs):
-                raise ValueError("every plot must be a non-empty 2D array (N, D)")
-            ld = srcs[0].shape[1]
-            self.sizes = np.fromiter(map(len, srcs), dtype=np.int64, count=len(srcs))
-            self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
-            try:
-                self.src = np.concatenate(srcs, axis=0)     # one C-contiguous copy; checks the column counts itself
-            except ValueError:
-                raise ValueError("all plots must have the same number of columns") from None
+        self.src, self.offsets, self.sizes = stack_plots(sources)
+        ld = self.src.shape[1]
         self.index = index
         self.match_dims = 3 if (ld >= 3 and index.has_z) else 2
         self.n_plots = int(self.sizes.shape[0])

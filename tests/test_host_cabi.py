@@ -150,6 +150,29 @@ def test_plot_geometry_pass_of_batch_create(threads, monkeypatch):
         assert _plot_geometry(bad, off, cen, use_z)[0] == want
 
 
+def test_stack_plots_forms_and_errors():
+    """The three input forms of register_batch / IcpBatch give the same C-contiguous stack - also for Fortran-ordered,
+    sliced, integer and list-of-lists plots (np.concatenate keeps Fortran order: the real Data/2014 arrays come that way)."""
+    from coregistrationgame_b200.batch import stack_plots
+    rng = np.random.default_rng(5)
+    base = [rng.normal(size=(n, 3)) for n in (4, 1, 9)]
+    want = np.vstack(base)
+    for form in (base, [np.asfortranarray(a) for a in base], [np.hstack([a, a])[:, :3] for a in base], [a.tolist() for a in base],
+                 (want, np.array([0, 4, 5, 14])), (np.asfortranarray(want), [0, 4, 5, 14])):
+        src, off, sizes = stack_plots(form)
+        assert src.flags["C_CONTIGUOUS"] and src.dtype == np.float64 and off.dtype == np.int64
+        np.testing.assert_array_equal(src, want)
+        np.testing.assert_array_equal(off, [0, 4, 5, 14])
+        np.testing.assert_array_equal(sizes, [4, 1, 9])
+    src, off, sizes = stack_plots(np.arange(6).reshape(3, 2))          # one plot, integer input
+    assert src.dtype == np.float64 and off.tolist() == [0, 3] and sizes.tolist() == [3]
+    for bad, msg in (([], "non-empty"), ([base[0], np.empty((0, 3))], "non-empty"), ([base[0], np.zeros(3)], "non-empty"),
+                     ([base[0], np.zeros((2, 2))], "same number of columns"), ((want, np.array([0, 4, 4, 14])), "offsets"),
+                     ((want, np.array([1, 14])), "offsets"), ((want, np.array([0, 13])), "offsets")):
+        with pytest.raises(ValueError, match=msg):
+            stack_plots(bad)
+
+
 def test_host_helpers_match_oracle():
     from coregistrationgame_b200 import batch
     np.testing.assert_array_equal(batch.hypothesis_table(16, (0, 1), batch.translation_lattice(3, 2.5)),
