@@ -202,9 +202,10 @@ class IcpBatch:
         self.n_plots = int(self.sizes.shape[0])
         self.hyp = np.ascontiguousarray(IDENTITY_HYPOTHESIS if hyp_table is None else
                                         np.asarray(hyp_table, dtype=np.float64).reshape(-1, 6))
-        if centres is None:
-            centres = plot_centres(self.src, self.offsets)
-        self.centres = np.ascontiguousarray(np.asarray(centres, dtype=np.float64).reshape(self.n_plots, 2))
+        # centres=None: the library takes each plot's own centroid while it prepares the rows (ficp_batch_create with
+        # centres = NULL); the `centres` property computes the same bits on first use (winners-only callers never need them)
+        self._centres = None if centres is None else \
+            np.ascontiguousarray(np.asarray(centres, dtype=np.float64).reshape(self.n_plots, 2))
         self.n_stages = int(n_stages)
         lam2 = STAGE2_LAMBDA[self.match_dims] if stage2_lambda is None else stage2_lambda
         self.lambdas = [lambda_val, lam2][: self.n_stages]
@@ -230,7 +231,7 @@ class IcpBatch:
                                int(trace_passes), (0 if cta_per_icp is None else (2 if cta_per_icp else 1)), 0)
         self._h = C.c_void_p()
         _lib.check(lib.ficp_batch_create(index.handle, _lib.ptr(self.src), ld, int(self.match_dims == 3),
-                                         _lib.ptr(self.offsets), self.n_plots, _lib.ptr(self.centres),
+                                         _lib.ptr(self.offsets), self.n_plots, _lib.ptr(self._centres),
                                          _lib.ptr(self.hyp), self.hyp.shape[0], self.hyp_begin, self.hyp_stride,
                                          _lib.ptr(self.weights), _lib.ptr(self.weight_offsets),
                                          _lib.ptr(self.plot_tab), len(uniq), _lib.ptr(self.fixed_k), C.byref(prm),
@@ -242,7 +243,14 @@ class IcpBatch:
         self.n_hyp = self.hyp.shape[0]
         self.n_hyp_local = bi.n_hyp_local
         self.want_final_xy = bool(want_final_xy) and self.n_hyp_local == 1
-        self.h2d_bytes = int(self.src.nbytes + self.hyp.nbytes + self.centres.nbytes + self.weights.nbytes)
+        self.h2d_bytes = int(self.src.nbytes + self.hyp.nbytes + 16 * self.n_plots + self.weights.nbytes)
+
+    @property
+    def centres(self):
+        """(n_plots, 2) point the start poses of each plot turn about (given, or each plot's centroid)."""
+        if self._centres is None:
+            self._centres = plot_centres(self.src, self.offsets)
+        return self._centres
 
     def run(self, stream=None):
         _lib.check(_lib.load().ficp_batch_run(self._h, _stream_ptr(stream)), "ficp_batch_run")

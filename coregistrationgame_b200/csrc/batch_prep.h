@@ -8,8 +8,8 @@
 //   ubar    = (u_0 + ... + u_{n-1}) / n in row order (shift point of the fit sums)
 //   rho     >= max_i |u_i - ubar|   radius of the plot about ubar; only sizes the shared-memory window, never a result
 // Config 4 (1250 plots x 150 trees per GPU, one ICP each) spends 0.22 ms on the device per batch, so this pass is what an
-// end-to-end step costs: plots are independent -> a few host threads; rho from the largest SQUARED distance (one square
-// root per plot instead of one hypot per tree: 6.6 -> 1.3 ms single-threaded for 187 500 rows).
+// end-to-end step costs: rho from the largest SQUARED distance (one square root per plot instead of one hypot per tree:
+// 6.6 -> 1.0 ms for 187 500 rows in the build container); plots are independent, so large batches use a few host threads.
 #pragma once
 #include <algorithm>
 #include <atomic>
@@ -21,17 +21,20 @@
 
 namespace ficp {
 
-// threads for a host pass over `rows` source rows: one per 32 K rows, at most 4 (ranks of a multi-GPU job share the host),
-// FICP_HOST_THREADS overrides (1 = serial)
+// Threads for a host pass over `rows` source rows.  Measured on the B200 box (profiles/r02_c4_e2e_probe.jsonl: 187 500 rows,
+// ficp_batch_create as a whole): 1 thread 0.70 ms, 2 threads 0.68, 4 threads 0.90, 8 threads 0.97 - starting and joining a
+// thread costs as much as 50 K rows of the pass, so a thread is added per 512 K rows only, at most 4 (ranks of a multi-GPU
+// job share the host).  FICP_HOST_THREADS=n asks for up to n threads, one per 32 K rows (1 = always serial).
 inline int host_threads_for(long long rows) {
     int cap = 4;
+    long long rows_per_thread = 524288;
     if (const char* e = std::getenv("FICP_HOST_THREADS")) {
         const int v = std::atoi(e);
-        if (v >= 1) cap = std::min(v, 64);
+        if (v >= 1) { cap = std::min(v, 64); rows_per_thread = 32768; }
     }
     const unsigned hw = std::thread::hardware_concurrency();
     if (hw >= 1) cap = std::min<int>(cap, (int)hw);
-    return (int)std::max<long long>(1, std::min<long long>(cap, rows / 32768));
+    return (int)std::max<long long>(1, std::min<long long>(cap, rows / rows_per_thread));
 }
 
 // run fn(p_begin, p_end) over [0, n_plots) cut into contiguous ranges of roughly equal ROW count

@@ -616,7 +616,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
                       const int64_t* weight_offsets, const int32_t* plot_tab, int32_t n_tabs, const int32_t* fixed_k,
                       const ficp_batch_params* prm, int32_t want_final_xy, void* stream, ficp_batch** out) {
     if (out) *out = nullptr;
-    if (!th || !src_host || !plot_offsets || !centres || !hyp || !weights || !weight_offsets || !plot_tab || !prm || !out) {
+    if (!th || !src_host || !plot_offsets || !hyp || !weights || !weight_offsets || !plot_tab || !prm || !out) {
         set_error("ficp_batch_create: null pointer");
         return kErrInvalid;
     }
@@ -675,10 +675,37 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     double* const h_z = z3 ? h_u + 2 * (size_t)rows : nullptr;
     double* const h_ubar = h_u + (size_t)rows * (z3 ? 3 : 2);
     double* const h_rho = h_ubar + 2 * (size_t)n_plots;
-    if (!plot_geometry_host(src_host, ld, z3, plot_offsets, n_plots, centres, h_u, h_z, h_ubar, h_rho,
-                            host_threads_for(rows))) {
-        set_error("source contains non-finite coordinates ('x' must be finite)");
-        return kErrNonFinite;
+    // The rows leave for the device in up to four slices of plots, each as soon as it is written: the copy of one slice (DMA
+    // from the page-locked block) runs under the geometry pass of the next.
+    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows, s));
+    if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows, s));
+    // centres == NULL: every plot turns about the in-order mean of its first two columns (ficp_plot_centres: the bits of
+    // `rows[:, :2].mean(axis=0)`), taken here slice by slice right before the slice's geometry pass reads the same rows
+    std::vector<double> own_centres(centres ? 0 : 2 * (size_t)n_plots);
+    if (!centres) centres = own_centres.data();
+    {
+        const int n_slices_up = (stage.pinned && rows >= 65536) ? (int)std::min<int64_t>(4, n_plots) : 1;
+        int64_t p0 = 0;
+        for (int sl = 1; sl <= n_slices_up; ++sl) {
+            int64_t p1 = n_plots;
+            if (sl < n_slices_up) {
+                p1 = std::lower_bound(plot_offsets, plot_offsets + n_plots, rows * sl / n_slices_up) - plot_offsets;
+                p1 = std::max(p0, std::min(p1, n_plots));
+            }
+            if (p1 == p0) continue;
+            const long long r0 = plot_offsets[p0], r1 = plot_offsets[p1];
+            if (!own_centres.empty())
+                plot_centres_host(src_host, ld, plot_offsets + p0, p1 - p0, own_centres.data() + 2 * p0, host_threads_for(r1 - r0));
+            if (!plot_geometry_host(src_host, ld, z3, plot_offsets + p0, p1 - p0, centres + 2 * p0, h_u, h_z, h_ubar + 2 * p0, h_rho + p0,
+                                    host_threads_for(r1 - r0))) {
+                set_error("source contains non-finite coordinates ('x' must be finite)");
+                return kErrNonFinite;
+            }
+            stage.pending_on = s; stage.pending = true;
+            FICP_CUDA(cudaMemcpyAsync(b->d_src_u + r0, h_u + 2 * (size_t)r0, sizeof(double2) * (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
+            if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z + r0, h_z + (size_t)r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyHostToDevice, s));
+            p0 = p1;
+        }
     }
     struct Foot { double rho, fx0, fx1, fy0, fy1; };
     std::vector<Foot> foot((size_t)n_plots);
@@ -852,8 +879,6 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     }
 
     // ---- device buffers
-    FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows, s));
-    if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows, s));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_plots), sizeof(PlotMeta) * (size_t)n_plots, s));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_hyp), sizeof(double) * 6 * (size_t)n_hyp, s));
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tabs), sizeof(double) * h_tabs.size(), s));
@@ -873,9 +898,6 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_k), sizeof(int) * recs, s));
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_f), sizeof(double) * recs, s));
     }
-    stage.pending_on = s; stage.pending = true;
-    FICP_CUDA(cudaMemcpyAsync(b->d_src_u, h_u, sizeof(double2) * (size_t)rows, cudaMemcpyHostToDevice, s));
-    if (z3) FICP_CUDA(cudaMemcpyAsync(b->d_src_z, h_z, sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * 6 * (size_t)n_hyp, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_tabs, h_tabs.data(), sizeof(double) * h_tabs.size(), cudaMemcpyHostToDevice, s));

@@ -195,7 +195,8 @@ FICP_API int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_
 /* ---- kernel 4: persistent batched ICP.  Replaces _iterate()/run() (ficp.py:122-154), batched over
  * plots and start-pose hypotheses.
  *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1])
- *   centres         n_plots x 2: the point each hypothesis rotates about (trees.py:165-222)
+ *   centres         n_plots x 2: the point each hypothesis rotates about (trees.py:165-222); NULL = the mean of each plot's
+ *                   first two columns, rows added in order (what ficp_plot_centres returns)
  *   hyp             n_hyp x 6: m00 m01 m10 m11 dx dy ; start pose = M (p - centre) + centre + d
  *   hyp_begin/stride  this process runs hypotheses hyp_begin, hyp_begin+stride, ... (multi-GPU sharding)
  *   weights         for table t and stage s: weights[weight_offsets[t] + s*n_t + (k-1)] = 1/((k/n_t)**lambda_s)

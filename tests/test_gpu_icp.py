@@ -640,6 +640,34 @@ def test_stacked_input_equals_list_of_plots(gpu):
         register_batch((rows, np.r_[offs[:3], offs[2:]]), tgt, hyp)
 
 
+def test_library_centres_and_sliced_upload_equal_explicit_centres(gpu):
+    """ficp_batch_create with centres = NULL takes each plot's centroid itself (in-order mean, the bits of
+    `rows[:, :2].mean(axis=0)`) and, from 65 536 rows on, sends the rows to the device in slices while it prepares the next
+    one: the per-plot results equal those of a batch given the numpy centroids explicitly, bit for bit - for a batch below
+    and one above the slicing threshold (ragged sizes, UTM offsets, Fortran-ordered plots), with 1 and 3 host threads."""
+    from coregistrationgame_b200 import IcpBatch, TargetIndex
+    tgt, plots, _ = orc.synthetic_scene(60000, 160, seed=21, dims=3, n_plots=520, hidden_pose=False)
+    tgt = tgt + [420000.0, 6483000.0, 0.0]
+    plots = [np.asfortranarray(p[: 100 + (i * 7) % 61] + [420000.0, 6483000.0, 0.0]) for i, p in enumerate(plots)]
+    ti = TargetIndex(tgt)
+    for ps in (plots[:40], plots):                                       # 5 k rows (one slice) / 67 k rows (four slices)
+        assert (sum(len(p) for p in ps) >= 65536) == (len(ps) > 40)
+        cen = np.array([np.ascontiguousarray(p)[:, :2].mean(axis=0) for p in ps])
+        want = IcpBatch(ti, ps, None, centres=cen, min_k=0).run().results()
+        for threads in ("1", "3"):
+            os.environ["FICP_HOST_THREADS"] = threads
+            try:
+                b = IcpBatch(ti, ps, None, min_k=0)
+                got = b.run().results()
+                np.testing.assert_array_equal(b.centres, cen)
+            finally:
+                del os.environ["FICP_HOST_THREADS"]
+            np.testing.assert_array_equal(got["best_key"], want["best_key"])
+            assert _rows_equal_except_flags(got["hyp"], want["hyp"])
+            assert got["stats"]["passes"] == want["stats"]["passes"]
+    ti.close()
+
+
 def test_planner_picks_the_kernel_shape_by_batch_size(gpu):
     """Auto launch shape (capi.cu): CTA-per-ICP up to 14 ICPs per SM, warp-per-ICP above; plots of <= 32 trees are one warp
     either way."""
