@@ -36,7 +36,7 @@ class BatchInfo(C.Structure):
                 ("match_z", c_i32), ("warps_per_cta", c_i32), ("ctas", c_i32), ("ctas_per_sm", c_i32),
                 ("slices_per_plot", c_i32), ("window_pts_cap", c_i32), ("window_cells_cap", c_i32),
                 ("team_warps", c_i32), ("helpers", c_i32), ("trace_passes", c_i32), ("smem_bytes", c_i64), ("rows", c_i64),
-                ("trace_stride", c_i32), ("cta_per_icp", c_i32)]
+                ("trace_stride", c_i32), ("cta_per_icp", c_i32), ("rows_direct", c_i32), ("reserved", c_i32)]
 
 
 # numpy view of ficp_hyp_result

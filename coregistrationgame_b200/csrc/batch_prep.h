@@ -74,7 +74,8 @@ inline void plot_centres_host(const double* src, int ld, const int64_t* offsets,
 }
 
 // u (2 doubles per row), z (1 per row, when z3), ubar (2 per plot), rho (1 per plot).  Returns false when a matched
-// coordinate is not finite (the reference raises in scipy: "'x' must be finite", ficp.py:70).
+// coordinate is not finite (the reference raises in scipy: "'x' must be finite", ficp.py:70).  u == nullptr: the per-plot
+// values only, nothing is written per row (ficp_batch_create when the device splits the rows itself) - a read-only pass.
 inline bool plot_geometry_host(const double* src, int ld, bool z3, const int64_t* offsets, int64_t n_plots, const double* centres,
                                double* u, double* z, double* ubar, double* rho, int threads) {
     std::atomic<bool> finite{true};
@@ -90,9 +91,11 @@ inline bool plot_geometry_host(const double* src, int ld, bool z3, const int64_t
                 const double probe = (r[0] - r[0]) + (r[1] - r[1]) + (z3 ? (r[2] - r[2]) : 0.0);
                 ok &= (probe == 0.0);
                 const double ux = r[0] - cx, uy = r[1] - cy;   // same single subtraction as the oracle
-                u[2 * (size_t)(off + i)] = ux;
-                u[2 * (size_t)(off + i) + 1] = uy;
-                if (z3) z[(size_t)(off + i)] = r[2];
+                if (u) {
+                    u[2 * (size_t)(off + i)] = ux;
+                    u[2 * (size_t)(off + i) + 1] = uy;
+                    if (z3) z[(size_t)(off + i)] = r[2];
+                }
                 sx += ux;
                 sy += uy;
             }
@@ -101,7 +104,8 @@ inline bool plot_geometry_host(const double* src, int ld, bool z3, const int64_t
             ubar[2 * p + 1] = by;
             double m2 = 0.0;
             for (long long i = 0; i < n; ++i) {
-                const double a = u[2 * (size_t)(off + i)] - bx, b = u[2 * (size_t)(off + i) + 1] - by;
+                const double* r = src + (size_t)(off + i) * ld;       // the plot's rows are in L1 from the loop above
+                const double a = (r[0] - cx) - bx, b = (r[1] - cy) - by;
                 m2 = std::max(m2, a * a + b * b);
             }
             // rounded up: two roundings in a*a + b*b, one in sqrt - a radius that is never below any tree's distance

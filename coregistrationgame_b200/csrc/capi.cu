@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -136,6 +137,7 @@ struct Batch {
     long long rows = 0;
     bool z3 = false;
     bool want_final = false;
+    bool rows_direct = false;   // the rows went to the device as the caller holds them and were split there
     IcpParams params{};
     IcpLaunch launch{};
     int ctas_per_sm = 0;
@@ -595,7 +597,7 @@ int ficp_plot_centres(const double* src_host, int32_t ld, const int64_t* plot_of
 
 int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_z, const int64_t* plot_offsets, int64_t n_plots,
                        const double* centres, double* u_out, double* z_out, double* ubar_out, double* rho_out) {
-    if (!src_host || !plot_offsets || !centres || !u_out || !ubar_out || !rho_out || (use_z && !z_out) || ld < 2 || (use_z && ld < 3)) {
+    if (!src_host || !plot_offsets || !centres || !ubar_out || !rho_out || (u_out && use_z && !z_out) || ld < 2 || (use_z && ld < 3)) {
         set_error("ficp_plot_geometry: null pointer or too few columns");
         return kErrInvalid;
     }
@@ -670,20 +672,41 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
     // ---- per-plot geometry: local coordinates u = p - centre, shift point, footprint of the start poses
     // (batch_prep.h: a few host threads over the plots - with one ICP per plot this pass is the end-to-end step)
     std::vector<PlotMeta> plots((size_t)n_plots);
-    HostStage stage(sizeof(double) * ((size_t)rows * (z3 ? 3 : 2) + 3 * (size_t)n_plots));
-    double* const h_u = static_cast<double*>(stage.p);                    // (ux, uy) per row = the device's double2
-    double* const h_z = z3 ? h_u + 2 * (size_t)rows : nullptr;
-    double* const h_ubar = h_u + (size_t)rows * (z3 ? 3 : 2);
+    // Two routes for the rows.  (a) The caller's array is page-locked (a torch pinned tensor, cudaHostRegister'ed memory) and
+    // narrow: it goes to the device AS IT IS - one DMA, started before the host pass below and running under it - and a small
+    // kernel splits it into u = (x, y) - centre and z (launch_split_rows: the same single subtraction, the same bits); the host
+    // only READS the rows once (centres, shift points, radii, finiteness).  (b) Otherwise the host writes u and z into a
+    // page-locked block of the library and that block is copied, in up to four slices of plots, each as soon as it is written.
+    // FICP_HOST_STAGING=1 forces (b) (tests compare the two).
+    bool direct = false;
+    if (ld <= 4 && !std::getenv("FICP_HOST_STAGING")) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src_host) == cudaSuccess) direct = (at.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    const size_t per_row = direct ? 0 : (z3 ? 3 : 2);
+    HostStage stage(sizeof(double) * ((size_t)rows * per_row + 3 * (size_t)n_plots));
+    double* const h_u = direct ? nullptr : static_cast<double*>(stage.p);   // (ux, uy) per row = the device's double2
+    double* const h_z = (!direct && z3) ? h_u + 2 * (size_t)rows : nullptr;
+    double* const h_ubar = static_cast<double*>(stage.p) + (size_t)rows * per_row;
     double* const h_rho = h_ubar + 2 * (size_t)n_plots;
-    // The rows leave for the device in up to four slices of plots, each as soon as it is written: the copy of one slice (DMA
-    // from the page-locked block) runs under the geometry pass of the next.
     FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_u), sizeof(double2) * (size_t)rows, s));
     if (z3) FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_src_z), sizeof(double) * (size_t)rows, s));
+    DevBuf<double> d_raw(s);
     // centres == NULL: every plot turns about the in-order mean of its first two columns (ficp_plot_centres: the bits of
-    // `rows[:, :2].mean(axis=0)`), taken here slice by slice right before the slice's geometry pass reads the same rows
+    // `rows[:, :2].mean(axis=0)`), taken here right before the geometry pass reads the same rows
     std::vector<double> own_centres(centres ? 0 : 2 * (size_t)n_plots);
     if (!centres) centres = own_centres.data();
-    {
+    if (direct) {
+        if (int rc = d_raw.alloc((size_t)rows * ld)) return rc;
+        stage.pending_on = s; stage.pending = true;   // from here on the stream reads the CALLER's array: never return before it is done
+        FICP_CUDA(cudaMemcpyAsync(d_raw.p, src_host, sizeof(double) * (size_t)rows * ld, cudaMemcpyHostToDevice, s));
+        if (!own_centres.empty()) plot_centres_host(src_host, ld, plot_offsets, n_plots, own_centres.data(), host_threads_for(rows));
+        if (!plot_geometry_host(src_host, ld, z3, plot_offsets, n_plots, centres, nullptr, nullptr, h_ubar, h_rho, host_threads_for(rows))) {
+            set_error("source contains non-finite coordinates ('x' must be finite)");
+            return kErrNonFinite;
+        }
+    } else {
         const int n_slices_up = (stage.pinned && rows >= 65536) ? (int)std::min<int64_t>(4, n_plots) : 1;
         int64_t p0 = 0;
         for (int sl = 1; sl <= n_slices_up; ++sl) {
@@ -707,6 +730,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
             p0 = p1;
         }
     }
+    b->rows_direct = direct;
     struct Foot { double rho, fx0, fx1, fy0, fy1; };
     std::vector<Foot> foot((size_t)n_plots);
     for (int64_t p = 0; p < n_plots; ++p) {
@@ -899,6 +923,7 @@ int ficp_batch_create(const ficp_target* th, const double* src_host, int32_t ld,
         FICP_CUDA(dev_alloc(reinterpret_cast<void**>(&b->d_tr_f), sizeof(double) * recs, s));
     }
     FICP_CUDA(cudaMemcpyAsync(b->d_plots, plots.data(), sizeof(PlotMeta) * (size_t)n_plots, cudaMemcpyHostToDevice, s));
+    if (direct) { if (int rc = launch_split_rows(d_raw.p, ld, b->d_plots, (int)n_plots, z3, b->d_src_u, b->d_src_z, s)) return rc; }
     FICP_CUDA(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * 6 * (size_t)n_hyp, cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaMemcpyAsync(b->d_tabs, h_tabs.data(), sizeof(double) * h_tabs.size(), cudaMemcpyHostToDevice, s));
     FICP_CUDA(cudaStreamSynchronize(s));  // the staging block and vectors go out of scope below
@@ -937,6 +962,7 @@ int ficp_batch_get_info(const ficp_batch* bh, ficp_batch_info* info) {
     info->window_pts_cap = b->params.wcap_pts; info->window_cells_cap = b->params.wcap_cells; info->team_warps = b->launch.warps / b->launch.slots; info->helpers = b->launch.elastic ? 1 : 0;
     info->smem_bytes = (int64_t)b->launch.smem; info->rows = b->rows;
     info->trace_passes = b->trace_cap; info->trace_stride = b->trace_stride; info->cta_per_icp = b->launch.cta_per_icp ? 1 : 0;
+    info->rows_direct = b->rows_direct ? 1 : 0; info->reserved = 0;
     return kOk;
 }
 

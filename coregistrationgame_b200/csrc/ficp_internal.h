@@ -193,4 +193,7 @@ int launch_pack_best(const unsigned long long* d_best, const HypResult* d_result
                      int n_hyp_local, int hyp_begin, int hyp_stride, const unsigned long long* d_stats,
                      unsigned long long* d_dst, cudaStream_t stream);
 
+int launch_split_rows(const double* d_raw, int ld, const PlotMeta* d_plots, int n_plots, bool z3, double2* d_u, double* d_z,
+                      cudaStream_t stream);
+
 }  // namespace ficp

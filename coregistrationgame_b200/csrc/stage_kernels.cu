@@ -359,6 +359,34 @@ __global__ void __launch_bounds__(256) pack_best_kernel(const unsigned long long
 
 }  // namespace
 
+// Raw plot rows (as the caller holds them: `ld` doubles per row) -> the batch's layout: u = (x, y) - centre of the row's plot
+// as double2, z apart.  One warp per plot; the subtraction is the single IEEE operation the host pass of batch_prep.h (and the
+// oracle's pre_transform) performs, so both routes give the same bits.
+namespace {
+template <bool Z3>
+__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ raw, int ld, const PlotMeta* __restrict__ plots,
+                                                         int n_plots, double2* __restrict__ u, double* __restrict__ z) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_plots) return;
+    const PlotMeta pm = plots[p];
+    for (int i = threadIdx.x & 31; i < pm.n; i += 32) {
+        const double* r = raw + (size_t)(pm.off + i) * ld;
+        u[pm.off + i] = make_double2(r[0] - pm.cinx, r[1] - pm.ciny);
+        if (Z3) z[pm.off + i] = r[2];
+    }
+}
+}  // namespace
+
+int launch_split_rows(const double* d_raw, int ld, const PlotMeta* d_plots, int n_plots, bool z3, double2* d_u, double* d_z,
+                      cudaStream_t stream) {
+    if (n_plots <= 0) return kOk;
+    const int blocks = (n_plots + 7) / 8;
+    if (z3) split_rows_kernel<true><<<blocks, 256, 0, stream>>>(d_raw, ld, d_plots, n_plots, d_u, d_z);
+    else split_rows_kernel<false><<<blocks, 256, 0, stream>>>(d_raw, ld, d_plots, n_plots, d_u, d_z);
+    FICP_CUDA(cudaGetLastError());
+    return kOk;
+}
+
 int launch_pack_best(const unsigned long long* d_best, const HypResult* d_results, const PlotMeta* d_plots, int n_plots,
                      int n_hyp_local, int hyp_begin, int hyp_stride, const unsigned long long* d_stats,
                      unsigned long long* d_dst, cudaStream_t stream) {

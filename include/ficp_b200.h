@@ -93,6 +93,8 @@ typedef struct {
     int64_t rows;
     int32_t trace_stride;      /* entries per pass record of ficp_batch_trace */
     int32_t cta_per_icp;       /* 1 = the CTA-per-ICP kernel was chosen */
+    int32_t rows_direct;       /* 1 = src_host was page-locked: uploaded as it is and split into (u, z) on the device */
+    int32_t reserved;
 } ficp_batch_info;
 
 FICP_API const char* ficp_last_error(void);
@@ -186,7 +188,8 @@ FICP_API void ficp_stepper_destroy(ficp_stepper* s);
  *                        (trees.py:201-222)
  *   ficp_plot_geometry   the pass ficp_batch_create itself makes over the rows (exported so that it can be checked without a
  *                        GPU): u_out [rows*2] = row - centre, z_out [rows] (use_z), ubar_out [n_plots*2] = mean of u,
- *                        rho_out [n_plots] >= max |u - ubar| (sizes the on-chip window only).  -2 on a non-finite coordinate. */
+ *                        rho_out [n_plots] >= max |u - ubar| (sizes the on-chip window only).  -2 on a non-finite coordinate.
+ *                        u_out = NULL: the per-plot values only (the read-only pass of the page-locked route). */
 FICP_API int ficp_plot_centres(const double* src_host, int32_t ld, const int64_t* plot_offsets, int64_t n_plots,
                       double* centres_out);
 FICP_API int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_z, const int64_t* plot_offsets, int64_t n_plots,
@@ -194,7 +197,9 @@ FICP_API int ficp_plot_geometry(const double* src_host, int32_t ld, int32_t use_
 
 /* ---- kernel 4: persistent batched ICP.  Replaces _iterate()/run() (ficp.py:122-154), batched over
  * plots and start-pose hypotheses.
- *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1])
+ *   src_host        concatenated plot rows; plot p owns rows [plot_offsets[p], plot_offsets[p+1]).  Page-locked memory
+ *                   (cudaHostAlloc / cudaHostRegister, a torch pinned tensor) with ld <= 4 is sent by one DMA as it is and
+ *                   split on the device; anything else is staged through a page-locked block of the library - same results
  *   centres         n_plots x 2: the point each hypothesis rotates about (trees.py:165-222); NULL = the mean of each plot's
  *                   first two columns, rows added in order (what ficp_plot_centres returns)
  *   hyp             n_hyp x 6: m00 m01 m10 m11 dx dy ; start pose = M (p - centre) + centre + d

@@ -665,6 +665,34 @@ def test_library_centres_and_sliced_upload_equal_explicit_centres(gpu):
             np.testing.assert_array_equal(got["best_key"], want["best_key"])
             assert _rows_equal_except_flags(got["hyp"], want["hyp"])
             assert got["stats"]["passes"] == want["stats"]["passes"]
+            assert b.info["rows_direct"] == 0                            # pageable numpy memory: staged by the library
+        # page-locked rows (a torch pinned tensor) go to the device as they are and are split there: same bits again;
+        # FICP_HOST_STAGING=1 sends the same array through the staging route
+        import torch
+        stacked = np.vstack([np.ascontiguousarray(p) for p in ps])
+        offs = np.concatenate([[0], np.cumsum([len(p) for p in ps])]).astype(np.int64)
+        for cols, md3 in ((3, True), (2, False), (4, True), (5, True)):
+            wide = np.hstack([stacked, stacked[:, :2]])[:, :cols] if cols > 3 else stacked[:, :cols]
+            pin = torch.empty(wide.shape, dtype=torch.float64, pin_memory=True).numpy()
+            pin[...] = wide
+            ref = want if md3 else IcpBatch(ti, (np.ascontiguousarray(wide), offs), None, min_k=0).run().results()
+            for staging in (False, True):
+                if staging:
+                    os.environ["FICP_HOST_STAGING"] = "1"
+                try:
+                    b = IcpBatch(ti, (pin, offs), None, min_k=0)
+                    got = b.run().results()
+                finally:
+                    os.environ.pop("FICP_HOST_STAGING", None)
+                assert b.info["rows_direct"] == (0 if (staging or cols > 4) else 1), (cols, staging, b.info)
+                np.testing.assert_array_equal(got["best_key"], ref["best_key"])
+                assert _rows_equal_except_flags(got["hyp"], ref["hyp"])
+                b.close()
+    with pytest.raises(ValueError, match="finite"):                      # the read-only host pass still refuses NaN rows
+        bad = torch.empty(stacked.shape, dtype=torch.float64, pin_memory=True).numpy()
+        bad[...] = stacked
+        bad[len(bad) // 2, 1] = np.nan
+        IcpBatch(ti, (bad, offs), None, min_k=0)
     ti.close()
 
 

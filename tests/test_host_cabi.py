@@ -37,7 +37,7 @@ def test_abi_struct_sizes():
     from coregistrationgame_b200 import _lib
     assert _lib.HYP_RESULT_DTYPE.itemsize == 80
     assert C.sizeof(_lib.BatchParams) == 64
-    assert C.sizeof(_lib.BatchInfo) == 80
+    assert C.sizeof(_lib.BatchInfo) == 88
     assert C.sizeof(_lib.TargetInfo) == 96
 
 
@@ -136,6 +136,13 @@ def test_plot_geometry_pass_of_batch_create(threads, monkeypatch):
                 sx += a
                 sy += b
             assert (ubar[p, 0], ubar[p, 1]) == (sx / len(up), sy / len(up))
+        # the read-only form (u_out = NULL: rows go to the device as they are) returns the same per-plot values
+        ubar2, rho2 = np.full_like(ubar, np.nan), np.full_like(rho, np.nan)
+        from coregistrationgame_b200 import _lib
+        assert _lib.load().ficp_plot_geometry(_lib.ptr(src), src.shape[1], int(use_z), _lib.ptr(off), len(sizes), _lib.ptr(cen),
+                                              None, None, _lib.ptr(ubar2), _lib.ptr(rho2)) == 0
+        np.testing.assert_array_equal(ubar2, ubar)
+        np.testing.assert_array_equal(rho2, rho)
         far = np.array([np.hypot(*(u[off[p]:off[p + 1]] - ubar[p]).T).max() for p in range(len(sizes))])
         assert (rho >= far).all() and (rho <= far * (1 + 1e-14) + 1e-300).all()
     # a non-finite matched coordinate anywhere -> status -2 ('x' must be finite, ficp.py:70 via scipy); unmatched columns may hold anything

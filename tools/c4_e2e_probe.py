@@ -1,6 +1,8 @@
 """Where an end-to-end step of config 4 goes (1250 plots x 150 trees, one ICP per plot, resident target index): wall clock
-around the parts of register_batch((rows, offsets), index=...), with 1 / 2 / 4 host threads in ficp_batch_create's geometry
-pass.  One JSON line per thread setting.  (GPU box only.)"""
+around the parts of register_batch((rows, offsets), index=...), for the stacked rows in pageable memory (staged by the library),
+in page-locked memory (uploaded as they are, split on the device) and in page-locked memory with FICP_HOST_STAGING=1.
+One JSON line per case.  PROBE_THREADS=1,2,4,8 sweeps FICP_HOST_THREADS on pageable rows instead (profiles/r02_c4_e2e_probe.jsonl).
+(GPU box only.)"""
 import json
 import os
 import sys
@@ -33,8 +35,19 @@ def main():
         clock["create_c"] += time.perf_counter() - t
         return rc
     lib.ficp_batch_create = timed_create
-    for threads in ("1", "2", "4", "8"):
-        os.environ["FICP_HOST_THREADS"] = threads
+    import torch
+    pinned = torch.empty(rows.shape, dtype=torch.float64, pin_memory=True).numpy()
+    pinned[...] = rows
+    pageable = rows
+    if os.environ.get("PROBE_THREADS"):
+        cases = [("pageable", pageable, {"FICP_HOST_THREADS": t}) for t in os.environ["PROBE_THREADS"].split(",")]
+    else:
+        cases = [("pageable", pageable, {}), ("pinned", pinned, {}), ("pinned, FICP_HOST_STAGING=1", pinned, {"FICP_HOST_STAGING": "1"})]
+    for what, rows, env in cases:
+        for k in ("FICP_HOST_THREADS", "FICP_HOST_STAGING"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        threads = env.get("FICP_HOST_THREADS", "0")
         acc = {k: 0.0 for k in ("init", "create_c", "run", "best", "close", "transform", "total")}
         passes = 0
         for rep in range(reps + 3):
@@ -57,7 +70,7 @@ def main():
                          ("transform", t5 - t4), ("total", t5 - t0)):
                 acc[k] += v
             passes += out["stats"]["passes"]
-        line = {"host_threads": int(threads), "points": points, "plots": n_plots, "trees": trees, "reps": reps,
+        line = {"rows_in": what, "rows_direct": int(b.info["rows_direct"]), "host_threads": int(threads), "points": points, "plots": n_plots, "trees": trees, "reps": reps,
                 "ms_per_step": {k: round(v / reps * 1e3, 4) for k, v in acc.items()},
                 "python_in_init_ms": round((acc["init"] - acc["create_c"]) / reps * 1e3, 4),
                 "hyp_iter_per_s": passes / acc["total"], "launch": {k: b.info[k] for k in ("cta_per_icp", "warps_per_cta", "n_ctas") if k in b.info}}
