@@ -6,7 +6,8 @@
 //             the reference-side callers and the oracle take as the point start poses rotate about (trees.py:201-222)
 //   u_i     = r_i - centre          one subtraction per coordinate, the oracle's `pre_transform` arithmetic
 //   ubar    = (u_0 + ... + u_{n-1}) / n in row order (shift point of the fit sums)
-//   rho     >= max_i |u_i - ubar|   radius of the plot about ubar; only sizes the shared-memory window, never a result
+//   rho     >= max_i |u_i - ubar|   radius of the plot about ubar (at most 1e-6 (rho + 1) above it); only sizes the shared-memory
+//                                   window, never a result
 // Config 4 (1250 plots x 150 trees per GPU, one ICP each) spends 0.22 ms on the device per batch, so this pass is what an
 // end-to-end step costs: rho from the largest SQUARED distance (one square root per plot instead of one hypot per tree:
 // 6.6 -> 1.0 ms for 187 500 rows in the build container); plots are independent, so large batches use a few host threads.
@@ -79,37 +80,55 @@ inline void plot_centres_host(const double* src, int ld, const int64_t* offsets,
 inline bool plot_geometry_host(const double* src, int ld, bool z3, const int64_t* offsets, int64_t n_plots, const double* centres,
                                double* u, double* z, double* ubar, double* rho, int threads) {
     std::atomic<bool> finite{true};
+    constexpr double kUp = 1.0 + 8.0 * 2.220446049250313e-16;   // covers the roundings of a*a + b*b and of the square root
     for_plot_ranges(offsets, n_plots, threads, [&](int64_t p0, int64_t p1) {
         bool ok = true;
         for (int64_t p = p0; p < p1; ++p) {
             const long long off = offsets[p], n = offsets[p + 1] - offsets[p];
             const double cx = centres[2 * p], cy = centres[2 * p + 1];
-            double sx = 0.0, sy = 0.0;
+            // One walk over the rows, four independent chains: the two in-order sums, the largest squared distance from the
+            // centre, and a finiteness witness for z.  A non-finite x or y needs no test of its own: it makes u = x - c
+            // non-finite, and a sum that has met an inf or a NaN never becomes finite again.
+            double sx = 0.0, sy = 0.0, zw = 0.0, m2c = 0.0;
             for (long long i = 0; i < n; ++i) {
                 const double* r = src + (size_t)(off + i) * ld;
-                // x - x is 0 for every finite x and NaN for inf / NaN: one test for the row
-                const double probe = (r[0] - r[0]) + (r[1] - r[1]) + (z3 ? (r[2] - r[2]) : 0.0);
-                ok &= (probe == 0.0);
                 const double ux = r[0] - cx, uy = r[1] - cy;   // same single subtraction as the oracle
                 if (u) {
                     u[2 * (size_t)(off + i)] = ux;
                     u[2 * (size_t)(off + i) + 1] = uy;
                     if (z3) z[(size_t)(off + i)] = r[2];
                 }
+                if (z3) zw += r[2] - r[2];                     // 0 for a finite z, NaN for inf / NaN
                 sx += ux;
                 sy += uy;
+                m2c = std::max(m2c, ux * ux + uy * uy);
+            }
+            if (!(((sx - sx) + (sy - sy)) + zw == 0.0)) {
+                // suspicious (a non-finite coordinate - or finite ones whose sum overflowed): the rows decide
+                for (long long i = 0; i < n; ++i) {
+                    const double* r = src + (size_t)(off + i) * ld;
+                    const double probe = (r[0] - r[0]) + (r[1] - r[1]) + (z3 ? (r[2] - r[2]) : 0.0);
+                    ok &= (probe == 0.0);
+                }
             }
             const double bx = sx / (double)n, by = sy / (double)n;
             ubar[2 * p] = bx;
             ubar[2 * p + 1] = by;
-            double m2 = 0.0;
-            for (long long i = 0; i < n; ++i) {
-                const double* r = src + (size_t)(off + i) * ld;       // the plot's rows are in L1 from the loop above
-                const double a = (r[0] - cx) - bx, b = (r[1] - cy) - by;
-                m2 = std::max(m2, a * a + b * b);
+            // radius about ubar, rounded up.  When the plot turns about its own centroid ubar is rounding noise and
+            // max |u| + |ubar| bounds it (triangle inequality) without a second walk; otherwise (a caller's centre far from
+            // the plot, e.g. the origin for FractionalICP.run) the distances from ubar are taken one by one.
+            const double rc = std::sqrt(m2c) * kUp, nb = std::sqrt(bx * bx + by * by) * kUp;
+            if (nb <= 1e-6 * (rc + 1.0)) {
+                rho[p] = (rc + nb) * kUp;
+            } else {
+                double m2 = 0.0;
+                for (long long i = 0; i < n; ++i) {
+                    const double* r = src + (size_t)(off + i) * ld;   // the plot's rows are in L1 from the walk above
+                    const double a = (r[0] - cx) - bx, b = (r[1] - cy) - by;
+                    m2 = std::max(m2, a * a + b * b);
+                }
+                rho[p] = std::sqrt(m2) * kUp;
             }
-            // rounded up: two roundings in a*a + b*b, one in sqrt - a radius that is never below any tree's distance
-            rho[p] = std::sqrt(m2) * (1.0 + 8.0 * 2.220446049250313e-16);
         }
         if (!ok) finite.store(false, std::memory_order_relaxed);
     });

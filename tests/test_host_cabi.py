@@ -144,7 +144,17 @@ def test_plot_geometry_pass_of_batch_create(threads, monkeypatch):
         np.testing.assert_array_equal(ubar2, ubar)
         np.testing.assert_array_equal(rho2, rho)
         far = np.array([np.hypot(*(u[off[p]:off[p + 1]] - ubar[p]).T).max() for p in range(len(sizes))])
-        assert (rho >= far).all() and (rho <= far * (1 + 1e-14) + 1e-300).all()
+        assert (rho >= far).all() and (rho <= far * (1 + 1e-14) + 2.1e-6 * (far + 1)).all()
+        # a caller's centre far from the plot (FractionalICP.run turns about the origin): the radius is still tight
+        zero = np.zeros_like(cen)
+        rc, u0, _, ubar0, rho0 = _plot_geometry(src, off, zero, use_z)
+        assert rc == 0
+        np.testing.assert_array_equal(u0, src[:, :2])
+        far0 = np.array([np.hypot(*(u0[off[p]:off[p + 1]] - ubar0[p]).T).max() for p in range(len(sizes))])
+        assert (rho0 >= far0).all() and (rho0 <= far0 * (1 + 1e-14) + 1e-300).all()
+    # finite coordinates whose SUM overflows are still finite input (the rows decide, not the sums)
+    big = np.full((4, 2), 1.7e308)
+    assert _plot_geometry(big, np.array([0, 4]), np.zeros((1, 2)), False)[0] == 0
     # a non-finite matched coordinate anywhere -> status -2 ('x' must be finite, ficp.py:70 via scipy); unmatched columns may hold anything
     src = rng.normal(size=(70000, 4))
     off = np.arange(0, 70001, 100).astype(np.int64)
