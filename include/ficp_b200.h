@@ -182,7 +182,8 @@ FICP_API int ficp_stepper_read_xy(ficp_stepper* s, double* xy_out);
 FICP_API void ficp_stepper_destroy(ficp_stepper* s);
 
 /* ---- host-side plot geometry (no device needed).  What a caller of ficp_batch_create needs for thousands of plots without
- * thousands of numpy calls; a few host threads over the plots (FICP_HOST_THREADS caps them, 1 = serial).
+ * thousands of numpy calls.  One thread up to 512 K rows (starting a thread costs as much as 50 K rows of the pass, measured), one
+ * more per further 512 K rows, at most 4; FICP_HOST_THREADS=n allows up to n threads, one per 32 K rows (1 = always serial).
  *   ficp_plot_centres    centres_out[2p..2p+1] = mean of columns 0,1 of plot p, rows added in order - the bits of
  *                        `rows[:, :2].mean(axis=0)`, the point `Plot.rotate_plot` / `coordinate_flip` turn about
  *                        (trees.py:201-222)
