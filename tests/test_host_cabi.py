@@ -231,6 +231,25 @@ def test_nn_search_host_check(tmp_path, flags):
     assert "mismatches=0" in out.stdout
 
 
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_batch_prep_host_check_under_sanitizers(tmp_path, sanitizer):
+    """csrc/batch_prep.h - the host walk over the plot rows that ficp_batch_create makes, incl. its thread fan-out and the
+    slice addressing of the staging route - compiled with g++ under ASan + UBSan and under TSan and compared with a plain
+    serial restatement (bit-exact centres, u, ubar; covering radius; non-finite rows refused) for 1 / 2 / 3 / 8 threads."""
+    exe = tmp_path / "batch_prep_check"
+    cmd = ["g++", "-O1", "-g", "-std=c++17", f"-fsanitize={sanitizer}", "-fno-sanitize-recover=all", "-pthread",
+           os.path.join(ROOT, "tests", "hostcheck", "batch_prep_check.cpp"), "-o", str(exe)]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0 and "sanitize" in built.stderr:
+        pytest.skip(f"this toolchain has no -fsanitize={sanitizer} runtime")
+    assert built.returncode == 0, built.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    if sanitizer == "thread" and "FATAL: ThreadSanitizer" in out.stderr and "mmap" in out.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory in this container")
+    assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
+    assert "cases ok" in out.stdout
+
+
 def test_bench_cli_parses_without_a_gpu():
     """`bench.py --help` must render (a stray '%' in a help string once broke argparse) and `--impl reference` must be
     importable on a box without CUDA (the reference arm never touches the GPU)."""
