@@ -216,12 +216,14 @@ def test_product_path_never_imports_the_oracle():
     assert "oracle" not in open(os.path.join(ROOT, "ficp.py")).read()
 
 
-@pytest.mark.parametrize("flags", [[], ["-DFICP_TIETEST_STREAM"], ["-DFICP_PRESCAN_OWN_CELL"]],
-                         ids=["product", "tietest-stream-variant", "prescan-experiment"])
+@pytest.mark.parametrize("flags", [[], ["-DFICP_TIETEST_STREAM"], ["-DFICP_PRESCAN_OWN_CELL"],
+                                   ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all"]],
+                         ids=["product", "tietest-stream-variant", "prescan-experiment", "product-under-asan-ubsan"])
 def test_nn_search_host_check(tmp_path, flags):
     """The grid NN search (ring/termination/tie logic, window + global accessors, streamed form with arbitrary
     seeds, runner-up and lower bound of the tracked form) is host-compilable: build it with g++ and compare 19 200
-    queries / 67 430 tracked searches (global and window accessor) against brute force.  Also for the experimental build flags kept in the source."""
+    queries / 67 430 tracked searches (global and window accessor) against brute force.  Also for the experimental build flags kept in the
+    source, and once under AddressSanitizer + UBSan (every window / cell-table / candidate index of the search stays in range)."""
     exe = tmp_path / "nn_check"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", *flags, "-I", os.path.join(ROOT, "coregistrationgame_b200", "csrc"),
                            "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "hostcheck", "nn_search_check.cpp"),
